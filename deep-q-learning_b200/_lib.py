@@ -1,0 +1,112 @@
+"""ctypes binding of ``libdqn_b200.so`` (``include/dqn_b200.h``).
+
+There is deliberately no fallback: if the CUDA library has not been built (``__graft_entry__.build()``
+or ``make -C deep-q-learning_b200/csrc``) importing a compute entry point raises, and if no sm_100a
+device is present ``dqn_create`` fails with ``DQN_E_ARCH``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdqn_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dqn_b200.h")
+
+DQN_OPT_ADAM, DQN_OPT_ADAMW = 0, 1
+DQN_PARAMS_ONLINE, DQN_PARAMS_TARGET = 0, 1
+DQN_MAX_BATCH, DQN_MAX_OBS_DIM, DQN_MAX_ACTIONS = 1024, 16, 7
+LOSS_RING = 4096
+
+
+class DqnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libdqn_b200 error {code}: {msg}")
+        self.code = code
+
+
+class DqnConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32), ("n_agents", C.c_int32),
+        ("obs_dim", C.c_int32), ("num_actions", C.c_int32), ("hidden1", C.c_int32),
+        ("hidden2", C.c_int32), ("batch_size", C.c_int32), ("buffer_size", C.c_int64),
+        ("gamma", C.c_float), ("opt_kind", C.c_int32),
+        ("lr", C.c_float), ("b1", C.c_float), ("b2", C.c_float), ("eps", C.c_float),
+        ("eps_root", C.c_float), ("weight_decay", C.c_float),
+        ("seed", C.c_uint64), ("agent_id_base", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p), ("arena", C.c_void_p), ("arena_bytes", C.c_uint64),
+    ]
+
+
+class DqnHparams(C.Structure):
+    _fields_ = [("gamma", C.c_float), ("batch_size", C.c_int32), ("lr", C.c_float), ("b1", C.c_float),
+                ("b2", C.c_float), ("eps", C.c_float), ("eps_root", C.c_float), ("weight_decay", C.c_float)]
+
+
+class DqnDebugTaps(C.Structure):
+    _fields_ = [("indices", C.c_void_p), ("q", C.c_void_p), ("next_q", C.c_void_p), ("next_q_tm", C.c_void_p),
+                ("max_actions", C.c_void_p), ("targets", C.c_void_p), ("loss", C.c_void_p), ("grads", C.c_void_p)]
+
+
+_H = C.c_void_p          # dqn_handle*
+_P = C.c_void_p          # any data pointer
+_i32, _i64 = C.c_int32, C.c_int64
+
+# name -> (restype, argtypes); one entry per function declared in include/dqn_b200.h
+PROTOTYPES = {
+    "dqn_abi_version": (C.c_int, []),
+    "dqn_last_error": (C.c_char_p, []),
+    "dqn_arena_bytes": (C.c_int, [C.POINTER(DqnConfig), C.POINTER(C.c_uint64)]),
+    "dqn_create": (C.c_int, [C.POINTER(DqnConfig), C.POINTER(_H)]),
+    "dqn_destroy": (C.c_int, [_H]),
+    "dqn_param_count": (C.c_int, [_H, C.POINTER(_i32)]),
+    "dqn_synchronize": (C.c_int, [_H]),
+    "dqn_set_params": (C.c_int, [_H, _i32, _i32, _P, _i32]),
+    "dqn_get_params": (C.c_int, [_H, _i32, _i32, _P, _i32]),
+    "dqn_set_opt_state": (C.c_int, [_H, _i32, _i32, _P, _P, _i32]),
+    "dqn_get_opt_state": (C.c_int, [_H, _i32, C.POINTER(_i32), _P, _P, _i32]),
+    "dqn_set_hparams": (C.c_int, [_H, _i32, C.POINTER(DqnHparams)]),
+    "dqn_get_hparams": (C.c_int, [_H, _i32, C.POINTER(DqnHparams)]),
+    "dqn_store": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P]),
+    "dqn_store_device": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P]),
+    "dqn_buffer_state": (C.c_int, [_H, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
+    "dqn_buffer_export": (C.c_int, [_H, _i32, _P, _P, _P, _P, _P]),
+    "dqn_sample_indices": (C.c_int, [_H, _i32, _i64, _i32, _P]),
+    "dqn_sample_batch": (C.c_int, [_H, _i32, _P, _i64, _i32, _P, _P, _P, _P, _P]),
+    "dqn_sample_batch_device": (C.c_int, [_H, _i32, _P, _i64, _i32, _P, _P, _P, _P, _P]),
+    "dqn_train_step": (C.c_int, [_H, _i32, _i32, _i32, _P, C.POINTER(DqnDebugTaps)]),
+    "dqn_train_step_device_idx": (C.c_int, [_H, _i32, _i32, _i32, _P]),
+    "dqn_get_losses": (C.c_int, [_H, _i32, _i32, _P, C.POINTER(_i64)]),
+    "dqn_sync_target": (C.c_int, [_H, _i32, _i32]),
+    "dqn_act": (C.c_int, [_H, _i32, _P, C.POINTER(_i32)]),
+    "dqn_act_batch": (C.c_int, [_H, _i32, _i32, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every prototype.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; "
+            "g.build()').  There is no CPU/PyTorch fallback for the DQN hot path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)            # AttributeError if the .so lacks a declared symbol
+        fn.restype, fn.argtypes = res, args
+    if lib.dqn_abi_version() != 1:
+        raise ImportError("libdqn_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = _lib.dqn_last_error() if _lib is not None else b""
+        raise DqnError(rc, (msg or b"").decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """Raw data pointer of a C-contiguous numpy array (or None)."""
+    return None if a is None else a.ctypes.data

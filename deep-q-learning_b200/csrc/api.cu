@@ -1,0 +1,617 @@
+// api.cu -- the C ABI of include/dqn_b200.h: handle management, host<->device staging, launches.
+// No compute happens on the host; every entry point either moves bytes or launches a kernel.
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dqn_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace dqn;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _b[512];                                                                                \
+      snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return fail(DQN_E_CUDA, _b);                                                                 \
+    }                                                                                              \
+  } while (0)
+
+constexpr size_t kStageBytes = 8u << 20;
+constexpr size_t kPinnedBytes = 128u << 10;   // [0,64K): ring of store slots; [64K,128K): bounce for synchronous calls
+constexpr size_t kSlotBytes = 2u << 10;
+constexpr int kSlots = 32;
+constexpr size_t kBounceOff = 64u << 10;
+constexpr size_t kBounceBytes = 64u << 10;
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Carve {
+  size_t params, ctl, rings, loss, stage, taps, total;
+};
+
+struct TapsOff {
+  size_t idx, q, nq, nqt, maxa, tgt, loss, grads, bytes;
+};
+
+TapsOff taps_layout(const Dims& d) {
+  TapsOff t;
+  size_t o = 0;
+  t.idx = o; o += align_up((size_t)DQN_MAX_BATCH * 8, 256);
+  t.q = o; o += align_up((size_t)DQN_MAX_BATCH * d.A * 4, 256);
+  t.nq = o; o += align_up((size_t)DQN_MAX_BATCH * d.A * 4, 256);
+  t.nqt = o; o += align_up((size_t)DQN_MAX_BATCH * d.A * 4, 256);
+  t.tgt = o; o += align_up((size_t)DQN_MAX_BATCH * d.A * 4, 256);
+  t.maxa = o; o += align_up((size_t)DQN_MAX_BATCH * 4, 256);
+  t.loss = o; o += 256;
+  t.grads = o; o += align_up((size_t)d.PF * 4, 256);
+  t.bytes = o;
+  return t;
+}
+
+Carve carve(const Dims& d, int n_agents) {
+  Carve c;
+  size_t o = 0;
+  c.params = o; o += align_up((size_t)n_agents * 4 * d.PF * 4, 256);
+  c.ctl = o; o += align_up((size_t)n_agents * sizeof(AgentCtl), 256);
+  c.rings = o; o += align_up((size_t)n_agents * (size_t)d.N * d.recw * 4, 256);
+  c.loss = o; o += align_up((size_t)n_agents * kLossCap * 4, 256);
+  c.stage = o; o += kStageBytes;
+  c.taps = o; o += taps_layout(d).bytes;
+  c.total = o;
+  return c;
+}
+
+int validate(const dqn_config* cfg, Dims* d) {
+  if (!cfg) return fail(DQN_E_INVALID, "config is NULL");
+  if (cfg->struct_size != (int32_t)sizeof(dqn_config))
+    return fail(DQN_E_INVALID, "dqn_config.struct_size mismatch (ABI version skew)");
+  if (cfg->n_agents < 1) return fail(DQN_E_INVALID, "n_agents must be >= 1");
+  if (cfg->obs_dim < 1 || cfg->obs_dim > DQN_MAX_OBS_DIM) return fail(DQN_E_INVALID, "obs_dim must be in [1,16]");
+  if (cfg->num_actions < 2 || cfg->num_actions > DQN_MAX_ACTIONS) return fail(DQN_E_INVALID, "num_actions must be in [2,7]");
+  if (cfg->hidden1 != kH1 || cfg->hidden2 != kH2)
+    return fail(DQN_E_INVALID, "the fused path implements the reference network only: hidden = (32, 64) (LunarLander/dddqn.py:19-20)");
+  if (cfg->batch_size < 1 || cfg->batch_size > DQN_MAX_BATCH) return fail(DQN_E_INVALID, "batch_size must be in [1,1024]");
+  if (cfg->buffer_size < 1 || cfg->buffer_size >= (1ll << 31)) return fail(DQN_E_INVALID, "buffer_size must be in [1, 2^31)");
+  if (cfg->opt_kind != DQN_OPT_ADAM && cfg->opt_kind != DQN_OPT_ADAMW) return fail(DQN_E_INVALID, "opt_kind must be adam or adamw");
+  d->D = cfg->obs_dim;
+  d->A = cfg->num_actions;
+  d->P = flat_param_count(d->D, d->A);
+  d->PF = (d->P + 3) & ~3;
+  d->recw = record_words(d->D);
+  d->N = cfg->buffer_size;
+  return DQN_OK;
+}
+
+}  // namespace
+
+struct dqn_handle {
+  dqn_config cfg;
+  Dims dims;
+  cudaStream_t stream;
+  uint8_t* arena;
+  bool own_arena;
+  Carve cv;
+  TapsOff to;
+  float* params;
+  AgentCtl* ctl;
+  uint32_t* rings;
+  float* loss_ring;
+  uint8_t* stage;
+  uint8_t* taps;
+  uint8_t* pinned;
+  uint8_t* bounce;              // pinned + kBounceOff
+  cudaEvent_t slot_ev[kSlots];  // completion of the H2D copy that last used each pinned store slot
+  int slot_next;
+  std::vector<AgentCtl> hctl;   // host mirror of the per-agent control blocks
+};
+
+namespace {
+
+int check_agent(const dqn_handle* h, int agent) {
+  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
+  if (agent < 0 || agent >= h->cfg.n_agents) return fail(DQN_E_INVALID, "agent index out of range");
+  return DQN_OK;
+}
+int check_range(const dqn_handle* h, int b, int e) {
+  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
+  if (b < 0 || e > h->cfg.n_agents || b >= e) return fail(DQN_E_INVALID, "agent range out of bounds or empty");
+  return DQN_OK;
+}
+uint32_t* ring_of(dqn_handle* h, int agent) { return h->rings + (size_t)agent * (size_t)h->dims.N * h->dims.recw; }
+long long size_of(const dqn_handle* h, int agent) {
+  const long long c = h->hctl[agent].ring_counter;
+  return c < h->dims.N ? c : h->dims.N;
+}
+
+struct SoA {   // carve of the staging buffer into the five transition arrays for n transitions
+  float* s; long long* a; float* r; float* s2; uint8_t* done;
+};
+SoA stage_soa(dqn_handle* h, long long n) {
+  const int D = h->dims.D;
+  uint8_t* p = h->stage;
+  SoA o;
+  o.a = (long long*)p; p += align_up((size_t)n * 8, 16);
+  o.s = (float*)p; p += align_up((size_t)n * D * 4, 16);
+  o.s2 = (float*)p; p += align_up((size_t)n * D * 4, 16);
+  o.r = (float*)p; p += align_up((size_t)n * 4, 16);
+  o.done = p;
+  return o;
+}
+long long stage_capacity(const dqn_handle* h) { return (long long)((kStageBytes - 128) / (8 * h->dims.D + 13)); }
+
+}  // namespace
+
+extern "C" {
+
+DQN_API int dqn_abi_version(void) { return DQN_ABI_VERSION; }
+DQN_API const char* dqn_last_error(void) { return g_err.c_str(); }
+
+DQN_API int dqn_arena_bytes(const dqn_config* cfg, uint64_t* bytes_out) {
+  Dims d;
+  if (int rc = validate(cfg, &d)) return rc;
+  if (!bytes_out) return fail(DQN_E_INVALID, "bytes_out is NULL");
+  *bytes_out = carve(d, cfg->n_agents).total;
+  return DQN_OK;
+}
+
+DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
+  Dims d;
+  if (int rc = validate(cfg, &d)) return rc;
+  if (!out) return fail(DQN_E_INVALID, "out is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(DQN_E_ARCH, "no CUDA device visible: libdqn_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(DQN_E_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    char b[256];
+    snprintf(b, sizeof b, "device %d is sm_%d%d; libdqn_b200 is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+    return fail(DQN_E_ARCH, b);
+  }
+  CU(cudaSetDevice(cfg->device));
+  dqn_handle* h = new dqn_handle();
+  h->cfg = *cfg;
+  h->dims = d;
+  h->stream = (cudaStream_t)cfg->stream;
+  h->cv = carve(d, cfg->n_agents);
+  h->to = taps_layout(d);
+  if (cfg->arena) {
+    if (cfg->arena_bytes < h->cv.total || ((uintptr_t)cfg->arena & 255)) {
+      delete h;
+      return fail(DQN_E_INVALID, "arena too small (see dqn_arena_bytes) or not 256-byte aligned");
+    }
+    h->arena = (uint8_t*)cfg->arena;
+    h->own_arena = false;
+  } else {
+    cudaError_t e = cudaMalloc((void**)&h->arena, h->cv.total);
+    if (e != cudaSuccess) { delete h; return fail(DQN_E_NOMEM, std::string("cudaMalloc(arena) failed: ") + cudaGetErrorString(e)); }
+    h->own_arena = true;
+  }
+  h->params = (float*)(h->arena + h->cv.params);
+  h->ctl = (AgentCtl*)(h->arena + h->cv.ctl);
+  h->rings = (uint32_t*)(h->arena + h->cv.rings);
+  h->loss_ring = (float*)(h->arena + h->cv.loss);
+  h->stage = h->arena + h->cv.stage;
+  h->taps = h->arena + h->cv.taps;
+  h->pinned = nullptr;
+  cudaError_t e = cudaMallocHost((void**)&h->pinned, kPinnedBytes);
+  if (e != cudaSuccess) { if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaMallocHost failed"); }
+  h->bounce = h->pinned + kBounceOff;
+  h->slot_next = 0;
+  for (int i = 0; i < kSlots; ++i) cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming);
+  // zero parameters / moments / rings / losses (ReplayBuffer.__init__ zero-fills, replay_buffer.py:26-30)
+  e = cudaMemsetAsync(h->arena, 0, h->cv.stage, h->stream);
+  if (e == cudaSuccess) e = train_fused_prepare(d);
+  AgentCtl c;
+  memset(&c, 0, sizeof c);
+  c.gamma = cfg->gamma; c.lr = cfg->lr; c.b1 = cfg->b1; c.b2 = cfg->b2; c.eps = cfg->eps;
+  c.eps_root = cfg->eps_root; c.wd = cfg->opt_kind == DQN_OPT_ADAMW ? cfg->weight_decay : 0.f;
+  c.batch_size = cfg->batch_size;
+  h->hctl.assign(cfg->n_agents, c);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h->ctl, h->hctl.data(), sizeof(AgentCtl) * cfg->n_agents, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    std::string m = std::string("dqn_create: device initialisation failed: ") + cudaGetErrorString(e);
+    for (int i = 0; i < kSlots; ++i) cudaEventDestroy(h->slot_ev[i]);
+    cudaFreeHost(h->pinned);
+    if (h->own_arena) cudaFree(h->arena);
+    delete h;
+    return fail(e == cudaErrorNoKernelImageForDevice || e == cudaErrorInvalidDeviceFunction ? DQN_E_ARCH : DQN_E_CUDA, m);
+  }
+  *out = h;
+  return DQN_OK;
+}
+
+DQN_API int dqn_destroy(dqn_handle* h) {
+  if (!h) return DQN_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < kSlots; ++i) cudaEventDestroy(h->slot_ev[i]);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->own_arena) cudaFree(h->arena);
+  delete h;
+  return DQN_OK;
+}
+
+DQN_API int dqn_param_count(const dqn_handle* h, int32_t* p_out) {
+  if (!h || !p_out) return fail(DQN_E_INVALID, "NULL argument");
+  *p_out = h->dims.P;
+  return DQN_OK;
+}
+
+DQN_API int dqn_synchronize(dqn_handle* h) {
+  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+
+DQN_API int dqn_set_params(dqn_handle* h, int32_t agent, int32_t which, const float* host_flat, int32_t n) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if ((which != DQN_PARAMS_ONLINE && which != DQN_PARAMS_TARGET) || !host_flat || n != h->dims.P)
+    return fail(DQN_E_INVALID, "dqn_set_params: bad `which`, NULL pointer or n != dqn_param_count");
+  CU(cudaSetDevice(h->cfg.device));
+  float* dst = h->params + ((size_t)agent * 4 + which) * h->dims.PF;
+  CU(cudaMemcpyAsync(dst, host_flat, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+
+DQN_API int dqn_get_params(dqn_handle* h, int32_t agent, int32_t which, float* host_flat, int32_t n) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if ((which != DQN_PARAMS_ONLINE && which != DQN_PARAMS_TARGET) || !host_flat || n != h->dims.P)
+    return fail(DQN_E_INVALID, "dqn_get_params: bad `which`, NULL pointer or n != dqn_param_count");
+  CU(cudaSetDevice(h->cfg.device));
+  const float* src = h->params + ((size_t)agent * 4 + which) * h->dims.PF;
+  CU(cudaMemcpyAsync(host_flat, src, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+
+DQN_API int dqn_set_opt_state(dqn_handle* h, int32_t agent, int32_t count, const float* mu, const float* nu, int32_t n) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (!mu || !nu || n != h->dims.P || count < 0) return fail(DQN_E_INVALID, "dqn_set_opt_state: NULL pointer, n != dqn_param_count or count < 0");
+  CU(cudaSetDevice(h->cfg.device));
+  float* base = h->params + (size_t)agent * 4 * h->dims.PF;
+  CU(cudaMemcpyAsync(base + 2 * h->dims.PF, mu, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(base + 3 * h->dims.PF, nu, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  h->hctl[agent].adam_count = count;
+  CU(cudaMemcpyAsync(&h->ctl[agent].adam_count, &h->hctl[agent].adam_count, 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+
+DQN_API int dqn_get_opt_state(dqn_handle* h, int32_t agent, int32_t* count, float* mu, float* nu, int32_t n) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (n != h->dims.P) return fail(DQN_E_INVALID, "dqn_get_opt_state: n != dqn_param_count");
+  CU(cudaSetDevice(h->cfg.device));
+  const float* base = h->params + (size_t)agent * 4 * h->dims.PF;
+  if (mu) CU(cudaMemcpyAsync(mu, base + 2 * h->dims.PF, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (nu) CU(cudaMemcpyAsync(nu, base + 3 * h->dims.PF, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  int32_t* pc = (int32_t*)h->bounce;
+  CU(cudaMemcpyAsync(pc, &h->ctl[agent].adam_count, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (count) *count = *pc;
+  return DQN_OK;
+}
+
+DQN_API int dqn_set_hparams(dqn_handle* h, int32_t agent, const dqn_hparams* hp) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (!hp) return fail(DQN_E_INVALID, "hp is NULL");
+  AgentCtl& c = h->hctl[agent];
+  if (hp->batch_size > DQN_MAX_BATCH || hp->batch_size == 0) return fail(DQN_E_INVALID, "batch_size must be in [1,1024]");
+  if (hp->gamma == hp->gamma && hp->gamma >= 0.f) c.gamma = hp->gamma;
+  if (hp->batch_size > 0) c.batch_size = hp->batch_size;
+  if (hp->lr == hp->lr && hp->lr >= 0.f) c.lr = hp->lr;
+  if (hp->b1 == hp->b1 && hp->b1 >= 0.f) c.b1 = hp->b1;
+  if (hp->b2 == hp->b2 && hp->b2 >= 0.f) c.b2 = hp->b2;
+  if (hp->eps == hp->eps && hp->eps >= 0.f) c.eps = hp->eps;
+  if (hp->eps_root == hp->eps_root && hp->eps_root >= 0.f) c.eps_root = hp->eps_root;
+  if (hp->weight_decay == hp->weight_decay && hp->weight_decay >= 0.f) c.wd = hp->weight_decay;
+  CU(cudaSetDevice(h->cfg.device));
+  // only the hyper-parameter prefix: the counters behind it are owned by the device
+  memcpy(h->bounce, &c, offsetof(AgentCtl, adam_count));
+  CU(cudaMemcpyAsync(&h->ctl[agent], h->bounce, offsetof(AgentCtl, adam_count), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+
+DQN_API int dqn_get_hparams(dqn_handle* h, int32_t agent, dqn_hparams* hp) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (!hp) return fail(DQN_E_INVALID, "hp is NULL");
+  const AgentCtl& c = h->hctl[agent];
+  hp->gamma = c.gamma; hp->batch_size = c.batch_size; hp->lr = c.lr; hp->b1 = c.b1; hp->b2 = c.b2;
+  hp->eps = c.eps; hp->eps_root = c.eps_root; hp->weight_decay = c.wd;
+  return DQN_OK;
+}
+
+DQN_API int dqn_store_device(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a, const float* r,
+                     const float* s2, const uint8_t* done) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (n < 0 || (n > 0 && (!s || !a || !r || !s2 || !done))) return fail(DQN_E_INVALID, "dqn_store: negative n or NULL array");
+  if (n == 0) return DQN_OK;
+  CU(cudaSetDevice(h->cfg.device));
+  const long long N = h->dims.N;
+  long long counter = h->hctl[agent].ring_counter;
+  long long skip = 0;
+  if (n > N) {   // only the last N transitions survive n scalar add() calls; the counter still advances by n
+    skip = n - N;
+  }
+  const int D = h->dims.D;
+  CU(launch_replay_store(h->stream, ring_of(h, agent), h->dims, counter + skip, n - skip, s + skip * D,
+                         (const long long*)a + skip, r + skip, s2 + skip * D, done + skip, &h->ctl[agent]));
+  h->hctl[agent].ring_counter = counter + n;
+  return DQN_OK;
+}
+
+DQN_API int dqn_store(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a, const float* r,
+              const float* s2, const uint8_t* done) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (n < 0 || (n > 0 && (!s || !a || !r || !s2 || !done))) return fail(DQN_E_INVALID, "dqn_store: negative n or NULL array");
+  CU(cudaSetDevice(h->cfg.device));
+  const int D = h->dims.D;
+  if (n > 0 && (size_t)n * (8 * D + 13) + 64 <= kSlotBytes) {
+    // small store (the reference adds ONE transition per env step): pack the five arrays into a pinned
+    // slot in the staging layout and move them with a single asynchronous copy
+    const int slot = h->slot_next;
+    h->slot_next = (slot + 1) % kSlots;
+    CU(cudaEventSynchronize(h->slot_ev[slot]));
+    uint8_t* p = h->pinned + (size_t)slot * kSlotBytes;
+    SoA d = stage_soa(h, n);
+    const size_t bytes = (size_t)(d.done - h->stage) + (size_t)n;
+    memcpy(p + ((uint8_t*)d.a - h->stage), a, (size_t)n * 8);
+    memcpy(p + ((uint8_t*)d.s - h->stage), s, (size_t)n * D * 4);
+    memcpy(p + ((uint8_t*)d.s2 - h->stage), s2, (size_t)n * D * 4);
+    memcpy(p + ((uint8_t*)d.r - h->stage), r, (size_t)n * 4);
+    memcpy(p + (d.done - h->stage), done, (size_t)n);
+    CU(cudaMemcpyAsync(h->stage, p, bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaEventRecord(h->slot_ev[slot], h->stream));
+    return dqn_store_device(h, agent, n, d.s, (const int64_t*)d.a, d.r, d.s2, d.done);
+  }
+  const long long cap = stage_capacity(h);
+  for (long long off = 0; off < n; off += cap) {
+    const long long m = n - off < cap ? n - off : cap;
+    SoA d = stage_soa(h, m);
+    CU(cudaMemcpyAsync(d.s, s + off * D, (size_t)m * D * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d.a, a + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d.r, r + off, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d.s2, s2 + off * D, (size_t)m * D * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d.done, done + off, (size_t)m, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = dqn_store_device(h, agent, m, d.s, (const int64_t*)d.a, d.r, d.s2, d.done)) return rc;
+  }
+  return DQN_OK;
+}
+
+DQN_API int dqn_buffer_state(dqn_handle* h, int32_t agent, int64_t* size_out, int64_t* counter_out) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (size_out) *size_out = size_of(h, agent);
+  if (counter_out) *counter_out = h->hctl[agent].ring_counter;
+  return DQN_OK;
+}
+
+DQN_API int dqn_sample_batch_device(dqn_handle* h, int32_t agent, const int64_t* idx_dev, int64_t step, int32_t batch,
+                            float* s, int64_t* a, float* r, float* s2, uint8_t* done) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (batch < 0 || !s || !a || !r || !s2 || !done) return fail(DQN_E_INVALID, "dqn_sample_batch: negative batch or NULL output");
+  const long long size = size_of(h, agent);
+  if (batch > 0 && size == 0) return fail(DQN_E_INVALID, "dqn_sample_batch: the replay ring is empty (randint(0, 0) raises in the reference)");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(launch_replay_gather(h->stream, ring_of(h, agent), h->dims, idx_dev ? 0 : 1, (const long long*)idx_dev, h->cfg.seed, h->cfg.agent_id_base + agent,
+                          step, size, batch, s, (long long*)a, r, s2, done));
+  return DQN_OK;
+}
+
+namespace {
+// gather `count` records (mode 0: staged explicit idx, 1: philox, 2: identity from `first`) to host arrays via staging
+int gather_to_host(dqn_handle* h, int agent, int mode, const int64_t* idx_host, long long step, long long first,
+                   long long count, float* s, int64_t* a, float* r, float* s2, uint8_t* done) {
+  const int D = h->dims.D;
+  const long long cap = (long long)((kStageBytes - 256) / (8 * D + 13 + 8));
+  const long long size = size_of(h, agent);
+  for (long long off = 0; off < count; off += cap) {
+    const long long m = count - off < cap ? count - off : cap;
+    SoA d = stage_soa(h, m);
+    long long* didx = (long long*)(d.done + align_up((size_t)m, 16));
+    const uint32_t* ring = ring_of(h, agent);
+    if (mode == 0) {
+      CU(cudaMemcpyAsync(didx, idx_host + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+      CU(launch_replay_gather(h->stream, ring, h->dims, 0, didx, 0, agent, 0, size, m, d.s, d.a, d.r, d.s2, d.done));
+    } else if (mode == 1) {
+      // Philox slot index i is global within the step: draw then gather explicitly for chunks beyond the first
+      CU(launch_philox_indices(h->stream, didx, (int)m, h->cfg.seed, h->cfg.agent_id_base + agent, step, size));
+      if (off != 0) return fail(DQN_E_INVALID, "dqn_sample_batch: batch too large for one staging chunk");
+      CU(launch_replay_gather(h->stream, ring, h->dims, 0, didx, 0, agent, 0, size, m, d.s, d.a, d.r, d.s2, d.done));
+    } else {
+      CU(launch_replay_gather(h->stream, ring + (size_t)(first + off) * h->dims.recw, h->dims, 2, nullptr, 0, agent, 0, size, m,
+                              d.s, d.a, d.r, d.s2, d.done));
+    }
+    CU(cudaMemcpyAsync(s + off * D, d.s, (size_t)m * D * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(a + off, d.a, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(r + off, d.r, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(s2 + off * D, d.s2, (size_t)m * D * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(done + off, d.done, (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return DQN_OK;
+}
+}  // namespace
+
+DQN_API int dqn_buffer_export(dqn_handle* h, int32_t agent, float* s, int64_t* a, float* r, float* s2, uint8_t* done) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (!s || !a || !r || !s2 || !done) return fail(DQN_E_INVALID, "dqn_buffer_export: NULL output");
+  CU(cudaSetDevice(h->cfg.device));
+  return gather_to_host(h, agent, 2, nullptr, 0, 0, h->dims.N, s, a, r, s2, done);
+}
+
+DQN_API int dqn_sample_indices(dqn_handle* h, int32_t agent, int64_t step, int32_t batch, int64_t* idx_out) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (batch < 0 || (size_t)batch * 8 > kStageBytes || !idx_out) return fail(DQN_E_INVALID, "dqn_sample_indices: bad batch or NULL output");
+  const long long size = size_of(h, agent);
+  if (batch > 0 && size == 0) return fail(DQN_E_INVALID, "dqn_sample_indices: the replay ring is empty");
+  if (batch == 0) return DQN_OK;
+  CU(cudaSetDevice(h->cfg.device));
+  CU(launch_philox_indices(h->stream, (long long*)h->stage, batch, h->cfg.seed, h->cfg.agent_id_base + agent, step, size));
+  CU(cudaMemcpyAsync(idx_out, h->stage, (size_t)batch * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+
+DQN_API int dqn_sample_batch(dqn_handle* h, int32_t agent, const int64_t* idx, int64_t step, int32_t batch,
+                     float* s, int64_t* a, float* r, float* s2, uint8_t* done) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (batch < 0 || !s || !a || !r || !s2 || !done) return fail(DQN_E_INVALID, "dqn_sample_batch: negative batch or NULL output");
+  const long long size = size_of(h, agent);
+  if (batch > 0 && size == 0) return fail(DQN_E_INVALID, "dqn_sample_batch: the replay ring is empty (randint(0, 0) raises in the reference)");
+  if (idx) for (int i = 0; i < batch; ++i) if (idx[i] < 0 || idx[i] >= h->dims.N) return fail(DQN_E_INVALID, "dqn_sample_batch: index out of range");
+  CU(cudaSetDevice(h->cfg.device));
+  return gather_to_host(h, agent, idx ? 0 : 1, idx, step, 0, batch, s, a, r, s2, done);
+}
+
+namespace {
+int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, dqn_debug_taps* taps) {
+  const int n_sel = e - b;
+  for (int ag = b; ag < e; ++ag) {
+    if (size_of(h, ag) == 0) return fail(DQN_E_INVALID, "dqn_train_step: replay ring of an agent is empty");
+  }
+  TrainArgs ta;
+  memset(&ta, 0, sizeof ta);
+  ta.params = h->params; ta.ctl = h->ctl; ta.rings = h->rings; ta.loss_ring = h->loss_ring;
+  ta.idx = idx_dev; ta.dims = h->dims; ta.seed = h->cfg.seed; ta.agent_begin = b; ta.agent_id_base = h->cfg.agent_id_base; ta.n_sel = n_sel; ta.K = K;
+  if (taps) {
+    if (K != 1 || n_sel != 1) return fail(DQN_E_INVALID, "dqn_train_step: debug taps need K == 1 and a single agent");
+    uint8_t* t = h->taps;
+    ta.taps.enabled = 1;
+    ta.taps.indices = (long long*)(t + h->to.idx);
+    ta.taps.q = (float*)(t + h->to.q);
+    ta.taps.next_q = (float*)(t + h->to.nq);
+    ta.taps.next_q_tm = (float*)(t + h->to.nqt);
+    ta.taps.targets = (float*)(t + h->to.tgt);
+    ta.taps.max_actions = (int*)(t + h->to.maxa);
+    ta.taps.loss = (float*)(t + h->to.loss);
+    ta.taps.grads = (float*)(t + h->to.grads);
+  }
+  CU(launch_train_fused(h->stream, ta));
+  for (int ag = b; ag < e; ++ag) {
+    AgentCtl& c = h->hctl[ag];
+    c.train_steps += K;
+    const long long cnt = (long long)c.adam_count + K;
+    c.adam_count = cnt > 0x7fffffffLL ? 0x7fffffff : (int)cnt;
+  }
+  if (taps) {
+    const int B = h->hctl[b].batch_size, A = h->dims.A;
+    uint8_t* t = h->taps;
+    if (taps->indices) CU(cudaMemcpyAsync(taps->indices, t + h->to.idx, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (taps->q) CU(cudaMemcpyAsync(taps->q, t + h->to.q, (size_t)B * A * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (taps->next_q) CU(cudaMemcpyAsync(taps->next_q, t + h->to.nq, (size_t)B * A * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (taps->next_q_tm) CU(cudaMemcpyAsync(taps->next_q_tm, t + h->to.nqt, (size_t)B * A * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (taps->targets) CU(cudaMemcpyAsync(taps->targets, t + h->to.tgt, (size_t)B * A * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (taps->max_actions) CU(cudaMemcpyAsync(taps->max_actions, t + h->to.maxa, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (taps->loss) CU(cudaMemcpyAsync(taps->loss, t + h->to.loss, 4, cudaMemcpyDeviceToHost, h->stream));
+    if (taps->grads) CU(cudaMemcpyAsync(taps->grads, t + h->to.grads, (size_t)h->dims.P * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return DQN_OK;
+}
+}  // namespace
+
+DQN_API int dqn_train_step(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K, const int64_t* idx, dqn_debug_taps* taps) {
+  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
+  if (K < 1) return fail(DQN_E_INVALID, "dqn_train_step: K must be >= 1");
+  CU(cudaSetDevice(h->cfg.device));
+  const long long* idx_dev = nullptr;
+  if (idx) {
+    // explicit indices need one common batch size across the selected agents (layout [n_sel][K][B])
+    const int B = h->hctl[agent_begin].batch_size;
+    size_t total = 0;
+    for (int ag = agent_begin; ag < agent_end; ++ag) {
+      if (h->hctl[ag].batch_size != B) return fail(DQN_E_INVALID, "dqn_train_step: explicit indices need equal batch sizes in the agent range");
+      const long long size = size_of(h, ag);
+      const int64_t* p = idx + (size_t)(ag - agent_begin) * K * B;
+      for (size_t i = 0; i < (size_t)K * B; ++i) if (p[i] < 0 || p[i] >= size) return fail(DQN_E_INVALID, "dqn_train_step: index outside [0, size)");
+      total += (size_t)K * B;
+    }
+    if (total * 8 > kStageBytes) return fail(DQN_E_INVALID, "dqn_train_step: explicit index block exceeds the 8 MiB staging buffer");
+    CU(cudaMemcpyAsync(h->stage, idx, total * 8, cudaMemcpyHostToDevice, h->stream));
+    idx_dev = (const long long*)h->stage;
+  }
+  return train_common(h, agent_begin, agent_end, K, idx_dev, taps);
+}
+
+DQN_API int dqn_train_step_device_idx(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K, const int64_t* idx_dev) {
+  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
+  if (K < 1) return fail(DQN_E_INVALID, "dqn_train_step: K must be >= 1");
+  CU(cudaSetDevice(h->cfg.device));
+  return train_common(h, agent_begin, agent_end, K, (const long long*)idx_dev, nullptr);
+}
+
+DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_out, int64_t* train_steps_out) {
+  if (int rc = check_agent(h, agent)) return rc;
+  const long long ts = h->hctl[agent].train_steps;
+  if (train_steps_out) *train_steps_out = ts;
+  if (n == 0) return DQN_OK;
+  if (n < 0 || n > kLossCap || n > ts || !loss_out) return fail(DQN_E_INVALID, "dqn_get_losses: n must be <= min(train steps so far, 4096)");
+  CU(cudaSetDevice(h->cfg.device));
+  std::vector<float> ring(kLossCap);
+  CU(cudaMemcpyAsync(ring.data(), h->loss_ring + (size_t)agent * kLossCap, kLossCap * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) loss_out[i] = ring[(size_t)((ts - n + i) % kLossCap)];
+  return DQN_OK;
+}
+
+DQN_API int dqn_sync_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end) {
+  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
+  CU(cudaSetDevice(h->cfg.device));
+  CU(launch_sync_target(h->stream, h->params, h->dims, agent_begin, agent_end - agent_begin));
+  return DQN_OK;
+}
+
+DQN_API int dqn_act_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* states, int32_t* actions_out) {
+  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
+  if (!states || !actions_out) return fail(DQN_E_INVALID, "dqn_act: NULL argument");
+  CU(cudaSetDevice(h->cfg.device));
+  const int n = agent_end - agent_begin, D = h->dims.D;
+  float* dstates = (float*)h->stage;
+  int* dact = (int*)(h->stage + align_up((size_t)n * D * 4, 256));
+  const bool small = (size_t)n * D * 4 <= kBounceBytes / 2 && (size_t)n * 4 <= kBounceBytes / 2;
+  if (small) {   // bounce through pinned memory: truly asynchronous copies, one synchronisation
+    memcpy(h->bounce, states, (size_t)n * D * 4);
+    CU(cudaMemcpyAsync(dstates, h->bounce, (size_t)n * D * 4, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CU(cudaMemcpyAsync(dstates, states, (size_t)n * D * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU(launch_act(h->stream, h->params, h->dims, agent_begin, n, dstates, dact, nullptr));
+  if (small) {
+    int32_t* pa = (int32_t*)(h->bounce + kBounceBytes / 2);
+    CU(cudaMemcpyAsync(pa, dact, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(actions_out, pa, (size_t)n * 4);
+  } else {
+    CU(cudaMemcpyAsync(actions_out, dact, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return DQN_OK;
+}
+
+DQN_API int dqn_act(dqn_handle* h, int32_t agent, const float* state, int32_t* action_out) {
+  if (int rc = check_agent(h, agent)) return rc;
+  return dqn_act_batch(h, agent, agent + 1, state, action_out);
+}
+
+}  // extern "C"

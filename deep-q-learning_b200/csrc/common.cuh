@@ -1,0 +1,77 @@
+// common.cuh -- shared device/host definitions for libdqn_b200 (sm_100a).
+//
+// HBM data layout (see DESIGN.md "Data layout"):
+//   params   f32 [n_agents][4][PF]        online | target | mu | nu, each in the FLAT layout of
+//                                          include/dqn_b200.h; PF = P rounded up to 4 floats.
+//   ctl      AgentCtl [n_agents]          per-agent hyper-parameters and counters.
+//   ring     u8  [n_agents][N][REC]       AoS replay records, REC = round_up((2D+4)*4, 32) bytes:
+//                                          words [0,D) s | [D,2D) s' | 2D,2D+1 action (i64) |
+//                                          2D+2 reward (f32) | 2D+3 done (u32 0/1) | zero padding.
+//            One record = one 32-byte-sector-aligned gather (96 B for D <= 10), instead of five
+//            scattered sectors for the reference's five SoA arrays (replay_buffer.py:26-30);
+//            dqn_buffer_export() de-interleaves back to those arrays bit-exactly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dqn {
+
+constexpr int kH1 = 32;        // LunarLander/dddqn.py:19
+constexpr int kH2 = 64;        // LunarLander/dddqn.py:20
+constexpr int kMaxD = 16;
+constexpr int kMaxA = 7;
+constexpr int kLossCap = 4096; // per-agent ring of recent losses
+
+struct AgentCtl {
+  float gamma, lr, b1, b2, eps, eps_root, wd;
+  int batch_size;
+  int adam_count;          // optax ScaleByAdamState.count (int32, saturating)
+  int pad0;
+  long long ring_counter;  // ReplayBuffer._counter (total adds)
+  long long train_steps;   // number of _step() calls so far == Philox step counter
+};
+
+struct Dims {
+  int D, A;      // obs dim, actions
+  int P;         // flat parameter count
+  int PF;        // P rounded up to a multiple of 4
+  int recw;      // record stride in 32-bit words
+  long long N;   // ring slots per agent
+};
+
+__host__ __device__ inline int flat_param_count(int D, int A) {
+  return D * kH1 + kH1 + kH1 * kH2 + kH2 + kH2 + 1 + kH2 * A + A;
+}
+__host__ __device__ inline int record_words(int D) { return (((2 * D + 4) * 4 + 31) / 32) * 8; }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Bit-exact twin of oracle/philox.py.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Slot index for sample `i` of train step `step` of `agent`: uniform in [0,size), with replacement
+// (the distribution of numpy.random.randint(0, size, B), replay_buffer.py:77).
+__device__ __forceinline__ long long philox_index(uint64_t seed, int agent, long long step, int i, long long size) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)i, (uint32_t)step, (uint32_t)((uint64_t)step >> 32), (uint32_t)agent,
+                (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  const uint64_t x = (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+  return (long long)__umul64hi(x, (uint64_t)size);
+}
+
+}  // namespace dqn

@@ -1,0 +1,55 @@
+// kernels.h -- host-side launchers of the sm_100a kernels (internal; the public surface is
+// include/dqn_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace dqn {
+
+// Device-pointer taps of one train step (see dqn_debug_taps in include/dqn_b200.h).
+struct TapsDev {
+  long long* indices;
+  float* q;
+  float* next_q;
+  float* next_q_tm;
+  int* max_actions;
+  float* targets;
+  float* loss;
+  float* grads;   // flat layout, P floats
+  int enabled;
+};
+
+struct TrainArgs {
+  float* params;              // [n_agents][4][PF]
+  AgentCtl* ctl;              // [n_agents]
+  const uint32_t* rings;      // [n_agents][N][recw]
+  float* loss_ring;           // [n_agents][kLossCap]
+  const long long* idx;       // device i64 [n_sel][K][B] or nullptr (Philox)
+  Dims dims;
+  unsigned long long seed;
+  int agent_begin;
+  int agent_id_base;   // Philox agent id = agent_id_base + agent
+  int n_sel;
+  int K;
+  TapsDev taps;
+};
+
+cudaError_t launch_replay_store(cudaStream_t st, uint32_t* ring, const Dims& d, long long counter, long long n,
+                                const float* s, const long long* a, const float* r, const float* s2,
+                                const uint8_t* done, AgentCtl* ctl);
+cudaError_t launch_philox_indices(cudaStream_t st, long long* out, int batch, uint64_t seed, int agent,
+                                  long long step, long long size);
+// mode: 0 explicit idx, 1 Philox(seed, agent, step), 2 identity (export)
+cudaError_t launch_replay_gather(cudaStream_t st, const uint32_t* ring, const Dims& d, int mode, const long long* idx,
+                                 uint64_t seed, int agent, long long step, long long size, long long batch,
+                                 float* s, long long* a, float* r, float* s2, uint8_t* done);
+
+size_t train_fused_smem_bytes(const Dims& d);
+cudaError_t train_fused_prepare(const Dims& d);   // cudaFuncSetAttribute for the instantiation
+cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args);
+
+cudaError_t launch_act(cudaStream_t st, const float* params, const Dims& d, int agent_begin, int n_sel,
+                       const float* states /* device [n_sel][D] */, int* actions_out /* device [n_sel] */,
+                       float* q_out /* device [n_sel][A] or nullptr */);
+cudaError_t launch_sync_target(cudaStream_t st, float* params, const Dims& d, int agent_begin, int n_sel);
+
+}  // namespace dqn

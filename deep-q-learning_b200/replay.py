@@ -1,0 +1,122 @@
+"""Drop-in for ``General/Base/replay_buffer.py`` over the HBM-resident ring.
+
+Same names and argument meaning as the reference: ``ReplayBuffer(buffer_size, obs_shape, ac_shape)``
+(``replay_buffer.py:20``), ``.add(state, action, reward, observation, done)`` (``:58``), ``.size``
+and the five array properties (``:34-56``), and the free function ``sample_batch(num_samples,
+states, actions, rewards, observations, dones, batch_size)`` (``:68-85``).  The arrays live on the
+device as AoS records; the properties return ``RingView`` handles that ``sample_batch`` recognises
+and that convert to the reference's numpy arrays (dtype and contents bit-identical) on
+``numpy.asarray``.
+"""
+import numpy as np
+
+from . import _lib
+from .specs import adam
+
+_FIELDS = ("states", "actions", "rewards", "observations", "dones")
+
+
+class RingView:
+    """Lazy view of one of the five replay arrays (device-resident)."""
+
+    def __init__(self, buffer, field):
+        self._buffer, self._field = buffer, field
+
+    def __array__(self, dtype=None, copy=None):
+        arr = self._buffer._export()[_FIELDS.index(self._field)]
+        return arr if dtype is None else arr.astype(dtype)
+
+    def __getitem__(self, item):
+        return np.asarray(self)[item]
+
+    def __len__(self):
+        return self._buffer._buffer_size
+
+    @property
+    def shape(self):
+        n, d = self._buffer._buffer_size, self._buffer._obs_dim
+        return (n, d) if self._field in ("states", "observations") else (n,)
+
+    @property
+    def dtype(self):
+        return {"states": np.dtype(np.float32), "observations": np.dtype(np.float32),
+                "rewards": np.dtype(np.float32), "actions": np.dtype(np.int64),
+                "dones": np.dtype(np.bool_)}[self._field]
+
+
+class ReplayBuffer:
+    def __init__(self, buffer_size, obs_shape, ac_shape, _engine=None, _agent=0, device=0, seed=0):
+        obs_shape, ac_shape = tuple(obs_shape), tuple(ac_shape)
+        if len(obs_shape) != 2 or obs_shape[0] != buffer_size or ac_shape != (buffer_size,):
+            raise ValueError("obs_shape must be (buffer_size, D) and ac_shape (buffer_size,) "
+                             "(Test/lunar_lander.py:40-41)")
+        self._buffer_size = int(buffer_size)
+        self._obs_dim = int(obs_shape[1])
+        if _engine is None:
+            from .engine import DqnEngine
+            _engine = DqnEngine(self._obs_dim, 4, self._buffer_size, 1, 0.0, adam(0.0), device=device, seed=seed)
+        self._engine, self._agent = _engine, _agent
+        d = self._obs_dim
+        # one-transition staging arrays reused by add() (the C side copies them into a pinned slot)
+        self._s1, self._o1 = np.zeros((1, d), np.float32), np.zeros((1, d), np.float32)
+        self._a1, self._r1, self._d1 = np.zeros(1, np.int64), np.zeros(1, np.float32), np.zeros(1, np.bool_)
+        self._ptrs = tuple(_lib.ptr(x) for x in (self._s1, self._a1, self._r1, self._o1, self._d1))
+        self._counter = 0
+        self._num_samples = 0
+        self._sample_calls = 0
+
+    # -- reference surface ----------------------------------------------------------------------------
+    @property
+    def size(self):
+        return self._num_samples
+
+    states = property(lambda self: RingView(self, "states"))
+    actions = property(lambda self: RingView(self, "actions"))
+    rewards = property(lambda self: RingView(self, "rewards"))
+    observations = property(lambda self: RingView(self, "observations"))
+    dones = property(lambda self: RingView(self, "dones"))
+
+    def add(self, state, action, reward, observation, done):
+        self._s1[0] = state
+        self._a1[0] = action
+        self._r1[0] = reward
+        self._o1[0] = observation
+        self._d1[0] = done
+        e = self._engine
+        _lib.check(e.lib.dqn_store(e.h, self._agent, 1, *self._ptrs))
+        self._counter += 1
+        self._num_samples = min(self._counter, self._buffer_size)
+
+    # -- vectorised extension ------------------------------------------------------------------------
+    def add_many(self, states, actions, rewards, observations, dones):
+        """n ``add`` calls in order, as one coalesced device store."""
+        self._engine.store(states, actions, rewards, observations, dones, agent=self._agent)
+        self._counter += len(np.asarray(actions))
+        self._num_samples = min(self._counter, self._buffer_size)
+
+    def sample(self, batch_size, indices=None):
+        step = self._sample_calls
+        self._sample_calls += 1
+        return self._engine.sample_batch(batch_size, indices=indices, step=step, agent=self._agent)
+
+    def _export(self):
+        return self._engine.buffer_export(self._agent)
+
+
+def sample_batch(num_samples, states, actions, rewards, observations, dones, batch_size, indices=None):
+    """``sample_batch`` of the reference, on device-resident arrays.
+
+    The five array arguments must be the ``RingView`` properties of one ``ReplayBuffer``;
+    ``num_samples`` must be its ``size`` (the reference passes ``replay_buffer.size``,
+    ``q_agent.py:147``).  Host numpy arrays are rejected: there is no CPU path.
+    """
+    views = (states, actions, rewards, observations, dones)
+    if not all(isinstance(v, RingView) for v in views):
+        raise TypeError("sample_batch: pass the ReplayBuffer's own array properties (device-resident); "
+                        "the B200 path has no CPU gather")
+    buf = states._buffer
+    if any(v._buffer is not buf for v in views) or tuple(v._field for v in views) != _FIELDS:
+        raise ValueError("sample_batch: arrays must be (states, actions, rewards, observations, dones) of one buffer")
+    if num_samples != buf.size:
+        raise ValueError("sample_batch: num_samples must equal replay_buffer.size")
+    return buf.sample(batch_size, indices=indices)

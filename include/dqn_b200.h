@@ -1,0 +1,180 @@
+/*
+ * dqn_b200.h -- C ABI of libdqn_b200.so: the B200 (sm_100a) dueling double-DQN train-step +
+ * replay path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference (hal9000universe/deep-q-learning) has no FFI layer: its seam is the set of Python
+ * callables and the buffer object that `Agent` stores (General/QLearning/q_agent.py:93-95,110-113).
+ * Each entry point below names the reference interface it replaces.  All state (online/target
+ * parameters, Adam moments, the replay ring, per-agent counters) is device-resident and owned by an
+ * opaque handle; a handle holds `n_agents >= 1` independent agents (1 = the reference's `Agent`,
+ * >1 = a population of the hyper-parameter sweep) that never communicate.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on failure (DQN_E_*); the message is available from
+ *     dqn_last_error() (thread-local, valid until the next failing call on the thread);
+ *   - there is NO CPU fallback: without a usable sm_100a device every compute call fails;
+ *   - all work is enqueued in order on the handle's stream; calls that return data to host
+ *     pointers synchronise that stream before returning, the others do not;
+ *   - a handle is not thread-safe (neither is the reference's Agent).
+ *
+ * Flat parameter layout (P = dqn_param_count floats), the reference checkpoint's leaves in order
+ * (Test/lunar_lander/params.pickle; haiku Linear stores w as [in,out], row-major):
+ *     W1[D][H1] b1[H1] | W2[H1][H2] b2[H2] | Wv[H2][1] bv[1] | Wa[H2][A] ba[A]
+ *     'model/~/linear'   'model/~/linear_1'  'model/~/linear_2'  'model/~/linear_3'
+ */
+#ifndef DQN_B200_H
+#define DQN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DQN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DQN_API __attribute__((visibility("default")))
+#else
+#define DQN_API
+#endif
+
+enum {
+  DQN_OK = 0,
+  DQN_E_INVALID = -1,  /* bad argument / shape / state */
+  DQN_E_CUDA = -2,     /* CUDA runtime error (message carries cudaGetErrorString) */
+  DQN_E_ARCH = -3,     /* no sm_100a device / library not built for this device */
+  DQN_E_NOMEM = -4
+};
+
+enum { DQN_OPT_ADAM = 0, DQN_OPT_ADAMW = 1 };
+enum { DQN_PARAMS_ONLINE = 0, DQN_PARAMS_TARGET = 1 };
+
+/* Construction-time configuration == the part of `Agent.__init__` (q_agent.py:61-118) that shapes
+ * the hot path.  `network` becomes (obs_dim, hidden1, hidden2, num_actions) -- the dueling MLP of
+ * LunarLander/dddqn.py:17-22; `optimizer` becomes (opt_kind, lr, b1, b2, eps, eps_root,
+ * weight_decay) -- optax.adamw(2e-4) in Test/lunar_lander.py:48, optax.adam(1e-4) in
+ * Test/lunar_lander_hyper_params.py:41.  Per-agent values can be changed later (dqn_set_hparams). */
+typedef struct dqn_config {
+  int32_t struct_size;   /* sizeof(dqn_config), for ABI checking */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t n_agents;      /* independent agents in this handle (>= 1) */
+  int32_t obs_dim;       /* D, 1..16  (9 in Test/lunar_lander.py:40, 8 in the synthetic configs) */
+  int32_t num_actions;   /* A, 2..7   (env.action_space.n, Test/lunar_lander.py:42) */
+  int32_t hidden1;       /* 32  (dddqn.py:19) */
+  int32_t hidden2;       /* 64  (dddqn.py:20) */
+  int32_t batch_size;    /* B, 1..DQN_MAX_BATCH (q_agent.py:153) */
+  int64_t buffer_size;   /* N slots per agent (replay_buffer.py:25) */
+  float gamma;           /* q_agent.py:111 */
+  int32_t opt_kind;      /* DQN_OPT_ADAM / DQN_OPT_ADAMW */
+  float lr, b1, b2, eps, eps_root, weight_decay;
+  uint64_t seed;         /* Philox key for minibatch indices */
+  int32_t agent_id_base; /* global id of local agent 0: the Philox counter uses (agent_id_base + agent), */
+  int32_t reserved0;     /*   so a sharded population draws the same indices as the unsharded one       */
+  void* stream;          /* cudaStream_t to enqueue on (NULL = default stream) */
+  void* arena;           /* optional caller-allocated device memory (e.g. a torch tensor's  */
+  uint64_t arena_bytes;  /*   data_ptr()); NULL => the library allocates dqn_arena_bytes() itself */
+} dqn_config;
+
+#define DQN_MAX_BATCH 1024
+#define DQN_MAX_OBS_DIM 16
+#define DQN_MAX_ACTIONS 7
+
+typedef struct dqn_handle dqn_handle;
+
+/* Per-agent hyper-parameters that the sweep injects (ParamAgent.inject,
+ * hyperparameter_optimization.py:76-91) plus the optimiser constants.  Fields < 0 / NaN keep the
+ * current value. */
+typedef struct dqn_hparams {
+  float gamma;
+  int32_t batch_size;
+  float lr, b1, b2, eps, eps_root, weight_decay;
+} dqn_hparams;
+
+/* Optional debug taps of ONE train step (K must be 1): every intermediate the parity tests compare
+ * with the oracle.  All pointers are HOST pointers or NULL; shapes use the agent's B, A, P. */
+typedef struct dqn_debug_taps {
+  int64_t* indices;   /* [B]    sampled slots */
+  float* q;           /* [B*A]  Q(theta, s)            q_learning_functions.py:52 */
+  float* next_q;      /* [B*A]  Q(theta, s')           :53 */
+  float* next_q_tm;   /* [B*A]  Q(theta^-, s')         :54 */
+  int32_t* max_actions; /* [B]  argmax_a Q(theta, s')  :55 */
+  float* targets;     /* [B*A]  q + tv*onehot(a)       :58-59 */
+  float* loss;        /* [1]    mean_i sum_j huber     :36 */
+  float* grads;       /* [P]    d loss / d theta, flat layout   :23 */
+} dqn_debug_taps;
+
+DQN_API int dqn_abi_version(void);
+DQN_API const char* dqn_last_error(void);
+
+/* Bytes of device memory a handle with this configuration needs (for caller-side allocation). */
+DQN_API int dqn_arena_bytes(const dqn_config* cfg, uint64_t* bytes_out);
+
+/* Agent.__init__ (q_agent.py:87-113): allocates / carves state; parameters start at zero, target =
+ * online, Adam count = 0, ring empty.  ReplayBuffer.__init__ (replay_buffer.py:20-32). */
+DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out);
+DQN_API int dqn_destroy(dqn_handle* h);
+DQN_API int dqn_param_count(const dqn_handle* h, int32_t* p_out);
+DQN_API int dqn_synchronize(dqn_handle* h);
+
+/* `self._params` / `self._target_params` (q_agent.py:88,91) in the flat layout, host pointers. */
+DQN_API int dqn_set_params(dqn_handle* h, int32_t agent, int32_t which, const float* host_flat, int32_t n);
+DQN_API int dqn_get_params(dqn_handle* h, int32_t agent, int32_t which, float* host_flat, int32_t n);
+/* `self._opt_state` = ScaleByAdamState(count, mu, nu) (Test/lunar_lander/opt_state.pickle). */
+DQN_API int dqn_set_opt_state(dqn_handle* h, int32_t agent, int32_t count, const float* mu, const float* nu, int32_t n);
+DQN_API int dqn_get_opt_state(dqn_handle* h, int32_t agent, int32_t* count, float* mu, float* nu, int32_t n);
+DQN_API int dqn_set_hparams(dqn_handle* h, int32_t agent, const dqn_hparams* hp);
+DQN_API int dqn_get_hparams(dqn_handle* h, int32_t agent, dqn_hparams* hp);
+
+/* ReplayBuffer.add (replay_buffer.py:58-65), vectorised: equivalent to n scalar add() calls in order
+ * into agent's ring (slot (counter+i) % N).  Host pointers: s/s2 f32[n*D], a i64[n], r f32[n],
+ * done u8[n] (numpy bool).  Asynchronous w.r.t. the host when the pointers are pinned. */
+DQN_API int dqn_store(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a,
+              const float* r, const float* s2, const uint8_t* done);
+/* Same with DEVICE pointers (no host copy). */
+DQN_API int dqn_store_device(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a,
+                     const float* r, const float* s2, const uint8_t* done);
+/* ReplayBuffer.size / ._counter (replay_buffer.py:34-36,64-65). */
+DQN_API int dqn_buffer_state(dqn_handle* h, int32_t agent, int64_t* size_out, int64_t* counter_out);
+/* ReplayBuffer.states/.actions/.rewards/.observations/.dones (replay_buffer.py:38-56): the whole
+ * ring de-interleaved into the reference's five arrays (f32[N*D], i64[N], f32[N], f32[N*D], u8[N]). */
+DQN_API int dqn_buffer_export(dqn_handle* h, int32_t agent, float* s, int64_t* a, float* r, float* s2, uint8_t* done);
+
+/* The index draw of sample_batch (replay_buffer.py:77): B Philox4x32-10 indices in [0,size) for
+ * train step `step` of `agent` (the indices dqn_train_step uses when given none). Host pointer. */
+DQN_API int dqn_sample_indices(dqn_handle* h, int32_t agent, int64_t step, int32_t batch, int64_t* idx_out);
+/* sample_batch (replay_buffer.py:68-85): gather `batch` transitions by `idx` (host i64[batch], or
+ * NULL = Philox indices of `step`) into the reference's five output arrays (host pointers). */
+DQN_API int dqn_sample_batch(dqn_handle* h, int32_t agent, const int64_t* idx, int64_t step, int32_t batch,
+                     float* s, int64_t* a, float* r, float* s2, uint8_t* done);
+/* Device-resident variant used for throughput measurement: indices (device i64[batch] or NULL) ->
+ * device output arrays.  Enqueue only. */
+DQN_API int dqn_sample_batch_device(dqn_handle* h, int32_t agent, const int64_t* idx_dev, int64_t step, int32_t batch,
+                            float* s, int64_t* a, float* r, float* s2, uint8_t* done);
+
+/* Agent._step (q_agent.py:146-169), K times back to back for every agent in [agent_begin,
+ * agent_end): sample -> preprocessing -> compute_q_targets -> train_step, fused in one persistent
+ * kernel.  `idx` is NULL (Philox indices) or a HOST array i64[n_sel*K*B] of explicit slots
+ * (agent-major, then step).  `taps` non-NULL requires K == 1 and a single agent.  Enqueue only
+ * (unless taps are requested). */
+DQN_API int dqn_train_step(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K,
+                   const int64_t* idx, dqn_debug_taps* taps);
+/* Same, explicit indices already on the device (i64[n_sel*K*B]) -- no host copy, enqueue only. */
+DQN_API int dqn_train_step_device_idx(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K,
+                              const int64_t* idx_dev);
+/* Loss of the most recent `n` train steps of `agent` (oldest first), host pointer. */
+DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_out, int64_t* train_steps_out);
+
+/* Agent._update_target_model (q_agent.py:143-144): theta^- := theta for agents in the range. */
+DQN_API int dqn_sync_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end);
+
+/* compute_action (q_learning_functions.py:67-73) as used by Agent._policy (q_agent.py:139):
+ * greedy argmax_a Q(theta, state) for ONE state f32[D] (host pointer).  Synchronises. */
+DQN_API int dqn_act(dqn_handle* h, int32_t agent, const float* state, int32_t* action_out);
+/* Batched: agents [agent_begin, agent_end), one state each (host f32[n_sel*D] -> i32[n_sel]). */
+DQN_API int dqn_act_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* states, int32_t* actions_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQN_B200_H */
