@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- DQN train-steps/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload single|population|replay]
+
+Default workload = BASELINE.json configs[1]: single-agent fused dueling double-DQN train step,
+synthetic 1M-transition replay, batch 64, D=8, A=4, hidden (32,64), AdamW(2e-4), gamma .99 on one B200.
+A "step" is one train step (one minibatch: sample -> targets -> loss -> backward -> Adam).  The single
+agent does not shard ("replicas only"), so --gpus N runs N independent replicas, one process
+per GPU, no data-path collective; `value` = all ranks' steps / max-over-ranks device time.
+
+  value  : steps/s with everything resident in HBM, K steps fused per persistent launch
+  e2e    : steps/s through the reference-facing API (ReplayBuffer.add x train_frequency from host
+           memory, Agent._step(), loss read back) -- host<->device copies inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md "Measurement"
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, numpy; the reference's
+jax/haiku/optax runtime is not installable) on the host cores -- the one place besides cpu_baseline
+where bench.py executes oracle code, and only as the thing the GPU is compared against.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D, A, B, N_RING = 8, 4, 64, 1_000_000
+GAMMA, LR = 0.99, 2e-4
+TRAIN_FREQUENCY = 4                      # Test/lunar_lander.py:30 -- env transitions stored per train step
+REC_BYTES_ALGO = 2 * 4 * D + 8 + 4 + 1   # 77 B per sampled transition in the reference's dtypes
+FLOP_PER_SAMPLE = 25728                  # D=8, H=(32,64): 3 forwards + backward
+STEPS_PER_LAUNCH = 500
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled during the timed region (pynvml thread, 10 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10,
+                 "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(1.0)
+
+    def summary(self):
+        if not self.samples:
+            try:   # fall back to one nvidia-smi sample
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0].split(",")
+                return {"sm_mhz": int(out[0]), "sm_max_mhz": int(out[1]), "reasons": [], "samples": 1}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def synthetic(rng, n):
+    """Synthetic transitions of SURVEY 8(d): s,s'~N(0,1); a~U{0..3}; r~2N(0,1); done~Bernoulli(0.01)."""
+    s = rng.standard_normal((n, D), dtype=np.float32)
+    a = rng.integers(0, A, n, dtype=np.int64)
+    r = (2.0 * rng.standard_normal(n)).astype(np.float32)
+    s2 = rng.standard_normal((n, D), dtype=np.float32)
+    d = rng.random(n) < 0.01
+    return s, a, r, s2, d
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle restatement of Agent._step on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_steps_per_sec(max_steps, warmup, budget_s, ring=N_RING, seed=0):
+    from threadpoolctl import threadpool_limits
+    from oracle import dqn_oracle as O
+    from oracle.agent_oracle import OracleAgent
+    rng = np.random.default_rng(seed)
+    params = O.init_params(rng, D, A)
+    ora = OracleAgent(params, O.init_opt_state(params), O.OptSpec("adamw", LR), ring, D, GAMMA, B, seed=seed)
+    data = synthetic(rng, ring)
+    r = ora.replay                                              # bulk-fill (equivalent to `ring` add() calls)
+    r.states[:], r.actions[:], r.rewards[:], r.observations[:], r.dones[:] = data
+    r.counter = r.size = ring
+    best = None
+    ncores = os.cpu_count() or 1
+    for threads in sorted({1, ncores}):
+        with threadpool_limits(limits=threads):
+            for _ in range(max(warmup, 3)):
+                ora.step()
+            t0 = time.perf_counter()
+            done = 0
+            while done < max_steps and time.perf_counter() - t0 < budget_s / 2:
+                ora.step()
+                done += 1
+            dt = time.perf_counter() - t0
+        rate = done / dt
+        if best is None or rate > best[0]:
+            best = (rate, threads, done, dt)
+    return best
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    rate, threads, done, dt = cpu_reference_steps_per_sec(args.steps, args.warmup, budget_s=120.0)
+    sample = f"{done} oracle train steps (B=64, D=8, 1M-slot ring) in {dt:.1f} s, BLAS threads={threads}"
+    line = {
+        "impl": "reference", "metric": "train_steps_per_sec", "value": rate, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 / rate, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "replay_samples_per_sec": rate * B,
+        "note": "numpy restatement of the reference step (jax/haiku/optax not installable); host cores: %d" % (os.cpu_count() or 1),
+    }
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {"workload": "configs[1]: single-agent fused dueling double-DQN train step, 1M-transition synthetic replay, batch 64",
+            "obs_dim": D, "num_actions": A, "hidden": [32, 64], "batch": B, "ring_slots": N_RING, "gamma": GAMMA,
+            "optimizer": "adamw(2e-4, wd 1e-4)", "steps_per_launch": STEPS_PER_LAUNCH,
+            "multi_gpu": "replicas only (single agent does not shard)",
+            "l2": "ring 96 MB < 126 MB L2: L2 flushed (512 MB write) before each timed region; every step gathers 64 random, mostly first-touch records"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def build_agent(dqn_b200, device, seed):
+    rng = np.random.default_rng(seed)
+    model = dqn_b200.Model(A)
+    params = model.init(rng, np.zeros((1, D), np.float32))
+    opt = dqn_b200.adamw(LR)
+    agent = dqn_b200.Agent(network=model, params=params, optimizer=opt, opt_state=opt.init(params), env=None,
+                           buffer_size=N_RING, obs_shape=(N_RING, D), ac_shape=(N_RING,), gamma=GAMMA, epsilon=1.0,
+                           epsilon_decay_rate=0.99, min_epsilon=0.15, max_episodes=10000, max_steps=1500,
+                           training_start=250, batch_size=B, train_frequency=TRAIN_FREQUENCY, back_up_frequency=50,
+                           replace_frequency=20, reward_to_reach=230.0, num_actions=A,
+                           saving_directory="/tmp/dqn_b200_bench", device=device, seed=seed)
+    data = synthetic(rng, N_RING)
+    for o in range(0, N_RING, 250_000):
+        agent._replay_buffer.add_many(*[x[o:o + 250_000] for x in data])
+    agent._engine.synchronize()
+    return agent, data
+
+
+def flush_l2(torch, device):
+    buf = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    buf.fill_(1)
+    torch.cuda.synchronize(device)
+    del buf
+
+
+def timed_fused(torch, agent, steps, device):
+    """K train steps, STEPS_PER_LAUNCH per persistent launch; CUDA events on the launching stream."""
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    start.record()
+    left = steps
+    while left > 0:
+        k = min(left, STEPS_PER_LAUNCH)
+        agent._steps(k)
+        left -= k
+        launches += 1
+    end.record()
+    torch.cuda.synchronize(device)
+    return start.elapsed_time(end) * 1e-3, launches
+
+
+def run_single(args):
+    import torch
+    import dqn_b200
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    agent, data = build_agent(dqn_b200, local, seed=rank)
+    eng = agent._engine
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- value: device-resident, fused ----------------------------------------------------------
+    agent._steps(max(args.warmup, 3))
+    flush_l2(torch, device)
+    barrier()
+    with ClockSampler(local) as clk:
+        secs, launches = timed_fused(torch, agent, args.steps, device)
+    barrier()
+    clocks = clk.summary()
+    tmax = torch.tensor([secs], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    secs_max = float(tmax.item())
+    value = world * args.steps / secs_max
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "steps_per_sec": value, "launches": launches}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- e2e: reference-facing API, host buffers, copies inside the timed region ------------------
+    e2e_steps = int(min(max(args.steps // 20, 200), 5000))
+    rb = agent._replay_buffer
+    s, a, r, s2, d = [x[:TRAIN_FREQUENCY * (e2e_steps + 8)] for x in data]
+    a_py, r_py, d_py = [int(x) for x in a], [float(x) for x in r], [bool(x) for x in d]
+
+    def e2e_loop(n, off=0):
+        last = 0.0
+        for i in range(n):
+            for j in range(TRAIN_FREQUENCY):                      # q_agent.py:182  one add() per env transition
+                k = off + i * TRAIN_FREQUENCY + j
+                rb.add(s[k], a_py[k], r_py[k], s2[k], d_py[k])
+            agent._step()                                          # q_agent.py:187
+            last = float(eng.losses(1)[0])                         # device -> host read of the step's loss
+        return last
+
+    e2e_loop(8)
+    flush_l2(torch, device)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    e2e_loop(e2e_steps, off=8 * TRAIN_FREQUENCY)
+    e1.record()
+    torch.cuda.synchronize(device)
+    e2e_wall = time.perf_counter() - t0
+    e2e_secs = max(e0.elapsed_time(e1) * 1e-3, e2e_wall)
+    te = torch.tensor([e2e_secs], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (dqn_train_fused_kernel), measured live ---------------
+    peak, peak_src = measured_peaks()
+    launch_s = secs / launches
+    steps_per_launch = args.steps / launches
+    algo_bytes = steps_per_launch * (B * REC_BYTES_ALGO + 4)          # gathered records + one loss store per step
+    achieved = algo_bytes / launch_s / 1e9
+    sm_hz = (clocks["sm_mhz"] or 1965) * 1e6
+    fp32_one_sm = 128 * 2 * sm_hz / 1e9
+    flops = B * FLOP_PER_SAMPLE / (secs / args.steps) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "dqn_train_fused_kernel<4>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": launch_s * 1e3,
+                "note": "latency-bound by construction: one agent = one CTA on one SM; theta/theta^-/grads stay in shared memory, "
+                        "so the only HBM traffic is 64 gathered records per step (prefetched one step ahead)",
+                "fp32": {"achieved_gflops": flops, "one_sm_ffma_peak_gflops": fp32_one_sm, "frac_of_one_sm": flops / fp32_one_sm,
+                         "flop_per_step": B * FLOP_PER_SAMPLE}}
+
+    # ---- K=1 launches (launch-bound variant) and replay-gather throughput, for the record -----------
+    extras = {}
+    try:
+        k1 = 2000
+        agent._steps(1)
+        torch.cuda.synchronize(device)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(k1):
+            agent._step()
+        s1.record()
+        torch.cuda.synchronize(device)
+        extras["k1_steps_per_sec"] = k1 / (s0.elapsed_time(s1) * 1e-3)
+        extras["replay_gather"] = bench_gather(torch, dqn_b200, eng, device, peak)
+    except Exception as ex:       # extras never invalidate the main line
+        extras["error"] = repr(ex)
+
+    # ---- CPU baseline (oracle port on the host cores), bounded sample ---------------------------------
+    rate, threads, done, dt = cpu_reference_steps_per_sec(20000, 50, budget_s=30.0)
+    cpu = {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
+           "sample": f"{done} oracle train steps (same workload) in {dt:.1f} s, BLAS threads={threads}, host cores={os.cpu_count()}"}
+
+    line = {
+        "metric": "train_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": TRAIN_FREQUENCY * REC_BYTES_ALGO,
+                "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                "api": "ReplayBuffer.add x4 (host numpy) + Agent._step() + loss readback per step"},
+        "gpu_launches": launches, "replay_samples_per_sec": value * B,
+        "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_gather(torch, dqn_b200, eng, device, peak):
+    """sample_batch as a standalone HBM-bound kernel: 65536 Philox-indexed samples per launch from the
+    1M-slot ring into SoA outputs (reads 77 B + writes 77 B algorithmic per sample)."""
+    import ctypes as C
+    nb = 65536
+    outs = [torch.empty(nb * D, dtype=torch.float32, device=device), torch.empty(nb, dtype=torch.int64, device=device),
+            torch.empty(nb, dtype=torch.float32, device=device), torch.empty(nb * D, dtype=torch.float32, device=device),
+            torch.empty(nb, dtype=torch.uint8, device=device)]
+    lib, chk = eng.lib, dqn_b200.pkg._lib.check
+    ptrs = [C.c_void_p(t.data_ptr()) for t in outs]
+    for i in range(5):
+        chk(lib.dqn_sample_batch_device(eng.h, 0, None, i, nb, *ptrs))
+    flush_l2(torch, device)
+    reps = 50
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(reps):
+        chk(lib.dqn_sample_batch_device(eng.h, 0, None, 100 + i, nb, *ptrs))
+    s1.record()
+    torch.cuda.synchronize(device)
+    dt = s0.elapsed_time(s1) * 1e-3 / reps
+    gbs = nb * 2 * REC_BYTES_ALGO / dt / 1e9
+    return {"samples_per_sec": nb / dt, "batch": nb, "us_per_launch": dt * 1e6, "achieved_gbs": gbs,
+            "frac_of_hbm_peak": gbs / peak, "note": "ring (96 MB) fits in L2; see profiles/ for the >L2 ring measurement"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200_000)
+    ap.add_argument("--warmup", type=int, default=2_000)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling aid (ncu): only the fused timed region, no e2e / extras / cpu baseline; not a bench value")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    _, world, _ = dist_env()
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_single(args)
+
+
+if __name__ == "__main__":
+    main()

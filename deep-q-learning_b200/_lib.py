@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdqn_b200.so")
+LIB_PATH = os.environ.get("DQN_B200_LIB") or os.path.join(_HERE, "csrc", "libdqn_b200.so")   # env override: A/B kernel variants only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dqn_b200.h")
 
 DQN_OPT_ADAM, DQN_OPT_ADAMW = 0, 1

@@ -568,10 +568,15 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
   if (n == 0) return DQN_OK;
   if (n < 0 || n > kLossCap || n > ts || !loss_out) return fail(DQN_E_INVALID, "dqn_get_losses: n must be <= min(train steps so far, 4096)");
   CU(cudaSetDevice(h->cfg.device));
-  std::vector<float> ring(kLossCap);
-  CU(cudaMemcpyAsync(ring.data(), h->loss_ring + (size_t)agent * kLossCap, kLossCap * 4, cudaMemcpyDeviceToHost, h->stream));
+  // the last n losses are at ring positions [(ts-n) % cap, ts % cap): at most two contiguous pieces
+  const size_t first = (size_t)((ts - n) % kLossCap);
+  const size_t n1 = first + (size_t)n <= (size_t)kLossCap ? (size_t)n : (size_t)kLossCap - first;
+  const float* src = h->loss_ring + (size_t)agent * kLossCap;
+  float* dst = (size_t)n * 4 <= kBounceBytes ? (float*)h->bounce : loss_out;   // pinned bounce keeps small reads cheap
+  CU(cudaMemcpyAsync(dst, src + first, n1 * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (n1 < (size_t)n) CU(cudaMemcpyAsync(dst + n1, src, ((size_t)n - n1) * 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  for (int i = 0; i < n; ++i) loss_out[i] = ring[(size_t)((ts - n + i) % kLossCap)];
+  if (dst != loss_out) memcpy(loss_out, dst, (size_t)n * 4);
   return DQN_OK;
 }
 

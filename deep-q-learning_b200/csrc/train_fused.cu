@@ -13,7 +13,7 @@
 // gathered records (one 96-byte record per sample for D <= 10) and one 4-byte loss.
 //
 // Shared-memory layouts
-//   weights ("smem layout"): [W1;b1] (D+1 x 32) | [W2;b2] (33 x 64) | [Wv Wa | bias row] (65 x 8),
+//   weights ("smem layout"): [W1;b1] (D+1 x 32) | [W2;b2] (33 x 64, row stride 68) | [Wv Wa | bias row] (65 x 8),
 //       i.e. bias = last row of each augmented matrix; head columns: 0 = V, 1..A = advantage, rest 0.
 //   activations: k-major ("transposed") [feature][row] with row strides 132 (two 64-row halves) or
 //       68; strides are = 4 (mod 32) words so 16-byte accesses of 8 consecutive rows hit 8 distinct
@@ -34,17 +34,25 @@ constexpr int BT = 64;           // batch rows per tile
 constexpr int RS2 = 2 * BT + 4;  // 132
 constexpr int RS1 = BT + 4;      // 68
 constexpr int HC = 8;            // padded head width
-constexpr int NPT = 13;          // ceil(max smem-layout params / NT), D = 16: (17*32 + 33*64 + 65*8) = 3176
+constexpr int WS2 = kH2 + 4;     // row stride of the [W2;b2] block in smem (68: rows 4 banks apart)
+constexpr int NPT = 13;
+#ifndef DQN_FFMA2
+#define DQN_FFMA2 1
+#endif
+#ifndef DQN_OP_UNROLL
+#define DQN_OP_UNROLL 8
+#endif
+constexpr int kOpUnroll = DQN_OP_UNROLL;          // ceil(max smem-layout params / NT), D = 16: (17*32 + 33*64 + 65*8) = 3176
 
 struct Lay {   // offsets in floats
   int pW2, pWh, PS;
-  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oQB, oScr, oAct, oRew, oDone, oRed, oStage, total;
+  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oQB, oScr, oMeta, oDummy, oRed, oStage, total;
 };
 
 __host__ __device__ inline Lay make_layout(int D, int recw) {
   Lay L;
   L.pW2 = (D + 1) * kH1;
-  L.pWh = L.pW2 + (kH1 + 1) * kH2;
+  L.pWh = L.pW2 + (kH1 + 1) * WS2;
   L.PS = L.pWh + (kH2 + 1) * HC;
   const int PSa = (L.PS + 3) & ~3;
   int o = 0;
@@ -60,9 +68,8 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
   L.oDhdT = o; o += HC * RS1;
   L.oQB = o; o += BT * HC;
   L.oScr = o; o += 3 * BT * 2 * HC;
-  L.oAct = o; o += BT;
-  L.oRew = o; o += BT;
-  L.oDone = o; o += BT;
+  L.oMeta = o; o += BT * 4;
+  L.oDummy = o; o += 4;
   L.oRed = o; o += 32;
   L.oStage = o; o += BT * recw;
   L.total = o;
@@ -71,10 +78,15 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
 
 // smem-layout index -> flat-layout index (-1 = padding)
 __device__ __forceinline__ int smem_to_flat(int p, int D, int A, const Lay& L) {
-  if (p < L.pWh) return p;   // [W1;b1] and [W2;b2] are contiguous in both layouts
+  if (p < L.pW2) return p;   // [W1;b1] is contiguous in both layouts
+  const int offWv = L.pW2 + (kH1 + 1) * kH2;   // flat offset of Wv = D*32+32+32*64+64
+  if (p < L.pWh) {           // [W2;b2]: smem rows are padded to WS2
+    const int q = p - L.pW2;
+    const int row = q / WS2, col = q - row * WS2;
+    return col < kH2 ? L.pW2 + row * kH2 + col : -1;
+  }
   const int q = p - L.pWh;
   const int k = q >> 3, c = q & 7;
-  const int offWv = L.pWh;                 // flat offset of Wv = D*32+32+32*64+64
   const int offbv = offWv + kH2;
   const int offWa = offbv + 1;
   const int offba = offWa + kH2 * A;
@@ -95,58 +107,133 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 
-// Outer-product-form tile: acc[i][j] (+)= sum_k A[k*lda + i] * Bw[k*ldb + j], i < 4, j < TN.
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2: two IEEE fp32 FMAs per lane per issue slot) ----
+typedef unsigned long long u64;
+struct u64x2 { u64 lo, hi; };
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) {
+#if DQN_FFMA2
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+#else
+  float dl, dh, al, ah, bl, bh;
+  unpack2(d, dl, dh); unpack2(a, al, ah); unpack2(b, bl, bh);
+  d = pack2(fmaf(al, bl, dl), fmaf(ah, bh, dh));
+#endif
+}
+__device__ __forceinline__ u64x2 ld2x64(const float* p) {   // one LDS.128 into two 64-bit register pairs
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+  return u64x2{v.x, v.y};
+}
+__device__ __forceinline__ u64 ld64(const float* p) { return *reinterpret_cast<const u64*>(p); }
+
+// Outer-product-form tile (forward GEMMs):  C[m0+i][n0+j] (+)= sum_k A[k*lda + i] * Bw[k*ldb + j],
+// i < 4, j < TN.  Accumulators are packed pairs along j.  Software-pipelined: the operands of step
+// k+1 are loaded before the FMAs of step k issue (row K of both operands is always mapped smem).
 template <int TN>
 __device__ __forceinline__ void op_tile4(const float* __restrict__ A, int lda, const float* __restrict__ Bw, int ldb,
-                                         int K, float (&acc)[4][TN]) {
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float4 a4 = ld4(A + k * lda);
-    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-    float b[TN];
-    if constexpr (TN == 2) {
-      const float2 b2 = *reinterpret_cast<const float2*>(Bw + k * ldb);
-      b[0] = b2.x; b[1] = b2.y;
-    } else {
+                                         int K, u64 (&acc)[4][TN / 2]) {
+  float4 an = ld4(A);
+  u64 bn[TN / 2];
+  if constexpr (TN == 2) bn[0] = ld64(Bw);
+  else {
 #pragma unroll
-      for (int j4 = 0; j4 < TN / 4; ++j4) {
-        const float4 b4 = ld4(Bw + k * ldb + 4 * j4);
-        b[4 * j4 + 0] = b4.x; b[4 * j4 + 1] = b4.y; b[4 * j4 + 2] = b4.z; b[4 * j4 + 3] = b4.w;
-      }
+    for (int q = 0; q < TN / 4; ++q) { const u64x2 v = ld2x64(Bw + 4 * q); bn[2 * q] = v.lo; bn[2 * q + 1] = v.hi; }
+  }
+#pragma unroll kOpUnroll
+  for (int k = 0; k < K; ++k) {
+    const float4 a = an;
+    u64 b[TN / 2];
+#pragma unroll
+    for (int q = 0; q < TN / 2; ++q) b[q] = bn[q];
+    an = ld4(A + (k + 1) * lda);
+    if constexpr (TN == 2) bn[0] = ld64(Bw + (k + 1) * ldb);
+    else {
+#pragma unroll
+      for (int q = 0; q < TN / 4; ++q) { const u64x2 v = ld2x64(Bw + (k + 1) * ldb + 4 * q); bn[2 * q] = v.lo; bn[2 * q + 1] = v.hi; }
     }
+    const u64 ad[4] = {pack2(a.x, a.x), pack2(a.y, a.y), pack2(a.z, a.z), pack2(a.w, a.w)};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int q = 0; q < TN / 2; ++q) ffma2(acc[i][q], ad[i], b[q]);
   }
 }
 
-// Dot-form tile over 64 reduction elements (16 chunks of 4):
-// acc[i][j] += sum_r A[(m0 + i*ms)*lda + r] * Bm[(n0 + j*ns)*ldb + r]
-template <int TM, int TN>
-__device__ __forceinline__ void dot_tile(const float* __restrict__ A, int lda, int m0, int ms,
-                                         const float* __restrict__ Bm, int ldb, int n0, int ns,
-                                         int chunk0, int nchunks, float (&acc)[TM][TN]) {
-#pragma unroll 2
-  for (int c = chunk0; c < chunk0 + nchunks; ++c) {
-    float4 a[TM], b[TN];
+// bias-initialised accumulators, relu, k-major store of a 4 x TN tile
+template <int TN>
+__device__ __forceinline__ void op_init(const float* __restrict__ bias, u64 (&acc)[4][TN / 2]) {
 #pragma unroll
-    for (int i = 0; i < TM; ++i) a[i] = ld4(A + (m0 + i * ms) * lda + 4 * c);
+  for (int q = 0; q < TN / 2; ++q) {
+    const u64 b = ld64(bias + 2 * q);
 #pragma unroll
-    for (int j = 0; j < TN; ++j) b[j] = ld4(Bm + (n0 + j * ns) * ldb + 4 * c);
+    for (int i = 0; i < 4; ++i) acc[i][q] = b;
+  }
+}
+template <int TN>
+__device__ __forceinline__ void op_store_relu(float* __restrict__ C, int ldc, const u64 (&acc)[4][TN / 2]) {
+#pragma unroll
+  for (int q = 0; q < TN / 2; ++q) {
+    float lo[4], hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack2(acc[i][q], lo[i], hi[i]);
+    st4(C + (2 * q) * ldc, fmaxf(lo[0], 0.f), fmaxf(lo[1], 0.f), fmaxf(lo[2], 0.f), fmaxf(lo[3], 0.f));
+    st4(C + (2 * q + 1) * ldc, fmaxf(hi[0], 0.f), fmaxf(hi[1], 0.f), fmaxf(hi[2], 0.f), fmaxf(hi[3], 0.f));
+  }
+}
+
+// Dot-form tile (gradient GEMMs) over NCH chunks of 4 reduction elements:
+//   out[i][j] = sum_r ap[i][r] * bp[j][r],  r in [0, 4*NCH)
+// ap / bp are per-thread row base pointers, so every load is [register + immediate].  The packed
+// accumulator holds the (even, odd) partial sums; loads of chunk c+1 are issued before the FMAs of c.
+template <int TM, int TN, int NCH>
+__device__ __forceinline__ void dot_tile(const float* const (&ap)[TM], const float* const (&bp)[TN], float (&out)[TM][TN]) {
+  u64 acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0ull;
+  u64x2 an[TM], bn[TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) an[i] = ld2x64(ap[i]);
+#pragma unroll
+  for (int j = 0; j < TN; ++j) bn[j] = ld2x64(bp[j]);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    u64x2 a[TM], b[TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) a[i] = an[i];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) b[j] = bn[j];
+    if (c + 1 < NCH) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i) an[i] = ld2x64(ap[i] + 4 * (c + 1));
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bn[j] = ld2x64(bp[j] + 4 * (c + 1));
+    }
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        float v = acc[i][j];
-        v = fmaf(a[i].x, b[j].x, v);
-        v = fmaf(a[i].y, b[j].y, v);
-        v = fmaf(a[i].z, b[j].z, v);
-        v = fmaf(a[i].w, b[j].w, v);
-        acc[i][j] = v;
-      }
+      for (int j = 0; j < TN; ++j) ffma2(acc[i][j], a[i].lo, b[j].lo);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) ffma2(acc[i][j], a[i].hi, b[j].hi);
   }
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) { float lo, hi; unpack2(acc[i][j], lo, hi); out[i][j] = lo + hi; }
 }
+
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -176,12 +263,10 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   float* const Dh2R = sm + L.oDh2R; // [64 r][68]
   float* const Dh1T = sm + L.oDh1T; // [32 k][68]
   float* const DhdT = sm + L.oDhdT; // [8 c][68]
-  float* const QB = sm + L.oQB;     // [64][8]   Q(theta^-, s')
-  float* const Scr = sm + L.oScr;   // head split-K partials
-  int* const Act = reinterpret_cast<int*>(sm + L.oAct);
-  float* const Rew = sm + L.oRew;
-  float* const Done = sm + L.oDone;
-  float* const Red = sm + L.oRed;   // [0..1] loss partials, [8..11] Adam bias corrections (double-buffered)
+  float* const QB = sm + L.oQB;     // [8 j][64 i]   Q(theta^-, s')
+  float* const Scr = sm + L.oScr;   // head split-K partials, [part][s|s'][c][i]
+  float* const Meta = sm + L.oMeta; // [64][4]  raw action lo, action hi, reward, done
+  float* const Red = sm + L.oRed;   // [0..1] loss partials, [8..11] Adam bias corrections, [16..31] head-bias partials
   float* const Stage = sm + L.oStage;
 
   float* const gW = args.params + (size_t)agent * 4 * PF;
@@ -218,54 +303,63 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   const float fB = (float)B;
   const int cpr = recw >> 2;
 
+  // Record word -> smem destination of this thread's staged chunks (fixed for the whole launch):
+  // thread t owns 16-byte chunks (t&3), (t&3)+4, (t&3)+8 of staged row t>>2.
+  const int urow = t >> 2, ul4 = t & 3;
+  int udst[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const int wd = 4 * (ul4 + 4 * (q >> 2)) + (q & 3);
+    int o = L.oDummy;
+    if (wd < D) o = L.oX + wd * RS2 + urow;
+    else if (wd < 2 * D) o = L.oX + (wd - D) * RS2 + BT + urow;
+    else if (wd < 2 * D + 4) o = L.oMeta + urow * 4 + (wd - 2 * D);
+    udst[q] = o;
+  }
+
   // gather of (step kstep, tile) into the staging buffer; 4 lanes per row, 16-byte cp.async each
   auto prefetch = [&](int kstep, int tile) {
-    const int row = t >> 2, l4 = t & 3;
-    const int i = tile * BT + row;
-    float* dst = Stage + row * recw;
+    const int i = tile * BT + urow;
+    float* dst = Stage + urow * recw;
     if (i < B) {
       long long slot;
       if (args.idx) slot = args.idx[((size_t)sel * args.K + kstep) * B + i];
       else slot = philox_index(args.seed, args.agent_id_base + agent, step0 + kstep, i, size);
       const uint32_t* src = ring + slot * recw;
-      for (int c = l4; c < cpr; c += 4) cp_async16(dst + 4 * c, src + 4 * c);
-      if (args.taps.enabled && l4 == 0 && args.taps.indices) args.taps.indices[i] = slot;
+      for (int c = ul4; c < cpr; c += 4) cp_async16(dst + 4 * c, src + 4 * c);
+      if (args.taps.enabled && ul4 == 0 && args.taps.indices) args.taps.indices[i] = slot;
     } else {
-      for (int c = l4; c < cpr; c += 4) st4(dst + 4 * c, 0.f, 0.f, 0.f, 0.f);
+      for (int c = ul4; c < cpr; c += 4) st4(dst + 4 * c, 0.f, 0.f, 0.f, 0.f);
     }
     cp_async_commit();
   };
 
+  double pb1 = 1.0, pb2 = 1.0;   // b1**count, b2**count (thread 0 only)
+  if (t == 0) { pb1 = pow((double)b1, (double)count0); pb2 = pow((double)b2, (double)count0); }
+
   prefetch(0, 0);
 
   for (int kstep = 0; kstep < args.K; ++kstep) {
-    const int count = (count0 > 0x7fffffff - 1 - kstep) ? 0x7fffffff : count0 + kstep + 1;   // safe_int32_increment
     if (t == 0) {
-      // optax bias correction 1 - decay**count, decay**count correctly rounded to fp32 (see oracle pow_f32)
-      // (double-buffered by step parity: slower warps may still be reading the previous step's pair)
-      Red[8 + 2 * (kstep & 1)] = 1.0f - (float)pow((double)b1, (double)count);
-      Red[9 + 2 * (kstep & 1)] = 1.0f - (float)pow((double)b2, (double)count);
+      // optax bias correction 1 - decay**count with decay**count rounded once to fp32 (oracle pow_f32).
+      // decay**count is carried in double across the fused steps (one DMUL per step instead of a pow()).
+      // Double-buffered by step parity: slower warps may still be reading the previous step's pair.
+      if (count0 + kstep < 0x7fffffff) { pb1 *= (double)b1; pb2 *= (double)b2; }   // safe_int32_increment saturates
+      Red[8 + 2 * (kstep & 1)] = 1.0f - (float)pb1;
+      Red[9 + 2 * (kstep & 1)] = 1.0f - (float)pb2;
     }
     float loss_acc = 0.f;   // meaningful in warps 0,1
 
     for (int tile = 0; tile < ntiles; ++tile) {
-      // ---- unpack staged records: preprocessing (q_learning_functions.py:76-85) ------------
+      // ---- unpack staged records (k-major X, raw meta words): part of preprocessing (:76-85) ----
       cp_async_wait_all();
       __syncthreads();
-      {
-        const int nw = 2 * D + 4;
-        for (int rr = 0; rr < 8; ++rr) {
-          const int row = warp * 8 + rr;
-          for (int wd = lane; wd < nw; wd += 32) {
-            const float v = Stage[row * recw + wd];
-            if (wd < D) X[wd * RS2 + row] = v;
-            else if (wd < 2 * D) X[(wd - D) * RS2 + BT + row] = v;
-            else if (wd == 2 * D) {
-              int a = __float_as_int(v);
-              Act[row] = a < 0 ? 0 : (a >= A ? A - 1 : a);   // jax clamps out-of-range gather indices
-            } else if (wd == 2 * D + 2) Rew[row] = v;
-            else if (wd == 2 * D + 3) Done[row] = __float_as_uint(v) ? 1.f : 0.f;   // dones.astype(float32)
-          }
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int c = ul4 + 4 * cc;
+        if (c < cpr) {
+          const float4 v = ld4(Stage + urow * recw + 4 * c);
+          sm[udst[4 * cc + 0]] = v.x; sm[udst[4 * cc + 1]] = v.y; sm[udst[4 * cc + 2]] = v.z; sm[udst[4 * cc + 3]] = v.w;
         }
       }
       __syncthreads();
@@ -274,117 +368,114 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
 
       // ================= batch B: Q(theta^-, s')  (q_learning_functions.py:54) ==============
       {  // layer 1: rows = s' (X cols 64..127) -> H1 cols 0..63
-        const int mt = t & 15, nt = t >> 4;
-        const int m0 = 4 * mt, n0 = 2 * nt;
-        float acc[4][2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) { const float bias = Wt[D * kH1 + n0 + j];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i][j] = bias; }
+        const int m0 = 4 * (t & 15), n0 = 2 * (t >> 4);
+        u64 acc[4][1];
+        op_init<2>(Wt + D * kH1 + n0, acc);
         op_tile4<2>(X + BT + m0, RS2, Wt + n0, kH1, D, acc);
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          st4(H1 + (n0 + j) * RS2 + m0, fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
+        op_store_relu<2>(H1 + n0 * RS2 + m0, RS2, acc);
       }
       __syncthreads();
       {  // layer 2
-        const int mt = t & 15, nt = t >> 4;
-        const int m0 = 4 * mt, n0 = 4 * nt;
-        float acc[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float bias = Wt[L.pW2 + kH1 * kH2 + n0 + j];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i][j] = bias; }
-        op_tile4<4>(H1 + m0, RS2, Wt + L.pW2 + n0, kH2, kH1, acc);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st4(H2 + (n0 + j) * RS2 + m0, fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
+        const int m0 = 4 * (t & 15), n0 = 4 * (t >> 4);
+        u64 acc[4][2];
+        op_init<4>(Wt + L.pW2 + kH1 * WS2 + n0, acc);
+        op_tile4<4>(H1 + m0, RS2, Wt + L.pW2 + n0, WS2, kH1, acc);
+        op_store_relu<4>(H2 + n0 * RS2 + m0, RS2, acc);
       }
       __syncthreads();
-      {  // head, split-K over 4 thread groups
+      {  // head, split-K over 4 thread groups; packed pairs over head columns (col 0 = V, 1..A = advantage)
         const int i = t & 63, part = t >> 6;
-        float acc[1 + A];
+        constexpr int NP = (A + 2) / 2;
+        u64 acc2[NP];
 #pragma unroll
-        for (int c = 0; c <= A; ++c) acc[c] = part == 0 ? Wt[L.pWh + kH2 * HC + c] : 0.f;
+        for (int q = 0; q < NP; ++q) acc2[q] = part == 0 ? ld64(Wt + L.pWh + kH2 * HC + 2 * q) : 0ull;
         const float* wh = Wt + L.pWh;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = 16 * part; k < 16 * part + 16; ++k) {
           const float h = H2[k * RS2 + i];
-#pragma unroll
-          for (int c = 0; c <= A; ++c) acc[c] = fmaf(h, wh[k * HC + c], acc[c]);
+          const u64 hh = pack2(h, h);
+          const u64x2 w0 = ld2x64(wh + k * HC);
+          ffma2(acc2[0], hh, w0.lo);
+          if constexpr (NP > 1) ffma2(acc2[1], hh, w0.hi);
+          if constexpr (NP > 2) { const u64x2 w1 = ld2x64(wh + k * HC + 4); ffma2(acc2[2], hh, w1.lo); if constexpr (NP > 3) ffma2(acc2[3], hh, w1.hi); }
         }
+        float acc[2 * NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) unpack2(acc2[q], acc[2 * q], acc[2 * q + 1]);
         if (part > 0) {
 #pragma unroll
-          for (int c = 0; c <= A; ++c) Scr[((part - 1) * BT + i) * HC + c] = acc[c];
+          for (int c = 0; c <= A; ++c) Scr[((part - 1) * HC + c) * BT + i] = acc[c];
         }
         __syncthreads();
         if (part == 0) {
 #pragma unroll
           for (int p = 0; p < 3; ++p)
 #pragma unroll
-            for (int c = 0; c <= A; ++c) acc[c] += Scr[(p * BT + i) * HC + c];
+            for (int c = 0; c <= A; ++c) acc[c] += Scr[(p * HC + c) * BT + i];
           float msum = 0.f;
 #pragma unroll
           for (int j = 1; j <= A; ++j) msum += acc[j];
           const float mean = msum / (float)A;
 #pragma unroll
-          for (int j = 0; j < A; ++j) QB[i * HC + j] = acc[0] + acc[1 + j] - mean;   // dddqn.py:31
+          for (int j = 0; j < A; ++j) QB[j * BT + i] = acc[0] + acc[1 + j] - mean;   // dddqn.py:31
         }
       }
-      // (no barrier needed here: the next phase writes H1 only; QB/Scr are re-read after later barriers)
+      // (no barrier: the next phase writes H1 only; QB / Scr are touched again only after later barriers)
 
       // ================= batch A: Q(theta, s) and Q(theta, s')  (:52-53) ====================
       {  // layer 1: 128 rows
-        const int mt = t & 31, nt = t >> 5;
-        const int m0 = 4 * mt, n0 = 4 * nt;
-        float acc[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float bias = W[D * kH1 + n0 + j];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i][j] = bias; }
+        const int m0 = 4 * (t & 31), n0 = 4 * (t >> 5);
+        u64 acc[4][2];
+        op_init<4>(W + D * kH1 + n0, acc);
         op_tile4<4>(X + m0, RS2, W + n0, kH1, D, acc);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st4(H1 + (n0 + j) * RS2 + m0, fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
+        op_store_relu<4>(H1 + n0 * RS2 + m0, RS2, acc);
       }
       __syncthreads();
-      {  // layer 2: 128 rows x 64
-        const int mt = t & 31, nt = t >> 5;
-        const int m0 = 4 * mt, n0 = 8 * nt;
-        float acc[4][8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const float bias = W[L.pW2 + kH1 * kH2 + n0 + j];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i][j] = bias; }
-        op_tile4<8>(H1 + m0, RS2, W + L.pW2 + n0, kH2, kH1, acc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          st4(H2 + (n0 + j) * RS2 + m0, fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
+      {  // layer 2: 128 rows x 64; a warp covers 64 rows x 16 columns (4 smem wavefronts per k-step)
+        const int m0 = 4 * ((lane & 15) + 16 * (warp & 1)), n0 = 8 * ((lane >> 4) + 2 * (warp >> 1));
+        u64 acc[4][4];
+        op_init<8>(W + L.pW2 + kH1 * WS2 + n0, acc);
+        op_tile4<8>(H1 + m0, RS2, W + L.pW2 + n0, WS2, kH1, acc);
+        op_store_relu<8>(H2 + n0 * RS2 + m0, RS2, acc);
       }
       __syncthreads();
       {  // head for rows i (s) and 64+i (s'), split-K; then targets / loss / d(head) on part 0
         const int i = t & 63, part = t >> 6;
-        float as[1 + A], an[1 + A];
+        constexpr int NP = (A + 2) / 2;
+        u64 as2[NP], an2[NP];
 #pragma unroll
-        for (int c = 0; c <= A; ++c) as[c] = an[c] = part == 0 ? W[L.pWh + kH2 * HC + c] : 0.f;
+        for (int q = 0; q < NP; ++q) as2[q] = an2[q] = part == 0 ? ld64(W + L.pWh + kH2 * HC + 2 * q) : 0ull;
         const float* wh = W + L.pWh;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = 16 * part; k < 16 * part + 16; ++k) {
           const float hs = H2[k * RS2 + i];
           const float hn = H2[k * RS2 + BT + i];
-#pragma unroll
-          for (int c = 0; c <= A; ++c) { const float w = wh[k * HC + c]; as[c] = fmaf(hs, w, as[c]); an[c] = fmaf(hn, w, an[c]); }
+          const u64 hs2 = pack2(hs, hs), hn2 = pack2(hn, hn);
+          const u64x2 w0 = ld2x64(wh + k * HC);
+          ffma2(as2[0], hs2, w0.lo); ffma2(an2[0], hn2, w0.lo);
+          if constexpr (NP > 1) { ffma2(as2[1], hs2, w0.hi); ffma2(an2[1], hn2, w0.hi); }
+          if constexpr (NP > 2) {
+            const u64x2 w1 = ld2x64(wh + k * HC + 4);
+            ffma2(as2[2], hs2, w1.lo); ffma2(an2[2], hn2, w1.lo);
+            if constexpr (NP > 3) { ffma2(as2[3], hs2, w1.hi); ffma2(an2[3], hn2, w1.hi); }
+          }
         }
+        float as[2 * NP], an[2 * NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { unpack2(as2[q], as[2 * q], as[2 * q + 1]); unpack2(an2[q], an[2 * q], an[2 * q + 1]); }
         if (part > 0) {
 #pragma unroll
-          for (int c = 0; c <= A; ++c) { Scr[(((part - 1) * BT + i) * 2 + 0) * HC + c] = as[c]; Scr[(((part - 1) * BT + i) * 2 + 1) * HC + c] = an[c]; }
+          for (int c = 0; c <= A; ++c) {
+            Scr[(((part - 1) * 2 + 0) * HC + c) * BT + i] = as[c];
+            Scr[(((part - 1) * 2 + 1) * HC + c) * BT + i] = an[c];
+          }
         }
         __syncthreads();
         if (part == 0) {
 #pragma unroll
           for (int p = 0; p < 3; ++p)
 #pragma unroll
-            for (int c = 0; c <= A; ++c) { as[c] += Scr[((p * BT + i) * 2 + 0) * HC + c]; an[c] += Scr[((p * BT + i) * 2 + 1) * HC + c]; }
+            for (int c = 0; c <= A; ++c) { as[c] += Scr[((p * 2 + 0) * HC + c) * BT + i]; an[c] += Scr[((p * 2 + 1) * HC + c) * BT + i]; }
           float ms = 0.f, mn = 0.f;
 #pragma unroll
           for (int j = 1; j <= A; ++j) { ms += as[j]; mn += an[j]; }
@@ -396,11 +487,15 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
           int astar = 0; float best = nq[0];
 #pragma unroll
           for (int j = 1; j < A; ++j) if (nq[j] > best) { best = nq[j]; astar = j; }   // first max wins
-          const int a = Act[i];
-          float qa = q[0], nqt = QB[i * HC + 0];
+          const float4 meta = ld4(Meta + 4 * i);
+          int a = __float_as_int(meta.x);
+          a = a < 0 ? 0 : (a >= A ? A - 1 : a);                 // jax clamps out-of-range gather indices
+          const float rew = meta.z;
+          const float done = __float_as_uint(meta.w) ? 1.f : 0.f;   // dones.astype(float32), :84
+          float qa = q[0], nqt = QB[i];
 #pragma unroll
-          for (int j = 1; j < A; ++j) { if (j == a) qa = q[j]; if (j == astar) nqt = QB[i * HC + j]; }
-          const float tv = Rew[i] + (1.0f - Done[i]) * (gamma * nqt - qa);      // :58 (F5 quirk kept)
+          for (int j = 1; j < A; ++j) { if (j == a) qa = q[j]; if (j == astar) nqt = QB[j * BT + i]; }
+          const float tv = rew + (1.0f - done) * (gamma * nqt - qa);              // :58 (F5 quirk kept)
           const float tgt = qa + tv;                                            // :59
           // ---- compute_loss (:35-36) with pred == q ----
           const float e = qa - tgt;
@@ -420,11 +515,12 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
             DhdT[(1 + j) * RS1 + i] = dadv;
             dsum[1 + j] = dadv;
           }
-          // head-bias gradient = column sums of d(head): warp shuffle + one shared atomic per warp
+          // head-bias gradient = column sums of d(head): warp shuffle, then a fixed-order add of the two
+          // warps' sums in the next phase (no atomics anywhere: results are run-to-run bit-identical)
 #pragma unroll
           for (int c = 0; c <= A; ++c) {
             const float s = warp_sum(dsum[c]);
-            if (lane == 0) atomicAdd(&G[L.pWh + kH2 * HC + c], s);
+            if (lane == 0) Red[16 + warp * 8 + c] = s;
           }
           loss_acc += warp_sum(l);
           if (args.taps.enabled && valid) {
@@ -433,7 +529,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
             for (int j = 0; j < A; ++j) {
               if (args.taps.q) args.taps.q[gi_row * A + j] = q[j];
               if (args.taps.next_q) args.taps.next_q[gi_row * A + j] = nq[j];
-              if (args.taps.next_q_tm) args.taps.next_q_tm[gi_row * A + j] = QB[i * HC + j];
+              if (args.taps.next_q_tm) args.taps.next_q_tm[gi_row * A + j] = QB[j * BT + i];
               if (args.taps.targets) args.taps.targets[gi_row * A + j] = (j == a) ? tgt : q[j];
             }
             if (args.taps.max_actions) args.taps.max_actions[gi_row] = astar;
@@ -445,11 +541,15 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
       // ================= backward (jax.grad(compute_loss), :23) =============================
       {  // dh2[r][j] = relu'(h2) * sum_c dhd[r][c] * Wh[j][c]   -> Dh2T (k-major) and Dh2R (row-major)
         const int rt = t & 15, jt = t >> 4;
-        float wh[4][1 + A];
+        if (t <= A) G[L.pWh + kH2 * HC + t] += Red[16 + t] + Red[24 + t];     // d(head bias), fixed order
+        float wh[4][HC];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-          for (int c = 0; c <= A; ++c) wh[jj][c] = W[L.pWh + (4 * jt + jj) * HC + c];
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 w0 = ld4(W + L.pWh + (4 * jt + jj) * HC), w1 = ld4(W + L.pWh + (4 * jt + jj) * HC + 4);
+          wh[jj][0] = w0.x; wh[jj][1] = w0.y; wh[jj][2] = w0.z; wh[jj][3] = w0.w;
+          wh[jj][4] = w1.x; wh[jj][5] = w1.y; wh[jj][6] = w1.z; wh[jj][7] = w1.w;
+        }
+        float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
           const int r = rt + 16 * ii;
@@ -464,63 +564,89 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
             for (int c = 0; c <= A; ++c) v = fmaf(dh[c], wh[jj][c], v);
             o[jj] = H2[(4 * jt + jj) * RS2 + r] > 0.f ? v : 0.f;
             Dh2T[(4 * jt + jj) * RS1 + r] = o[jj];
+            bsum[jj] += o[jj];
           }
           st4(Dh2R + r * RS1 + 4 * jt, o[0], o[1], o[2], o[3]);
         }
+        // db2[j] += sum_r dh2[r][j]: butterfly over the 16 lanes that share jt (fixed order)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) bsum[jj] += __shfl_xor_sync(0xffffffffu, bsum[jj], o);
+        }
+        if (rt == 0) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) G[L.pW2 + kH1 * WS2 + 4 * jt + jj] += bsum[jj];
+        }
       }
       __syncthreads();
-      {  // (a) dW2[k][j] += sum_r h1[r][k] * dh2[r][j]
-        const int mt = t & 15, nt = t >> 4;
-        float acc[2][4] = {};
-        dot_tile<2, 4>(H1, RS2, mt, 16, Dh2T, RS1, nt, 16, 0, 16, acc);
+      {  // (a) dW2[k][j] += sum_r h1[r][k] * dh2[r][j].  A warp owns a 16 x 16 block: every operand load
+         // touches <= 8 distinct rows (one smem wavefront) and the G update is bank-conflict free.
+        const int mi = lane & 7, ni = lane >> 3, k0 = 16 * (warp & 1) + mi, j0 = 16 * (warp >> 1) + ni;
+        const float* ap[2] = {H1 + k0 * RS2, H1 + (k0 + 8) * RS2};
+        const float* bp[4] = {Dh2T + j0 * RS1, Dh2T + (j0 + 4) * RS1, Dh2T + (j0 + 8) * RS1, Dh2T + (j0 + 12) * RS1};
+        float acc[2][4];
+        dot_tile<2, 4, 16>(ap, bp, acc);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) G[L.pW2 + (mt + 16 * i) * kH2 + nt + 16 * j] += acc[i][j];
+          for (int j = 0; j < 4; ++j) G[L.pW2 + (k0 + 8 * i) * WS2 + j0 + 4 * j] += acc[i][j];
       }
-      {  // (a') db2[j] += sum_r dh2[r][j]  (4-way split over r, shared atomics)
-        const int j = t & 63, part = t >> 6;
-        float s = 0.f;
+      {  // (b) dWh[j][c] += sum_r h2[r][j] * dhd[r][c]: 4-way split over r inside a warp, shuffle-reduced
+        const int j = warp * 8 + (lane & 7), part = lane >> 3;
+        const float* ap[1] = {H2 + j * RS2 + 16 * part};
+        const float* bp[1 + A];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { const float4 v = ld4(Dh2T + j * RS1 + 16 * part + 4 * c); s += (v.x + v.y) + (v.z + v.w); }
-        atomicAdd(&G[L.pW2 + kH1 * kH2 + j], s);
-      }
-      {  // (b) dWh[j][c] += sum_r h2[r][j] * dhd[r][c]   (4-way split over r, shared atomics)
-        const int j = t & 63, part = t >> 6;
-        float acc[1][1 + A] = {};
-        dot_tile<1, 1 + A>(H2, RS2, j, 0, DhdT, RS1, 0, 1, 4 * part, 4, acc);
+        for (int c = 0; c <= A; ++c) bp[c] = DhdT + c * RS1 + 16 * part;
+        float acc[1][1 + A];
+        dot_tile<1, 1 + A, 4>(ap, bp, acc);
 #pragma unroll
-        for (int c = 0; c <= A; ++c) atomicAdd(&G[L.pWh + j * HC + c], acc[0][c]);
+        for (int c = 0; c <= A; ++c) {
+          float v = acc[0][c];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (part == 0) G[L.pWh + j * HC + c] += v;
+        }
       }
-      {  // (c) dh1[r][k] = relu'(h1) * sum_j dh2[r][j] * W2[k][j]  -> Dh1T
-        const int mt = t & 15, nt = t >> 4;
-        float acc[4][2] = {};
-        dot_tile<4, 2>(Dh2R, RS1, mt, 16, W + L.pW2, kH2, nt, 16, 0, 16, acc);
+      {  // (c) dh1[r][k] = relu'(h1) * sum_j dh2[r][j] * W2[k][j]  -> Dh1T   (warp = 16 rows x 16 units)
+        const int mi = lane & 3, ni = lane >> 2, r0 = 16 * (warp & 3) + mi, k0 = 16 * (warp >> 2) + ni;
+        const float* ap[4] = {Dh2R + r0 * RS1, Dh2R + (r0 + 4) * RS1, Dh2R + (r0 + 8) * RS1, Dh2R + (r0 + 12) * RS1};
+        const float* bp[2] = {W + L.pW2 + k0 * WS2, W + L.pW2 + (k0 + 8) * WS2};
+        float acc[4][2];
+        dot_tile<4, 2, 16>(ap, bp, acc);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int r = mt + 16 * i, k = nt + 16 * j;
+            const int r = r0 + 4 * i, k = k0 + 8 * j;
             Dh1T[k * RS1 + r] = H1[k * RS2 + r] > 0.f ? acc[i][j] : 0.f;
           }
       }
       __syncthreads();
       {  // (d) [dW1;db1][d][h] += sum_r x[r][d] * dh1[r][h]   (row D of X is ones -> db1)
         const int hcol = t & 31, mt = t >> 5;
-        float acc[3][1] = {};
         // rows d = mt, mt+8, mt+16 (<= D); out-of-range rows are clamped for the loads and not stored
-        const int d0 = mt, d1 = mt + 8 <= D ? mt + 8 : D, d2 = mt + 16 <= D ? mt + 16 : D;
-#pragma unroll 2
-        for (int c = 0; c < 16; ++c) {
-          const float4 b = ld4(Dh1T + hcol * RS1 + 4 * c);
-          const float4 a0 = ld4(X + d0 * RS2 + 4 * c), a1 = ld4(X + d1 * RS2 + 4 * c), a2 = ld4(X + d2 * RS2 + 4 * c);
-          acc[0][0] = fmaf(a0.w, b.w, fmaf(a0.z, b.z, fmaf(a0.y, b.y, fmaf(a0.x, b.x, acc[0][0]))));
-          acc[1][0] = fmaf(a1.w, b.w, fmaf(a1.z, b.z, fmaf(a1.y, b.y, fmaf(a1.x, b.x, acc[1][0]))));
-          acc[2][0] = fmaf(a2.w, b.w, fmaf(a2.z, b.z, fmaf(a2.y, b.y, fmaf(a2.x, b.x, acc[2][0]))));
+        const int d1 = mt + 8 <= D ? mt + 8 : D, d2 = mt + 16 <= D ? mt + 16 : D;
+        const float* bp[1] = {Dh1T + hcol * RS1};
+        if (D <= 7) {
+          const float* ap[1] = {X + mt * RS2};
+          float acc[1][1];
+          dot_tile<1, 1, 16>(ap, bp, acc);
+          if (mt <= D) G[mt * kH1 + hcol] += acc[0][0];
+        } else if (D <= 15) {
+          const float* ap[2] = {X + mt * RS2, X + d1 * RS2};
+          float acc[2][1];
+          dot_tile<2, 1, 16>(ap, bp, acc);
+          G[mt * kH1 + hcol] += acc[0][0];
+          if (mt + 8 <= D) G[(mt + 8) * kH1 + hcol] += acc[1][0];
+        } else {
+          const float* ap[3] = {X + mt * RS2, X + d1 * RS2, X + d2 * RS2};
+          float acc[3][1];
+          dot_tile<3, 1, 16>(ap, bp, acc);
+          G[mt * kH1 + hcol] += acc[0][0];
+          G[(mt + 8) * kH1 + hcol] += acc[1][0];
+          if (mt + 16 <= D) G[(mt + 16) * kH1 + hcol] += acc[2][0];
         }
-        if (mt <= D) G[mt * kH1 + hcol] += acc[0][0];
-        if (mt + 8 <= D) G[(mt + 8) * kH1 + hcol] += acc[1][0];
-        if (mt + 16 <= D) G[(mt + 16) * kH1 + hcol] += acc[2][0];
       }
       // the barrier at the top of the next tile / before Adam orders these G updates
     }  // tiles
@@ -532,8 +658,11 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
       for (int p = t; p < L.PS; p += NT) { const int f = smem_to_flat(p, D, A, L); if (f >= 0) args.taps.grads[f] = G[p]; }
     }
     // ================= optimiser: optax adam / adamw (q_learning_functions.py:24-25) ==========
+    // mu/nu are updated in full precision; the bias-corrected quotient uses the SFU reciprocal / sqrt
+    // (<= 2 ulp each, i.e. ~1e-7 relative on an update that is itself lr ~ 1e-4 of the weight scale).
     {
       const float c1 = Red[8 + 2 * (kstep & 1)], c2 = Red[9 + 2 * (kstep & 1)];
+      const float rc1 = 1.0f / c1, rc2 = 1.0f / c2;
       const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
 #pragma unroll
       for (int i = 0; i < NPT; ++i) {
@@ -544,10 +673,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
           const float m = b1 * mreg[i] + omb1 * g;
           const float v = b2 * vreg[i] + omb2 * (g * g);
           mreg[i] = m; vreg[i] = v;
-          float u = (m / c1) / (sqrtf(v / c2 + eps_root) + eps);
+          const float u = (m * rc1) * fast_rcp(fast_sqrt(v * rc2 + eps_root) + eps);
           const float th = W[p];
-          if (wd != 0.f) u = u + wd * th;       // add_decayed_weights (adamw)
-          W[p] = th + (-lr) * u;                 // scale(-lr); apply_updates
+          W[p] = th - lr * (u + wd * th);        // add_decayed_weights (wd = 0 for adam); scale(-lr); apply_updates
         }
       }
     }

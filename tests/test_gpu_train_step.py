@@ -1,0 +1,220 @@
+"""GPU parity of the fused train step (through the C ABI) against the oracle on identical weights,
+transitions and indices.  Bar (north_star): indices / greedy actions bit-exact; Q-values, TD targets,
+loss, gradients and updated parameters within 1e-5 relative in fp32 (assert_close adds an absolute
+floor of 1e-6 x the tensor's largest magnitude for entries that are ~0 by cancellation)."""
+import numpy as np
+import pytest
+
+import dqn_b200
+from conftest import assert_close, golden_tree
+from oracle import dqn_oracle as O
+from oracle.agent_oracle import OracleAgent
+from oracle.philox import sample_indices
+from oracle.replay_oracle import synthetic_transitions
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(D=9, A=4, B=64, N=2000, n_fill=1500, kind="adamw", lr=2e-4, gamma=0.99, seed=0, params=None,
+              done_p=0.2, perturb_target=True):
+    rng = np.random.default_rng(seed)
+    if params is None:
+        params = O.init_params(rng, D, A, bias_std=0.05)
+    else:                                   # fixture theta_0 has zero biases: randomise them
+        params = O.tree_copy(params)
+        for m in O.MODULES:
+            params[m]["b"] = (0.05 * rng.standard_normal(params[m]["b"].shape)).astype(np.float32)
+    target = O.tree_map(lambda x: (x + 0.02 * rng.standard_normal(x.shape)).astype(np.float32), params) \
+        if perturb_target else O.tree_copy(params)
+    opt = dqn_b200.adamw(lr) if kind == "adamw" else dqn_b200.adam(lr)
+    eng = dqn_b200.DqnEngine(D, A, N, B, gamma, opt, seed=seed + 100)
+    eng.set_params(params, 0, 0)
+    eng.set_params(target, 0, 1)
+    ora = OracleAgent(params, O.init_opt_state(params), O.OptSpec(kind, lr), N, D, gamma, B, seed=seed + 100)
+    ora.target_params = O.tree_copy(target)
+    data = synthetic_transitions(rng, n_fill, D, A, done_p=done_p)
+    eng.store(*data)
+    ora.replay.add_many(*data)
+    return eng, ora, rng
+
+
+def compare_step(eng, ora, indices=None, what=""):
+    ref = ora.step(indices)
+    got = eng.train_step_debug(indices=indices)
+    assert np.array_equal(got["indices"], ref["indices"]), what + " indices"
+    assert np.array_equal(got["max_actions"], ref["max_actions"]), what + " argmax"
+    for k in ("q", "next_q", "next_q_tm", "targets"):
+        assert_close(got[k], ref[k], what=f"{what} {k}")
+    assert abs(float(got["loss"]) - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"])) + 1e-9, what + " loss"
+    for m in O.MODULES:
+        for k in ("w", "b"):
+            assert_close(got["grads"][m][k], ref["grads"][m][k], what=f"{what} grad {m}/{k}")
+    compare_state(eng, ora, what)
+    return got, ref
+
+
+def compare_state(eng, ora, what="", rtol=1e-5):
+    p = eng.get_params(0, 0)
+    cnt, mu, nu = eng.get_opt_state(0)
+    assert int(cnt) == int(ora.opt_state["count"]), what + " adam count"
+    for m in O.MODULES:
+        for k in ("w", "b"):
+            assert_close(p[m][k], ora.params[m][k], rtol=rtol, what=f"{what} param {m}/{k}")
+            assert_close(mu[m][k], ora.opt_state["mu"][m][k], rtol=rtol, what=f"{what} mu {m}/{k}")
+            assert_close(nu[m][k], ora.opt_state["nu"][m][k], rtol=rtol, what=f"{what} nu {m}/{k}")
+
+
+def test_lunar_lander_config_from_reference_checkpoint(golden):
+    """Config 1 (Test/lunar_lander.py): D=9, A=4, B=64, gamma .99, AdamW(2e-4), theta_0 = the shipped pickle."""
+    theta0 = golden_tree(golden["ref_checkpoint"], "params")
+    eng, ora, rng = make_pair(params=theta0)
+    for step in range(5):
+        compare_step(eng, ora, what=f"step{step}")          # Philox indices, drawn on both sides
+    t = eng.get_params(0, 1)
+    for m in O.MODULES:                                     # target network untouched by training
+        assert np.array_equal(t[m]["w"], ora.target_params[m]["w"])
+
+
+@pytest.mark.parametrize("D,A,B,kind,gamma", [
+    (8, 4, 64, "adam", 0.9028), (9, 4, 38, "adam", 0.0), (9, 4, 70, "adamw", 0.999), (8, 4, 1, "adam", 0.95),
+    (8, 4, 128, "adamw", 0.99), (16, 2, 33, "adam", 0.9), (1, 7, 65, "adamw", 0.5), (4, 3, 200, "adam", 0.99),
+])
+def test_shapes_batches_optimisers(D, A, B, kind, gamma):
+    eng, ora, rng = make_pair(D=D, A=A, B=B, kind=kind, lr=1e-3, gamma=gamma, seed=D * 7 + B)
+    for step in range(3):
+        compare_step(eng, ora, what=f"D{D} A{A} B{B} step{step}")
+
+
+def test_explicit_indices_and_duplicates():
+    eng, ora, rng = make_pair(B=64)
+    idx = rng.integers(0, 1500, 64)
+    idx[:8] = idx[8]                                        # with-replacement duplicates
+    compare_step(eng, ora, indices=idx, what="explicit")
+    compare_step(eng, ora, indices=np.zeros(64, np.int64), what="all-same-slot")
+
+
+def test_terminal_rows_follow_reference_quirk_F5():
+    eng, ora, rng = make_pair(done_p=1.0)
+    got, ref = compare_step(eng, ora, what="all-terminal")
+    batch_r = ora.replay.rewards[ref["indices"]]
+    rows = np.arange(64)
+    a = ora.replay.actions[ref["indices"]]
+    np.testing.assert_allclose(got["targets"][rows, a] - got["q"][rows, a], batch_r, rtol=1e-5, atol=1e-6)
+
+
+def test_hundred_step_drift_and_hard_sync():
+    """100 consecutive steps (hard sync every 25) stay within tolerance of the oracle."""
+    eng, ora, rng = make_pair(seed=3, lr=1e-3, perturb_target=False)
+    for step in range(100):
+        ora.step()
+        eng.train_steps(1)
+        if step % 25 == 24:
+            ora.update_target_model()
+            eng.sync_target()
+            t = eng.get_params(0, 1)
+            o = eng.get_params(0, 0)
+            for m in O.MODULES:
+                assert np.array_equal(t[m]["w"], o[m]["w"]) and np.array_equal(t[m]["b"], o[m]["b"])
+    compare_state(eng, ora, "after 100 steps", rtol=2e-4)     # fp32 summation-order drift accumulates
+    losses = eng.losses(100)
+    assert_close(losses[-1], np.float32(ora.last["loss"]), rtol=1e-3, what="loss[99]")
+    assert eng.train_step_count() == 100
+
+
+def test_fused_k_steps_equal_k_single_launches_bitwise():
+    """K steps in one persistent launch == K launches of one step (same Philox stream): bit-identical."""
+    eng1, _, _ = make_pair(seed=4, lr=1e-3)
+    eng2, _, _ = make_pair(seed=4, lr=1e-3)
+    eng3, _, _ = make_pair(seed=4, lr=1e-3)
+    for _ in range(37):
+        eng1.train_steps(1)
+    eng2.train_steps(37)
+    eng3.train_steps(20)
+    eng3.train_steps(17)
+    a, b, c = eng1.get_params_flat(), eng2.get_params_flat(), eng3.get_params_flat()
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    for e in (eng2, eng3):
+        c1, m1, v1 = eng1.get_opt_state()
+        c2, m2, v2 = e.get_opt_state()
+        assert c1 == c2 == 37
+        for m in O.MODULES:
+            assert np.array_equal(m1[m]["w"], m2[m]["w"]) and np.array_equal(v1[m]["w"], v2[m]["w"])
+    assert np.array_equal(eng1.losses(37), eng2.losses(37))
+
+
+def test_greedy_actions_bit_exact():
+    eng, ora, rng = make_pair(seed=9)
+    states = rng.standard_normal((2000, 9)).astype(np.float32)
+    q = O.forward(ora.params, states)
+    srt = np.sort(q, axis=1)
+    clear = (srt[:, -1] - srt[:, -2]) > 1e-5               # exclude numerical near-ties (none expected)
+    assert clear.mean() > 0.99
+    want = np.argmax(q, axis=1)
+    got = np.array([eng.act(s) for s in states[:300]])
+    assert np.array_equal(got[clear[:300]], want[:300][clear[:300]])
+    zero = O.tree_zeros_like(ora.params)
+    eng.set_params(zero, 0, 0)
+    assert eng.act(states[0]) == 0                          # all-equal Q -> first index, like numpy/jnp argmax
+
+
+def test_agent_dropin_matches_oracle_agent(golden):
+    """The reference-facing Agent object: constructor kwargs of Test/lunar_lander.py, add() per transition,
+    _step(), _update_target_model(), _policy() greedy branch."""
+    import asyncio
+    theta0 = golden_tree(golden["ref_checkpoint"], "params")
+    opt = dqn_b200.adamw(0.0002)
+    N, D, B = 1000, 9, 64
+    agent = dqn_b200.Agent(network=dqn_b200.Model(4), params=theta0, optimizer=opt, opt_state=opt.init(theta0),
+                           env=None, buffer_size=N, obs_shape=(N, D), ac_shape=(N,), gamma=0.99, epsilon=0.0,
+                           epsilon_decay_rate=0.99, min_epsilon=0.0, max_episodes=10, max_steps=1500,
+                           training_start=250, batch_size=B, train_frequency=4, back_up_frequency=50,
+                           replace_frequency=20, reward_to_reach=230.0, num_actions=4,
+                           saving_directory="/tmp/dqn_b200_test_agent", monitoring=False, seed=21)
+    ora = OracleAgent(theta0, O.init_opt_state(theta0), O.OptSpec("adamw", 2e-4), N, D, 0.99, B, seed=21)
+    rng = np.random.default_rng(8)
+    s, a, r, s2, d = synthetic_transitions(rng, 300, D, 4, done_p=0.2)
+    for i in range(300):
+        agent._replay_buffer.add(s[i], int(a[i]), float(r[i]), s2[i], bool(d[i]))
+        ora.add(s[i], int(a[i]), float(r[i]), s2[i], bool(d[i]))
+        if i >= 250 and i % 4 == 0:
+            agent._step()
+            ora.step()
+        if i == 280:
+            asyncio.run(agent._update_target_model())
+            ora.update_target_model()
+    p = agent._params
+    for m in O.MODULES:
+        for k in ("w", "b"):
+            assert_close(p[m][k], ora.params[m][k], what=f"agent param {m}/{k}")
+    assert agent._replay_buffer.size == 300
+    st = agent._opt_state
+    assert int(st[0].count) == int(ora.opt_state["count"]) and len(st) == 3
+    assert agent._policy(s[:1]) == ora.policy_greedy(s[:1])          # epsilon = 0 -> always greedy
+    agent._epsilon = 2.0                                             # epsilon > 1 -> always random
+    assert all(0 <= agent._policy(s[:1]) < 4 for _ in range(20))
+
+
+def test_param_agent_inject_and_gamma_modes():
+    theta = O.init_params(np.random.default_rng(0), 9, 4, bias_std=0.05)
+    opt = dqn_b200.adam(1e-4)
+    kw = dict(network=dqn_b200.Model(4), params=theta, optimizer=opt, opt_state=opt.init(theta), env=None,
+              buffer_size=500, obs_shape=(500, 9), ac_shape=(500,), max_episodes=10, max_steps=1500,
+              training_start=500, back_up_frequency=50, reward_to_reach=240.0, num_actions=4,
+              saving_directory="/tmp/dqn_b200_test_pagent")
+    data = synthetic_transitions(np.random.default_rng(1), 400, 9, 4, done_p=0.1)
+    for mode, eff_gamma in (("frozen", 0.0), ("live", 0.9028)):
+        ag = dqn_b200.ParamAgent(**kw, gamma_mode=mode, seed=5)
+        ag.inject(0.9028, 0.979, 0.9873, 0.1469, 25, 52, 7)           # the optimum recorded in the sweep script
+        assert ag._engine.get_hparams(0)["batch_size"] == 52 and ag._batch_size == 52
+        assert abs(ag._engine.get_hparams(0)["gamma"] - eff_gamma) < 1e-7
+        ag.max_episodes = 500
+        assert ag.max_episodes == 500
+        ag._replay_buffer.add_many(*data)
+        ora = OracleAgent(theta, O.init_opt_state(theta), O.OptSpec("adam", 1e-4), 500, 9, eff_gamma, 52, seed=5)
+        ora.replay.add_many(*data)
+        for _ in range(3):
+            ag._step()
+            ora.step()
+        p = ag._params
+        for m in O.MODULES:
+            assert_close(p[m]["w"], ora.params[m]["w"], what=f"{mode} {m}")
