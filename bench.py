@@ -278,7 +278,7 @@ def run_single(args):
                 k = off + i * TRAIN_FREQUENCY + j
                 rb.add(s[k], a_py[k], r_py[k], s2[k], d_py[k])
             agent._step()                                          # q_agent.py:187
-            last = float(eng.losses(1)[0])                         # device -> host read of the step's loss
+            last = eng.last_loss()                                 # device -> host read of the step's loss
         return last
 
     e2e_loop(8)

@@ -146,6 +146,7 @@ class Agent:
     def _step(self, indices=None):
         """One fused train step (sample -> preprocess -> targets -> grad -> adam).  ``indices``
         (optional, i64[batch_size]) replaces the Philox draw -- the hook parity runs use."""
+        self._replay_buffer.flush()
         if indices is None:
             _lib.check(self._lib.dqn_train_step(self._h, 0, 1, 1, None, None))
         else:
@@ -153,9 +154,11 @@ class Agent:
 
     def _steps(self, k):
         """``k`` consecutive ``_step()`` calls in one persistent launch (no stores in between)."""
+        self._replay_buffer.flush()
         _lib.check(self._lib.dqn_train_step(self._h, 0, 1, int(k), None, None))
 
     def _step_debug(self, indices=None):
+        self._replay_buffer.flush()
         return self._engine.train_step_debug(indices=indices, agent=0)
 
     def _run_episode(self, step_count, episode):

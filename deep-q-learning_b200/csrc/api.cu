@@ -115,6 +115,8 @@ struct dqn_handle {
   uint8_t* taps;
   uint8_t* pinned;
   uint8_t* bounce;              // pinned + kBounceOff
+  float* mailbox;               // mapped pinned host memory, [n_agents]: last loss of each agent's last launch
+  float* mailbox_dev;           // device alias of `mailbox`
   cudaEvent_t slot_ev[kSlots];  // completion of the H2D copy that last used each pinned store slot
   int slot_next;
   std::vector<AgentCtl> hctl;   // host mirror of the per-agent control blocks
@@ -213,6 +215,11 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   cudaError_t e = cudaMallocHost((void**)&h->pinned, kPinnedBytes);
   if (e != cudaSuccess) { if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaMallocHost failed"); }
   h->bounce = h->pinned + kBounceOff;
+  h->mailbox = nullptr; h->mailbox_dev = nullptr;
+  e = cudaHostAlloc((void**)&h->mailbox, sizeof(float) * cfg->n_agents, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->mailbox_dev, h->mailbox, 0);
+  if (e != cudaSuccess) { cudaFreeHost(h->pinned); if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaHostAlloc(mapped) failed"); }
+  memset(h->mailbox, 0, sizeof(float) * cfg->n_agents);
   h->slot_next = 0;
   for (int i = 0; i < kSlots; ++i) cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming);
   // zero parameters / moments / rings / losses (ReplayBuffer.__init__ zero-fills, replay_buffer.py:26-30)
@@ -230,6 +237,7 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   if (e != cudaSuccess) {
     std::string m = std::string("dqn_create: device initialisation failed: ") + cudaGetErrorString(e);
     for (int i = 0; i < kSlots; ++i) cudaEventDestroy(h->slot_ev[i]);
+    cudaFreeHost(h->mailbox);
     cudaFreeHost(h->pinned);
     if (h->own_arena) cudaFree(h->arena);
     delete h;
@@ -244,6 +252,7 @@ DQN_API int dqn_destroy(dqn_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   for (int i = 0; i < kSlots; ++i) cudaEventDestroy(h->slot_ev[i]);
+  if (h->mailbox) cudaFreeHost(h->mailbox);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_arena) cudaFree(h->arena);
   delete h;
@@ -492,7 +501,7 @@ int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, d
   }
   TrainArgs ta;
   memset(&ta, 0, sizeof ta);
-  ta.params = h->params; ta.ctl = h->ctl; ta.rings = h->rings; ta.loss_ring = h->loss_ring;
+  ta.params = h->params; ta.ctl = h->ctl; ta.rings = h->rings; ta.loss_ring = h->loss_ring; ta.loss_mailbox = h->mailbox_dev;
   ta.idx = idx_dev; ta.dims = h->dims; ta.seed = h->cfg.seed; ta.agent_begin = b; ta.agent_id_base = h->cfg.agent_id_base; ta.n_sel = n_sel; ta.K = K;
   if (taps) {
     if (K != 1 || n_sel != 1) return fail(DQN_E_INVALID, "dqn_train_step: debug taps need K == 1 and a single agent");
@@ -568,6 +577,11 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
   if (n == 0) return DQN_OK;
   if (n < 0 || n > kLossCap || n > ts || !loss_out) return fail(DQN_E_INVALID, "dqn_get_losses: n must be <= min(train steps so far, 4096)");
   CU(cudaSetDevice(h->cfg.device));
+  if (n == 1) {   // the kernel wrote it straight into mapped host memory: one synchronisation, no copy
+    CU(cudaStreamSynchronize(h->stream));
+    loss_out[0] = h->mailbox[agent];
+    return DQN_OK;
+  }
   // the last n losses are at ring positions [(ts-n) % cap, ts % cap): at most two contiguous pieces
   const size_t first = (size_t)((ts - n) % kLossCap);
   const size_t n1 = first + (size_t)n <= (size_t)kLossCap ? (size_t)n : (size_t)kLossCap - first;

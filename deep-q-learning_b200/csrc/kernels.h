@@ -23,6 +23,7 @@ struct TrainArgs {
   AgentCtl* ctl;              // [n_agents]
   const uint32_t* rings;      // [n_agents][N][recw]
   float* loss_ring;           // [n_agents][kLossCap]
+  float* loss_mailbox;        // [n_agents] zero-copy (mapped pinned host memory): loss of the launch's last step
   const long long* idx;       // device i64 [n_sel][K][B] or nullptr (Philox)
   Dims dims;
   unsigned long long seed;

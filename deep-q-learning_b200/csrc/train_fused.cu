@@ -189,10 +189,10 @@ __device__ __forceinline__ void op_store_relu(float* __restrict__ C, int ldc, co
 }
 
 // Dot-form tile (gradient GEMMs) over NCH chunks of 4 reduction elements:
-//   out[i][j] = sum_r ap[i][r] * bp[j][r],  r in [0, 4*NCH)
+//   out[i][j] = sum over chunks c < NCH of dot4(ap[i] + CSTEP*c, bp[j] + CSTEP*c)
 // ap / bp are per-thread row base pointers, so every load is [register + immediate].  The packed
 // accumulator holds the (even, odd) partial sums; loads of chunk c+1 are issued before the FMAs of c.
-template <int TM, int TN, int NCH>
+template <int TM, int TN, int NCH, int CSTEP = 4>
 __device__ __forceinline__ void dot_tile(const float* const (&ap)[TM], const float* const (&bp)[TN], float (&out)[TM][TN]) {
   u64 acc[TM][TN];
 #pragma unroll
@@ -213,9 +213,9 @@ __device__ __forceinline__ void dot_tile(const float* const (&ap)[TM], const flo
     for (int j = 0; j < TN; ++j) b[j] = bn[j];
     if (c + 1 < NCH) {
 #pragma unroll
-      for (int i = 0; i < TM; ++i) an[i] = ld2x64(ap[i] + 4 * (c + 1));
+      for (int i = 0; i < TM; ++i) an[i] = ld2x64(ap[i] + CSTEP * (c + 1));
 #pragma unroll
-      for (int j = 0; j < TN; ++j) bn[j] = ld2x64(bp[j] + 4 * (c + 1));
+      for (int j = 0; j < TN; ++j) bn[j] = ld2x64(bp[j] + CSTEP * (c + 1));
     }
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -246,6 +246,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
+  // OP-form tile coordinates: a half-warp is 8 m-tiles x 2 n-tiles (128-bit smem loads are served per
+  // half-warp, so this keeps every operand load at one wavefront per half-warp)
+  const int tmi = (lane & 7) + 8 * (lane >> 4), tni = (lane >> 3) & 1;
   const int sel = blockIdx.x;
   const int agent = args.agent_begin + sel;
   const int D = args.dims.D;
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
 
       // ================= batch B: Q(theta^-, s')  (q_learning_functions.py:54) ==============
       {  // layer 1: rows = s' (X cols 64..127) -> H1 cols 0..63
-        const int m0 = 4 * (t & 15), n0 = 2 * (t >> 4);
+        const int m0 = 4 * tmi, n0 = 2 * (tni + 2 * warp);
         u64 acc[4][1];
         op_init<2>(Wt + D * kH1 + n0, acc);
         op_tile4<2>(X + BT + m0, RS2, Wt + n0, kH1, D, acc);
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
       }
       __syncthreads();
       {  // layer 2
-        const int m0 = 4 * (t & 15), n0 = 4 * (t >> 4);
+        const int m0 = 4 * tmi, n0 = 4 * (tni + 2 * warp);
         u64 acc[4][2];
         op_init<4>(Wt + L.pW2 + kH1 * WS2 + n0, acc);
         op_tile4<4>(H1 + m0, RS2, Wt + L.pW2 + n0, WS2, kH1, acc);
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
 
       // ================= batch A: Q(theta, s) and Q(theta, s')  (:52-53) ====================
       {  // layer 1: 128 rows
-        const int m0 = 4 * (t & 31), n0 = 4 * (t >> 5);
+        const int m0 = 4 * (tmi + 16 * (warp & 1)), n0 = 4 * (tni + 2 * (warp >> 1));
         u64 acc[4][2];
         op_init<4>(W + D * kH1 + n0, acc);
         op_tile4<4>(X + m0, RS2, W + n0, kH1, D, acc);
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
       }
       __syncthreads();
       {  // layer 2: 128 rows x 64; a warp covers 64 rows x 16 columns (4 smem wavefronts per k-step)
-        const int m0 = 4 * ((lane & 15) + 16 * (warp & 1)), n0 = 8 * ((lane >> 4) + 2 * (warp >> 1));
+        const int m0 = 4 * (tmi + 16 * (warp & 1)), n0 = 8 * (tni + 2 * (warp >> 1));
         u64 acc[4][4];
         op_init<8>(W + L.pW2 + kH1 * WS2 + n0, acc);
         op_tile4<8>(H1 + m0, RS2, W + L.pW2 + n0, WS2, kH1, acc);
@@ -580,17 +583,30 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
         }
       }
       __syncthreads();
-      {  // (a) dW2[k][j] += sum_r h1[r][k] * dh2[r][j].  A warp owns a 16 x 16 block: every operand load
-         // touches <= 8 distinct rows (one smem wavefront) and the G update is bank-conflict free.
-        const int mi = lane & 7, ni = lane >> 3, k0 = 16 * (warp & 1) + mi, j0 = 16 * (warp >> 1) + ni;
-        const float* ap[2] = {H1 + k0 * RS2, H1 + (k0 + 8) * RS2};
-        const float* bp[4] = {Dh2T + j0 * RS1, Dh2T + (j0 + 4) * RS1, Dh2T + (j0 + 8) * RS1, Dh2T + (j0 + 12) * RS1};
-        float acc[2][4];
-        dot_tile<2, 4, 16>(ap, bp, acc);
+      // (a) and (c) below are smem-bandwidth critical: 4x4 register tiles with a 2-way split of the
+      // reduction across adjacent lanes (lane&1 takes the even / odd 16-byte chunks) halve the operand
+      // bytes per FMA; rows inside a half-warp are 2 apart so the 8 (row, chunk-parity) pairs of every
+      // 128-bit load hit 8 distinct bank groups (one wavefront per half-warp).
+      const int kh = lane & 1, ntl = (lane >> 1) & 3, mtl = (lane >> 3) & 1, hwid = t >> 4;
+      {  // (a) dW2[k][j] += sum_r h1[r][k] * dh2[r][j]
+        const int k0 = 16 * ((hwid >> 1) & 1) + (hwid & 1) + 2 * mtl;          // rows k0 + 4 i
+        const int j0 = 32 * (hwid >> 3) + ((hwid >> 2) & 1) + 2 * ntl;         // rows j0 + 8 jj
+        const float* ap[4];
+        const float* bp[4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 4; ++i) { ap[i] = H1 + (k0 + 4 * i) * RS2 + 4 * kh; bp[i] = Dh2T + (j0 + 8 * i) * RS1 + 4 * kh; }
+        float acc[4][4];
+        dot_tile<4, 4, 8, 8>(ap, bp, acc);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) G[L.pW2 + (k0 + 8 * i) * WS2 + j0 + 4 * j] += acc[i][j];
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 1);
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {      // lane kh finishes rows i = kh, kh + 2
+          const int i = kh + 2 * ii;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) G[L.pW2 + (k0 + 4 * i) * WS2 + j0 + 8 * j] += kh ? acc[1 + 2 * ii][j] : acc[2 * ii][j];
+        }
       }
       {  // (b) dWh[j][c] += sum_r h2[r][j] * dhd[r][c]: 4-way split over r inside a warp, shuffle-reduced
         const int j = warp * 8 + (lane & 7), part = lane >> 3;
@@ -608,19 +624,29 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
           if (part == 0) G[L.pWh + j * HC + c] += v;
         }
       }
-      {  // (c) dh1[r][k] = relu'(h1) * sum_j dh2[r][j] * W2[k][j]  -> Dh1T   (warp = 16 rows x 16 units)
-        const int mi = lane & 3, ni = lane >> 2, r0 = 16 * (warp & 3) + mi, k0 = 16 * (warp >> 2) + ni;
-        const float* ap[4] = {Dh2R + r0 * RS1, Dh2R + (r0 + 4) * RS1, Dh2R + (r0 + 8) * RS1, Dh2R + (r0 + 12) * RS1};
-        const float* bp[2] = {W + L.pW2 + k0 * WS2, W + L.pW2 + (k0 + 8) * WS2};
-        float acc[4][2];
-        dot_tile<4, 2, 16>(ap, bp, acc);
+      {  // (c) dh1[r][k] = relu'(h1) * sum_j dh2[r][j] * W2[k][j]  -> Dh1T
+        const int r0 = 16 * (hwid >> 2) + ((hwid >> 1) & 1) + 2 * mtl;           // rows r0 + 4 i
+        const int k0 = (hwid & 1) + 2 * ntl;                                      // units k0 + 8 jj
+        const float* ap[4];
+        const float* bp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ap[i] = Dh2R + (r0 + 4 * i) * RS1 + 4 * kh; bp[i] = W + L.pW2 + (k0 + 8 * i) * WS2 + 4 * kh; }
+        float acc[4][4];
+        dot_tile<4, 4, 8, 8>(ap, bp, acc);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int r = r0 + 4 * i, k = k0 + 8 * j;
-            Dh1T[k * RS1 + r] = H1[k * RS2 + r] > 0.f ? acc[i][j] : 0.f;
+          for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 1);
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+          const int r = r0 + 4 * (kh + 2 * ii);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + 8 * j;
+            const float v = kh ? acc[1 + 2 * ii][j] : acc[2 * ii][j];
+            Dh1T[k * RS1 + r] = H1[k * RS2 + r] > 0.f ? v : 0.f;
           }
+        }
       }
       __syncthreads();
       {  // (d) [dW1;db1][d][h] += sum_r x[r][d] * dh1[r][h]   (row D of X is ones -> db1)
@@ -682,6 +708,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
     if (t == 0) {
       const float loss = (Red[0] + Red[1]) / fB;
       args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
+      if (kstep == args.K - 1) args.loss_mailbox[agent] = loss;   // host-visible without a D2H copy
       if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
     }
     // next step's first barrier (top of tile loop) orders W/G/Red before reuse

@@ -52,6 +52,8 @@ class DqnEngine:
         _lib.check(self.lib.dqn_create(C.byref(cfg), C.byref(h)))
         self.h = h
         self._cfg = cfg
+        self._loss1 = np.empty(1, np.float32)
+        self._loss1_ptr = _lib.ptr(self._loss1)
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -172,6 +174,11 @@ class DqnEngine:
         ts = C.c_int64(0)
         _lib.check(self.lib.dqn_get_losses(self.h, agent, int(n), _lib.ptr(out), C.byref(ts)))
         return out
+
+    def last_loss(self, agent=0):
+        """Loss of the most recent train step (synchronises; the kernel writes it to mapped host memory)."""
+        _lib.check(self.lib.dqn_get_losses(self.h, agent, 1, self._loss1_ptr, None))
+        return float(self._loss1[0])
 
     def train_step_count(self, agent=0):
         ts = C.c_int64(0)

@@ -57,10 +57,15 @@ class ReplayBuffer:
             _engine = DqnEngine(self._obs_dim, 4, self._buffer_size, 1, 0.0, adam(0.0), device=device, seed=seed)
         self._engine, self._agent = _engine, _agent
         d = self._obs_dim
-        # one-transition staging arrays reused by add() (the C side copies them into a pinned slot)
-        self._s1, self._o1 = np.zeros((1, d), np.float32), np.zeros((1, d), np.float32)
-        self._a1, self._r1, self._d1 = np.zeros(1, np.int64), np.zeros(1, np.float32), np.zeros(1, np.bool_)
-        self._ptrs = tuple(_lib.ptr(x) for x in (self._s1, self._a1, self._r1, self._o1, self._d1))
+        # host staging for add(): transitions are appended here and moved to the device ring by ONE
+        # coalesced store right before anything can observe the ring (train step, sample, export, size
+        # of the device counter).  Semantically identical to n scalar adds; it turns the reference's
+        # 4 adds per train step (train_frequency, Test/lunar_lander.py:30) into one H2D copy + one launch.
+        self._cap = 64
+        self._ps, self._po = np.zeros((self._cap, d), np.float32), np.zeros((self._cap, d), np.float32)
+        self._pa, self._pr, self._pd = np.zeros(self._cap, np.int64), np.zeros(self._cap, np.float32), np.zeros(self._cap, np.bool_)
+        self._ptrs = tuple(_lib.ptr(x) for x in (self._ps, self._pa, self._pr, self._po, self._pd))
+        self._pending = 0
         self._counter = 0
         self._num_samples = 0
         self._sample_calls = 0
@@ -77,29 +82,42 @@ class ReplayBuffer:
     dones = property(lambda self: RingView(self, "dones"))
 
     def add(self, state, action, reward, observation, done):
-        self._s1[0] = state
-        self._a1[0] = action
-        self._r1[0] = reward
-        self._o1[0] = observation
-        self._d1[0] = done
-        e = self._engine
-        _lib.check(e.lib.dqn_store(e.h, self._agent, 1, *self._ptrs))
+        i = self._pending
+        self._ps[i] = state
+        self._pa[i] = action
+        self._pr[i] = reward
+        self._po[i] = observation
+        self._pd[i] = done
+        self._pending = i + 1
         self._counter += 1
         self._num_samples = min(self._counter, self._buffer_size)
+        if self._pending == self._cap:
+            self.flush()
+
+    def flush(self):
+        """Move staged add() transitions into the device ring (no-op when nothing is pending)."""
+        n = self._pending
+        if n:
+            e = self._engine
+            _lib.check(e.lib.dqn_store(e.h, self._agent, n, *self._ptrs))
+            self._pending = 0
 
     # -- vectorised extension ------------------------------------------------------------------------
     def add_many(self, states, actions, rewards, observations, dones):
         """n ``add`` calls in order, as one coalesced device store."""
+        self.flush()
         self._engine.store(states, actions, rewards, observations, dones, agent=self._agent)
         self._counter += len(np.asarray(actions))
         self._num_samples = min(self._counter, self._buffer_size)
 
     def sample(self, batch_size, indices=None):
+        self.flush()
         step = self._sample_calls
         self._sample_calls += 1
         return self._engine.sample_batch(batch_size, indices=indices, step=step, agent=self._agent)
 
     def _export(self):
+        self.flush()
         return self._engine.buffer_export(self._agent)
 
 
