@@ -383,6 +383,79 @@ def bench_gather(torch, dqn_b200, eng, device, peak):
             "frac_of_hbm_peak": gbs / peak, "note": "ring (96 MB) fits in L2; see profiles/ for the >L2 ring measurement"}
 
 
+def run_population(args):
+    """BASELINE configs[2]: 1024 independent agents of the hyper-parameter sweep (per-agent gamma, batch in
+    [38,70), Adam 1e-4, 40k-slot ring each), one CTA per agent, sharded over the ranks with NO data-path
+    collective.  `value` = aggregate agent-train-steps/s; total work is fixed -> strong scaling."""
+    import ctypes as C
+    import torch
+    import dqn_b200
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    n_global, ring = args.agents, 40_000                         # Test/lunar_lander_hyper_params.py:22
+    pop = dqn_b200.Population(n_global, D, A, ring, dqn_b200.adam(1e-4), rank=rank, world_size=world, seed=1, device=local)
+    eng, lib, chk = pop.engine, pop.engine.lib, dqn_b200.pkg._lib.check
+    # synthetic transitions generated on the device (torch as RNG/allocator only), one block per agent
+    g = torch.Generator(device=device)
+    for i in range(pop.n_local):
+        g.manual_seed(1000 + pop.global_id(i))
+        s = torch.randn(ring, D, generator=g, device=device)
+        s2 = torch.randn(ring, D, generator=g, device=device)
+        r = 2.0 * torch.randn(ring, generator=g, device=device)
+        a = torch.randint(0, A, (ring,), generator=g, device=device, dtype=torch.int64)
+        d = (torch.rand(ring, generator=g, device=device) < 0.01).to(torch.uint8)
+        chk(lib.dqn_store_device(eng.h, i, ring, C.c_void_p(s.data_ptr()), C.c_void_p(a.data_ptr()), C.c_void_p(r.data_ptr()),
+                                 C.c_void_p(s2.data_ptr()), C.c_void_p(d.data_ptr())))
+    torch.cuda.synchronize(device)
+    kpl = args.steps_per_launch
+    steps = max(kpl, (args.steps // kpl) * kpl)
+    pop.train_steps(max(args.warmup, 3))
+    flush_l2(torch, device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(steps // kpl):
+            pop.train_steps(kpl)
+        e1.record()
+        torch.cuda.synchronize(device)
+    secs = e0.elapsed_time(e1) * 1e-3
+    t = torch.tensor([secs], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs_max = float(t.item())
+    if rank == 0:
+        mean_b = float(np.mean([h["batch_size"] for h in dqn_b200.sweep_hparams(n_global)]))
+        value = n_global * steps / secs_max
+        sm_hz = (clk.summary()["sm_mhz"] or 1965) * 1e6
+        fp32_peak = world * 148 * 128 * 2 * sm_hz / 1e9
+        flops = value * mean_b * FLOP_PER_SAMPLE / 1e9
+        peak, peak_src = measured_peaks()
+        gbs = value * mean_b * REC_BYTES_ALGO / 1e9
+        print(json.dumps({
+            "metric": "agent_train_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": secs_max / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: population of %d independent sweep agents, one CTA per agent, sharded over ranks, no collective" % n_global,
+                       "obs_dim": D, "num_actions": A, "hidden": [32, 64], "ring_slots_per_agent": ring, "mean_batch": mean_b,
+                       "optimizer": "adam(1e-4)", "steps_per_launch": kpl, "l2": "rings total %.1f GB per rank >> L2" % (pop.n_local * ring * 96 / 1e9)},
+            "clocks": clk.summary(), "gpu_launches": steps // kpl,
+            "replay_samples_per_sec": value * mean_b,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s", "frac": gbs / (peak * world), "traffic": None,
+                         "kernel": "dqn_train_fused_kernel<4>", "peak_source": peak_src,
+                         "note": "compute-bound on the fp32 pipe, not HBM: see fp32",
+                         "fp32": {"achieved_gflops": flops, "ffma_peak_gflops": fp32_peak, "frac": flops / fp32_peak}}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -391,6 +464,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid (ncu): only the fused timed region, no e2e / extras / cpu baseline; not a bench value")
+    ap.add_argument("--workload", default="single", choices=["single", "population"])
+    ap.add_argument("--agents", type=int, default=1024)
+    ap.add_argument("--steps-per-launch", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -399,8 +475,11 @@ def main():
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--workload", args.workload, "--agents", str(args.agents), "--steps-per-launch", str(args.steps_per_launch)]
         sys.exit(subprocess.call(cmd))
+    if args.workload == "population":
+        return run_population(args)
     run_single(args)
 
 
