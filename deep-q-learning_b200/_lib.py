@@ -45,6 +45,17 @@ class DqnDebugTaps(C.Structure):
                 ("max_actions", C.c_void_p), ("targets", C.c_void_p), ("loss", C.c_void_p), ("grads", C.c_void_p)]
 
 
+class DqnLbConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32), ("obs_dim", C.c_int32), ("num_actions", C.c_int32),
+        ("hidden1", C.c_int32), ("hidden2", C.c_int32), ("batch_local", C.c_int32), ("gemm_mode", C.c_int32),
+        ("buffer_size", C.c_int64), ("gamma", C.c_float), ("opt_kind", C.c_int32),
+        ("lr", C.c_float), ("b1", C.c_float), ("b2", C.c_float), ("eps", C.c_float), ("eps_root", C.c_float),
+        ("weight_decay", C.c_float), ("seed", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32),
+        ("stream", C.c_void_p), ("arena", C.c_void_p), ("arena_bytes", C.c_uint64),
+    ]
+
+
 _H = C.c_void_p          # dqn_handle*
 _P = C.c_void_p          # any data pointer
 _i32, _i64 = C.c_int32, C.c_int64
@@ -77,6 +88,25 @@ PROTOTYPES = {
     "dqn_sync_target": (C.c_int, [_H, _i32, _i32]),
     "dqn_act": (C.c_int, [_H, _i32, _P, C.POINTER(_i32)]),
     "dqn_act_batch": (C.c_int, [_H, _i32, _i32, _P, _P]),
+    # large-batch data-parallel mode
+    "dqn_lb_arena_bytes": (C.c_int, [C.POINTER(DqnLbConfig), C.POINTER(C.c_uint64)]),
+    "dqn_lb_create": (C.c_int, [C.POINTER(DqnLbConfig), C.POINTER(_H)]),
+    "dqn_lb_destroy": (C.c_int, [_H]),
+    "dqn_lb_param_count": (C.c_int, [_H, C.POINTER(_i32)]),
+    "dqn_lb_set_params": (C.c_int, [_H, _i32, _P, _i32]),
+    "dqn_lb_get_params": (C.c_int, [_H, _i32, _P, _i32]),
+    "dqn_lb_set_opt_state": (C.c_int, [_H, _i32, _P, _P, _i32]),
+    "dqn_lb_get_opt_state": (C.c_int, [_H, C.POINTER(_i32), _P, _P, _i32]),
+    "dqn_lb_store": (C.c_int, [_H, _i64, _P, _P, _P, _P, _P]),
+    "dqn_lb_store_device": (C.c_int, [_H, _i64, _P, _P, _P, _P, _P]),
+    "dqn_lb_buffer_state": (C.c_int, [_H, C.POINTER(_i64), C.POINTER(_i64)]),
+    "dqn_lb_forward_backward": (C.c_int, [_H, _P, _i32]),
+    "dqn_lb_grads": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(_i64)]),
+    "dqn_lb_apply": (C.c_int, [_H]),
+    "dqn_lb_sync_target": (C.c_int, [_H]),
+    "dqn_lb_get_loss": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "dqn_lb_debug_read": (C.c_int, [_H, _i32, _P, C.c_uint64]),
+    "dqn_lb_synchronize": (C.c_int, [_H]),
 }
 
 _lib = None

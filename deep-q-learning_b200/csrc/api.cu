@@ -20,6 +20,11 @@ int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+}  // namespace
+namespace dqn {
+void set_last_error(const char* msg) { g_err = msg; }
+}
+namespace {
 
 #define CU(expr)                                                                                   \
   do {                                                                                             \

@@ -5,6 +5,8 @@
 
 namespace dqn {
 
+void set_last_error(const char* msg);   // thread-local message behind dqn_last_error()
+
 // Device-pointer taps of one train step (see dqn_debug_taps in include/dqn_b200.h).
 struct TapsDev {
   long long* indices;
@@ -37,8 +39,9 @@ struct TrainArgs {
 cudaError_t launch_replay_store(cudaStream_t st, uint32_t* ring, const Dims& d, long long counter, long long n,
                                 const float* s, const long long* a, const float* r, const float* s2,
                                 const uint8_t* done, AgentCtl* ctl);
+// out[i] = Philox slot index of sample (first + i) of `step` -- `first` lets a data-parallel rank draw its slice
 cudaError_t launch_philox_indices(cudaStream_t st, long long* out, int batch, uint64_t seed, int agent,
-                                  long long step, long long size);
+                                  long long step, long long size, int first = 0);
 // mode: 0 explicit idx, 1 Philox(seed, agent, step), 2 identity (export)
 cudaError_t launch_replay_gather(cudaStream_t st, const uint32_t* ring, const Dims& d, int mode, const long long* idx,
                                  uint64_t seed, int agent, long long step, long long size, long long batch,

@@ -1,0 +1,51 @@
+// large.h -- internal declarations of the large-batch data-parallel path (mlp_large.cu, gemm_tc.cu, api_lb.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dqn {
+
+enum { kEpiSplitK = 0, kEpiBiasRelu = 1, kEpiReluMask = 2 };
+enum { kGemmNN_BiasRelu = 0, kGemmNT_ReluMask = 1, kGemmTN_SplitK = 2 };
+enum { kGemmModeFFMA = 0, kGemmModeTC3xTF32 = 1 };
+
+struct LbDims {
+  int D, A, H1, H2;
+  int B;          // local batch rows (multiple of 128)
+  int P, PF;      // flat parameter count (+1 slot for the loss lives at grads[P]); PF = padded stride
+  int recw;
+  long long N;    // ring slots
+};
+
+struct LbTaps {
+  float* targets;     // [B][A]
+  int* max_actions;   // [B]
+  int enabled;
+};
+
+struct LbWorkspace {
+  float *theta, *theta_t, *mu, *nu, *grads;       // flat layout, PF floats each (grads has the loss at [P])
+  float *s, *r, *s2; long long* a; uint8_t* done; long long* idx;   // gathered local batch (SoA)
+  float *H1, *H2;      // [3B][H1], [3B][H2]   rows: (theta,s) | (theta,s') | (theta^-,s')
+  float *Q;            // [3B][A]
+  float *dhd;          // [B][8]
+  float *dH2, *dH1;    // [B][H2], [B][H1]
+  float *partial;      // [nblk][16]  targets-kernel block partials
+  float *colpart;      // column-sum partials  [B/128][max((2+kMaxA)*H2, (D+1)*H1)]
+  float *colred;       // [(2+kMaxA)*H2]
+  float *gemmpart;     // split-K partials [16][H1*H2]
+  float *tc_scratch;   // tcgen05 path: hi/lo operand splits
+};
+
+cudaError_t lb_gemm_ffma(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                         float* C, int ldc, const float* aux, int ldaux, int splitk);
+cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                       float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws);
+// dispatcher (gemm_mode: kGemmModeFFMA / kGemmModeTC3xTF32)
+cudaError_t lb_gemm(cudaStream_t st, int gemm_mode, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                    float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws);
+cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float gamma, float inv_global_batch,
+                                int gemm_mode, const LbTaps& taps);
+cudaError_t lb_adam(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float b1, float b2, float c1, float c2,
+                    float eps, float eps_root, float lr, float wd);
+
+}  // namespace dqn

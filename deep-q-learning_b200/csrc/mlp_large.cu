@@ -1,0 +1,459 @@
+// mlp_large.cu -- large-batch / wide-hidden dueling double-DQN step (BASELINE configs[3]: B = 65536,
+// hidden 1024x1024), data-parallel over GPUs.  Same arithmetic as the fused small-batch kernel
+// (q_learning_functions.py:14-64, dddqn.py:24-34), but here the layers are real dense contractions, so
+// the step is a sequence of kernels over HBM-resident activations:
+//
+//   gather (replay.cu) -> layer1 (K = D, elementwise-bound) -> GEMM NN + bias + relu (h2)
+//   -> head + dueling -> targets / Huber / d(head) -> fused {dH2, dWh, db2 partials}
+//   -> GEMM TN split-K (dW2) -> GEMM NT + relu' mask (dH1) -> fused {dW1, db1 partials}
+//   -> [NCCL all-reduce of the flat gradient + loss, done by the caller] -> Adam
+//
+// The three big GEMM shapes go through launch_gemm(), which dispatches to the fp32 FFMA2 tile kernel in
+// this file (exact fp32, the parity baseline) or to the tcgen05 3xTF32 kernel (gemm_tc.cu) when enabled.
+#include "common.cuh"
+#include "kernels.h"
+#include "large.h"
+
+namespace dqn {
+
+namespace {
+
+typedef unsigned long long u64;
+__device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
+// ------------------------------------------------------------------------------------------------
+// layer 1: H1[row][:] = relu(x[row] . W1 + b1).  rows [0,B): (theta, s); [B,2B): (theta, s'); [2B,3B): (theta^-, s')
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lb_layer1_kernel(const float* __restrict__ s, const float* __restrict__ s2, const float* __restrict__ theta,
+                 const float* __restrict__ theta_t, float* __restrict__ H1, int B, int D, int H1n) {
+  const int j4 = blockIdx.x * blockDim.x + threadIdx.x;      // float4 column index
+  if (j4 * 4 >= H1n) return;
+  const int pass = blockIdx.z;                                 // 0: theta on s, 1: theta on s', 2: theta^- on s'
+  const float* W1 = pass == 2 ? theta_t : theta;
+  const float* b1 = W1 + (size_t)D * H1n;
+  const float* x = pass == 0 ? s : s2;
+  float4 w[kMaxD];
+#pragma unroll
+  for (int d = 0; d < kMaxD; ++d) if (d < D) w[d] = *reinterpret_cast<const float4*>(W1 + (size_t)d * H1n + 4 * j4);
+  const float4 bias = *reinterpret_cast<const float4*>(b1 + 4 * j4);
+  for (int r = blockIdx.y; r < B; r += gridDim.y) {
+    float4 acc = bias;
+#pragma unroll
+    for (int d = 0; d < kMaxD; ++d) if (d < D) {
+      const float xv = __ldg(x + (size_t)r * D + d);
+      acc.x = fmaf(xv, w[d].x, acc.x); acc.y = fmaf(xv, w[d].y, acc.y); acc.z = fmaf(xv, w[d].z, acc.z); acc.w = fmaf(xv, w[d].w, acc.w);
+    }
+    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+    *reinterpret_cast<float4*>(H1 + ((size_t)pass * B + r) * H1n + 4 * j4) = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 tile GEMM (FFMA2): C[M,N] = op(A) * op(B) with fused epilogues.  128x128x16 tiles, 256 threads,
+// 8x8 outputs per thread (as 2x2 blocks of 4x4), double-buffered shared memory.
+//   TA = false: A[M][K] row-major      TA = true: A[K][M] row-major
+//   TB = false: B[K][N] row-major      TB = true: B[N][K] row-major
+// M, N multiples of 128; K (per split) a multiple of 16.
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 16;
+
+template <bool TA, bool TB, int EPI>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+             float* __restrict__ C, int ldc, const float* __restrict__ aux, int ldaux, int k_per_split) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int nk = k_per_split / BK;
+  if (EPI == kEpiSplitK) C += (size_t)blockIdx.z * M * ldc;
+
+  float4 ra[2], rb[2];
+  auto gload = [&](int kt) {
+    const int k0 = kbeg + kt * BK;
+    if (!TA) {        // A[m][k]: thread -> row m = tid & 127, k-octet = tid >> 7
+      const float* p = A + (size_t)(m0 + (tid & 127)) * lda + k0 + 8 * (tid >> 7);
+      ra[0] = *reinterpret_cast<const float4*>(p); ra[1] = *reinterpret_cast<const float4*>(p + 4);
+    } else {          // A[k][m]: thread -> k = tid >> 5 (+8), m4 = tid & 31
+      const float* p = A + (size_t)(k0 + (tid >> 5)) * lda + m0 + 4 * (tid & 31);
+      ra[0] = *reinterpret_cast<const float4*>(p); ra[1] = *reinterpret_cast<const float4*>(p + (size_t)8 * lda);
+    }
+    if (TB) {         // B[n][k]
+      const float* p = Bm + (size_t)(n0 + (tid & 127)) * ldb + k0 + 8 * (tid >> 7);
+      rb[0] = *reinterpret_cast<const float4*>(p); rb[1] = *reinterpret_cast<const float4*>(p + 4);
+    } else {          // B[k][n]
+      const float* p = Bm + (size_t)(k0 + (tid >> 5)) * ldb + n0 + 4 * (tid & 31);
+      rb[0] = *reinterpret_cast<const float4*>(p); rb[1] = *reinterpret_cast<const float4*>(p + (size_t)8 * ldb);
+    }
+  };
+  auto sstore = [&](int buf) {
+    if (!TA) {
+      const int m = tid & 127, kq = 8 * (tid >> 7);
+      As[buf][kq + 0][m] = ra[0].x; As[buf][kq + 1][m] = ra[0].y; As[buf][kq + 2][m] = ra[0].z; As[buf][kq + 3][m] = ra[0].w;
+      As[buf][kq + 4][m] = ra[1].x; As[buf][kq + 5][m] = ra[1].y; As[buf][kq + 6][m] = ra[1].z; As[buf][kq + 7][m] = ra[1].w;
+    } else {
+      *reinterpret_cast<float4*>(&As[buf][tid >> 5][4 * (tid & 31)]) = ra[0];
+      *reinterpret_cast<float4*>(&As[buf][(tid >> 5) + 8][4 * (tid & 31)]) = ra[1];
+    }
+    if (TB) {
+      const int n = tid & 127, kq = 8 * (tid >> 7);
+      Bs[buf][kq + 0][n] = rb[0].x; Bs[buf][kq + 1][n] = rb[0].y; Bs[buf][kq + 2][n] = rb[0].z; Bs[buf][kq + 3][n] = rb[0].w;
+      Bs[buf][kq + 4][n] = rb[1].x; Bs[buf][kq + 5][n] = rb[1].y; Bs[buf][kq + 6][n] = rb[1].z; Bs[buf][kq + 7][n] = rb[1].w;
+    } else {
+      *reinterpret_cast<float4*>(&Bs[buf][tid >> 5][4 * (tid & 31)]) = rb[0];
+      *reinterpret_cast<float4*>(&Bs[buf][(tid >> 5) + 8][4 * (tid & 31)]) = rb[1];
+    }
+  };
+
+  u64 acc[8][4];     // rows: 4*ty + i (i<4) and 64 + 4*ty + i;  column pairs: 4*tx + {0,1},{2,3} and 64 + ...
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload(kt + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][4 * ty]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + 4 * ty]);
+      const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(&Bs[buf][k][4 * tx]);
+      const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(&Bs[buf][k][64 + 4 * tx]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const u64 aa = pack2(av[i], av[i]);
+        ffma2(acc[i][0], aa, b0.x); ffma2(acc[i][1], aa, b0.y); ffma2(acc[i][2], aa, b1.x); ffma2(acc[i][3], aa, b1.y);
+      }
+    }
+    if (kt + 1 < nk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + 64 * h + 4 * tx;
+      float4 v;
+      unpack2(acc[i][2 * h], v.x, v.y);
+      unpack2(acc[i][2 * h + 1], v.z, v.w);
+      if (EPI == kEpiBiasRelu) {
+        const float4 b = *reinterpret_cast<const float4*>(aux + n);
+        v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+      } else if (EPI == kEpiReluMask) {
+        const float4 h1 = *reinterpret_cast<const float4*>(aux + (size_t)m * ldaux + n);
+        v.x = h1.x > 0.f ? v.x : 0.f; v.y = h1.y > 0.f ? v.y : 0.f; v.z = h1.z > 0.f ? v.z : 0.f; v.w = h1.w > 0.f ? v.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = v;
+    }
+  }
+}
+
+// out[i] = sum_z part[z][i]  (fixed order -> deterministic), i < n
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int nz, long long zstride) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < nz; ++z) s += part[(size_t)z * zstride + i];
+  out[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: Q = V + Adv - mean(Adv)  (dddqn.py:29-31).  One warp per row, rows [0,3B).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lb_head_kernel(const float* __restrict__ H2, const float* __restrict__ theta, const float* __restrict__ theta_t,
+               float* __restrict__ Q, int B, int H2n, int A, int offWv) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= 3 * B) return;
+  const float* th = row >= 2 * B ? theta_t : theta;
+  const float* Wv = th + offWv;
+  const float* bv = Wv + H2n;
+  const float* Wa = bv + 1;
+  const float* ba = Wa + (size_t)H2n * A;
+  const float* h = H2 + (size_t)row * H2n;
+  float acc[1 + kMaxA];
+#pragma unroll
+  for (int c = 0; c <= kMaxA; ++c) acc[c] = 0.f;
+  for (int k = lane; k < H2n; k += 32) {
+    const float hv = h[k];
+    acc[0] = fmaf(hv, __ldg(Wv + k), acc[0]);
+#pragma unroll
+    for (int j = 0; j < kMaxA; ++j) if (j < A) acc[1 + j] = fmaf(hv, __ldg(Wa + (size_t)k * A + j), acc[1 + j]);
+  }
+#pragma unroll
+  for (int c = 0; c <= kMaxA; ++c)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  if (lane == 0) {
+    const float val = acc[0] + bv[0];
+    float msum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxA; ++j) if (j < A) { acc[1 + j] += ba[j]; msum += acc[1 + j]; }
+    const float mean = msum / (float)A;
+#pragma unroll
+    for (int j = 0; j < kMaxA; ++j) if (j < A) Q[(size_t)row * A + j] = val + acc[1 + j] - mean;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// targets + Huber + d(head)   (q_learning_functions.py:55-59, :35-36).  One thread per sample.
+// dhd[i][0] = dV, dhd[i][1+j] = dAdv_j;  per-block partial sums of loss and of dhd columns (-> d head bias).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lb_targets_kernel(const float* __restrict__ Q, const long long* __restrict__ act, const float* __restrict__ rew,
+                  const uint8_t* __restrict__ done, float* __restrict__ dhd, float* __restrict__ partial,
+                  int B, int A, float gamma, float inv_global_batch, LbTaps taps) {
+  __shared__ float red[8][2 + kMaxA];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float vals[2 + kMaxA];
+#pragma unroll
+  for (int c = 0; c < 2 + kMaxA; ++c) vals[c] = 0.f;
+  if (i < B) {
+    float q[kMaxA], nq[kMaxA], nqt[kMaxA];
+#pragma unroll
+    for (int j = 0; j < kMaxA; ++j) if (j < A) {
+      q[j] = Q[(size_t)i * A + j]; nq[j] = Q[(size_t)(B + i) * A + j]; nqt[j] = Q[(size_t)(2 * B + i) * A + j];
+    }
+    int astar = 0; float best = nq[0];
+#pragma unroll
+    for (int j = 1; j < kMaxA; ++j) if (j < A && nq[j] > best) { best = nq[j]; astar = j; }
+    long long al = act[i];
+    const int a = al < 0 ? 0 : (al >= A ? A - 1 : (int)al);
+    float qa = q[0], nt = nqt[0];
+#pragma unroll
+    for (int j = 1; j < kMaxA; ++j) if (j < A) { if (j == a) qa = q[j]; if (j == astar) nt = nqt[j]; }
+    const float d = done[i] ? 1.f : 0.f;
+    const float tv = rew[i] + (1.0f - d) * (gamma * nt - qa);
+    const float tgt = qa + tv;
+    const float e = qa - tgt;
+    const float ae = fabsf(e), quad = fminf(ae, 1.0f);
+    vals[0] = (0.5f * quad * quad + (ae - quad)) * inv_global_batch;
+    const float gi = fminf(fmaxf(e, -1.0f), 1.0f) * inv_global_batch;
+    dhd[(size_t)i * 8 + 0] = gi;
+    vals[1] = gi;
+#pragma unroll
+    for (int j = 0; j < kMaxA; ++j) {
+      const float dadv = j < A ? (j == a ? gi : 0.f) - gi / (float)A : 0.f;
+      dhd[(size_t)i * 8 + 1 + j] = dadv;
+      vals[2 + j] = dadv;
+    }
+    if (taps.enabled) {
+      for (int j = 0; j < A; ++j) taps.targets[(size_t)i * A + j] = j == a ? tgt : q[j];
+      taps.max_actions[i] = astar;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 2 + kMaxA; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vals[c] += __shfl_xor_sync(0xffffffffu, vals[c], o);
+    if (lane == 0) red[warp][c] = vals[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 + kMaxA) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * 16 + threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused pass over H2(theta, s):  dH2 = relu'(h2) * (dhd . Wh^T);  partial column sums for dWh and db2.
+// thread = one hidden unit j, block = 256 units x RC rows.   part[chunk][c][j], c: 0..A = dWh cols, A+1 = db2
+// ------------------------------------------------------------------------------------------------
+constexpr int RC = 128;
+__global__ void __launch_bounds__(256)
+lb_dh2_kernel(const float* __restrict__ H2s, const float* __restrict__ dhd, const float* __restrict__ theta,
+              float* __restrict__ dH2, float* __restrict__ part, int B, int H2n, int A, int offWv) {
+  __shared__ float sd[RC][8];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * RC;
+  for (int q = threadIdx.x; q < RC * 8; q += blockDim.x) sd[q >> 3][q & 7] = dhd[(size_t)r0 * 8 + q];
+  __syncthreads();
+  const float* Wv = theta + offWv;
+  const float* Wa = Wv + H2n + 1;
+  float wh[1 + kMaxA], acc[2 + kMaxA];
+  wh[0] = Wv[j];
+#pragma unroll
+  for (int c = 0; c < kMaxA; ++c) wh[1 + c] = c < A ? Wa[(size_t)j * A + c] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 2 + kMaxA; ++c) acc[c] = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < RC; ++r) {
+    const float h = H2s[(size_t)(r0 + r) * H2n + j];
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c <= kMaxA; ++c) { const float dd = sd[r][c]; v = fmaf(dd, wh[c], v); acc[c] = fmaf(h, dd, acc[c]); }
+    v = h > 0.f ? v : 0.f;
+    dH2[(size_t)(r0 + r) * H2n + j] = v;
+    acc[1 + kMaxA] += v;
+  }
+#pragma unroll
+  for (int c = 0; c < 2 + kMaxA; ++c) part[((size_t)blockIdx.y * (2 + kMaxA) + c) * H2n + j] = acc[c];
+}
+
+// fused pass over dH1: partial sums for dW1[d][k] = sum_r x[r][d] dH1[r][k] and db1[k].  part[chunk][d][k], d = D -> db1
+__global__ void __launch_bounds__(256)
+lb_dw1_kernel(const float* __restrict__ s, const float* __restrict__ dH1, float* __restrict__ part, int B, int D, int H1n) {
+  __shared__ float sx[RC][kMaxD];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * RC;
+  for (int q = threadIdx.x; q < RC * D; q += blockDim.x) sx[q / D][q % D] = s[(size_t)r0 * D + q];
+  __syncthreads();
+  float acc[kMaxD + 1];
+#pragma unroll
+  for (int d = 0; d <= kMaxD; ++d) acc[d] = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < RC; ++r) {
+    const float g = dH1[(size_t)(r0 + r) * H1n + k];
+#pragma unroll
+    for (int d = 0; d < kMaxD; ++d) if (d < D) acc[d] = fmaf(sx[r][d], g, acc[d]);
+    acc[kMaxD] += g;
+  }
+  for (int d = 0; d < D; ++d) part[((size_t)blockIdx.y * (D + 1) + d) * H1n + k] = acc[d];
+  part[((size_t)blockIdx.y * (D + 1) + D) * H1n + k] = acc[kMaxD];
+}
+
+// scatter the reduced head partials [c][j] into the flat gradient: c = 0 -> dWv[j], 1..A -> dWa[j][c-1], A+1 (index 1+kMaxA) -> db2[j]
+__global__ void __launch_bounds__(256)
+lb_head_grads_kernel(const float* __restrict__ red, float* __restrict__ grads, int H2n, int A, int offb2, int offWv) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H2n) return;
+  grads[offWv + j] = red[j];
+  float* gWa = grads + offWv + H2n + 1;
+  for (int c = 0; c < A; ++c) gWa[(size_t)j * A + c] = red[(size_t)(1 + c) * H2n + j];
+  grads[offb2 + j] = red[(size_t)(1 + kMaxA) * H2n + j];
+}
+
+// final reduction of the targets-kernel partials: loss -> grads[P] (extra slot), d head bias -> grads
+__global__ void lb_finish_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ grads, int P, int A, int offbv) {
+  const int c = threadIdx.x;
+  if (c >= 2 + kMaxA) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * 16 + c];
+  if (c == 0) grads[P] = s;                       // loss (local share of the global mean), extra slot after the P gradients
+  else if (c == 1) grads[offbv] = s;              // d bv
+}
+
+// d ba lives after Wa: separate tiny kernel keeps the index arithmetic readable
+__global__ void lb_finish_ba_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ grads, int A, int offba) {
+  const int c = threadIdx.x;
+  if (c >= A) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * 16 + 2 + c];
+  grads[offba + c] = s;
+}
+
+// optax adam / adamw, exact fp32 (memory-bound: IEEE division and sqrt are free here)
+__global__ void __launch_bounds__(256)
+lb_adam_kernel(float* __restrict__ theta, float* __restrict__ mu, float* __restrict__ nu, const float* __restrict__ g,
+               int P, float b1, float b2, float c1, float c2, float eps, float eps_root, float lr, float wd) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float gr = g[p];
+  const float m = b1 * mu[p] + (1.0f - b1) * gr;
+  const float v = b2 * nu[p] + (1.0f - b2) * (gr * gr);
+  mu[p] = m; nu[p] = v;
+  float u = (m / c1) / (sqrtf(v / c2 + eps_root) + eps);
+  const float th = theta[p];
+  if (wd != 0.f) u = u + wd * th;
+  theta[p] = th + (-lr) * u;
+}
+
+template <bool TA, bool TB, int EPI>
+cudaError_t launch_sgemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                         float* C, int ldc, const float* aux, int ldaux, int splitk) {
+  dim3 grid(N / BN, M / BM, splitk);
+  sgemm_kernel<TA, TB, EPI><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, K / splitk);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t lb_gemm_ffma(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                         float* C, int ldc, const float* aux, int ldaux, int splitk) {
+  switch (kind) {
+    case kGemmNN_BiasRelu: return launch_sgemm<false, false, kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
+    case kGemmNT_ReluMask: return launch_sgemm<false, true, kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
+    case kGemmTN_SplitK: return launch_sgemm<true, false, kEpiSplitK>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, splitk);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+#define LBCHK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+
+// One forward/backward pass over the local batch already gathered into ws.s/a/r/s2/done.
+cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float gamma, float inv_global_batch,
+                                int gemm_mode, const LbTaps& taps) {
+  const int B = d.B, H1n = d.H1, H2n = d.H2, D = d.D, A = d.A;
+  const int offb1 = D * H1n, offW2 = offb1 + H1n, offb2 = offW2 + H1n * H2n, offWv = offb2 + H2n;
+  const int offbv = offWv + H2n, offba = offbv + 1 + H2n * A;
+  // ---- forward ----
+  {
+    dim3 grid((H1n / 4 + 255) / 256, B < 1024 ? B : 1024, 3);
+    lb_layer1_kernel<<<grid, 256, 0, st>>>(ws.s, ws.s2, ws.theta, ws.theta_t, ws.H1, B, D, H1n);
+    LBCHK(cudaGetLastError());
+  }
+  LBCHK(lb_gemm(st, gemm_mode, kGemmNN_BiasRelu, 2 * B, H2n, H1n, ws.H1, H1n, ws.theta + offW2, H2n, ws.H2, H2n, ws.theta + offb2, 0, 1, ws));
+  LBCHK(lb_gemm(st, gemm_mode, kGemmNN_BiasRelu, B, H2n, H1n, ws.H1 + (size_t)2 * B * H1n, H1n, ws.theta_t + offW2, H2n,
+                ws.H2 + (size_t)2 * B * H2n, H2n, ws.theta_t + offb2, 0, 1, ws));
+  lb_head_kernel<<<(3 * B + 7) / 8, 256, 0, st>>>(ws.H2, ws.theta, ws.theta_t, ws.Q, B, H2n, A, offWv);
+  LBCHK(cudaGetLastError());
+  const int nblk = (B + 255) / 256;
+  lb_targets_kernel<<<nblk, 256, 0, st>>>(ws.Q, ws.a, ws.r, ws.done, ws.dhd, ws.partial, B, A, gamma, inv_global_batch, taps);
+  LBCHK(cudaGetLastError());
+  lb_finish_kernel<<<1, 32, 0, st>>>(ws.partial, nblk, ws.grads, d.P, A, offbv);
+  lb_finish_ba_kernel<<<1, 32, 0, st>>>(ws.partial, nblk, ws.grads, A, offba);
+  LBCHK(cudaGetLastError());
+  // ---- backward ----
+  const int nchunk = B / RC;
+  {
+    dim3 grid(H2n / 256, nchunk);
+    lb_dh2_kernel<<<grid, 256, 0, st>>>(ws.H2, ws.dhd, ws.theta, ws.dH2, ws.colpart, B, H2n, A, offWv);
+    LBCHK(cudaGetLastError());
+    const long long n = (long long)(2 + kMaxA) * H2n;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.colpart, ws.colred, n, nchunk, n);
+    lb_head_grads_kernel<<<(H2n + 255) / 256, 256, 0, st>>>(ws.colred, ws.grads, H2n, A, offb2, offWv);
+    LBCHK(cudaGetLastError());
+  }
+  {   // dW2 = H1s^T . dH2  (reduction over the batch rows): split-K partials, fixed-order reduce
+    int splitk = 1;
+    while (splitk < 16 && (H1n / BM) * (H2n / BN) * splitk < 296 && (B / (splitk * 2)) % BK == 0 && B / (splitk * 2) >= 256) splitk *= 2;
+    LBCHK(lb_gemm(st, gemm_mode, kGemmTN_SplitK, H1n, H2n, B, ws.H1, H1n, ws.dH2, H2n, ws.gemmpart, H2n, nullptr, 0, splitk, ws));
+    const long long n = (long long)H1n * H2n;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.gemmpart, ws.grads + offW2, n, splitk, n);
+    LBCHK(cudaGetLastError());
+  }
+  LBCHK(lb_gemm(st, gemm_mode, kGemmNT_ReluMask, B, H1n, H2n, ws.dH2, H2n, ws.theta + offW2, H2n, ws.dH1, H1n, ws.H1, H1n, 1, ws));
+  {
+    dim3 grid(H1n / 256, nchunk);
+    lb_dw1_kernel<<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
+    LBCHK(cudaGetLastError());
+    const long long n = (long long)(D + 1) * H1n;                 // [d][k] == flat [W1 | b1]
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.colpart, ws.grads, n, nchunk, n);
+    LBCHK(cudaGetLastError());
+  }
+  return cudaSuccess;
+}
+
+cudaError_t lb_adam(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float b1, float b2, float c1, float c2,
+                    float eps, float eps_root, float lr, float wd) {
+  lb_adam_kernel<<<(d.P + 255) / 256, 256, 0, st>>>(ws.theta, ws.mu, ws.nu, ws.grads, d.P, b1, b2, c1, c2, eps, eps_root, lr, wd);
+  return cudaGetLastError();
+}
+
+}  // namespace dqn

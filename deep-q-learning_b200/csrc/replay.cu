@@ -43,9 +43,9 @@ replay_store_kernel(uint32_t* __restrict__ ring, long long N, int recw, int D, l
 }
 
 __global__ void __launch_bounds__(256)
-philox_indices_kernel(long long* __restrict__ out, int batch, uint64_t seed, int agent, long long step, long long size) {
+philox_indices_kernel(long long* __restrict__ out, int batch, uint64_t seed, int agent, long long step, long long size, int first) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < batch) out[i] = philox_index(seed, agent, step, i, size);
+  if (i < batch) out[i] = philox_index(seed, agent, step, first + i, size);
 }
 
 // One thread = one 16-byte chunk of one sampled record: a warp reads whole 32-byte sectors of the
@@ -90,8 +90,8 @@ cudaError_t launch_replay_store(cudaStream_t st, uint32_t* ring, const Dims& d, 
 }
 
 cudaError_t launch_philox_indices(cudaStream_t st, long long* out, int batch, uint64_t seed, int agent,
-                                  long long step, long long size) {
-  philox_indices_kernel<<<(batch + 255) / 256, 256, 0, st>>>(out, batch, seed, agent, step, size);
+                                  long long step, long long size, int first) {
+  philox_indices_kernel<<<(batch + 255) / 256, 256, 0, st>>>(out, batch, seed, agent, step, size, first);
   return cudaGetLastError();
 }
 

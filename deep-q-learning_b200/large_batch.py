@@ -1,0 +1,142 @@
+"""Large-batch data-parallel DDQN step (BASELINE configs[3]) over ``dqn_lb_*`` (``include/dqn_b200.h``).
+
+One agent, global minibatch ``B`` split contiguously over ``world_size`` ranks (one process per GPU).
+Per step every rank runs forward + backward on its ``B / world_size`` rows with gradients pre-scaled by
+``1/B`` (the loss of ``q_learning_functions.py:36`` is a mean over the batch, so shard gradients add up),
+the flat gradient (+ the loss, riding in the last slot) is summed with ONE NCCL all-reduce, and every rank
+applies the identical Adam update -- replicas stay bit-identical because they all consume the same
+reduced buffer.  torch is used for the arena allocation and for ``torch.distributed.all_reduce`` on a
+tensor view of the gradient region; all arithmetic is in ``libdqn_b200.so``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .specs import flatten_tree, unflatten_tree, param_count
+
+GEMM_MODES = {"fp32": 0, "tc3xtf32": 1}
+
+
+class LargeBatchTrainer:
+    def __init__(self, obs_dim, num_actions, hidden, batch_global, buffer_size, gamma, optimizer, rank=0,
+                 world_size=1, seed=0, device=0, gemm_mode="fp32", process_group=None):
+        import torch
+        self.torch, self.lib = torch, _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.DqnError(-3, "no CUDA device: the B200 DQN path has no CPU fallback")
+        if batch_global % world_size:
+            raise ValueError("batch_global must be divisible by world_size")
+        self.obs_dim, self.num_actions, self.hidden = int(obs_dim), int(num_actions), tuple(hidden)
+        self.rank, self.world, self.device, self.pg = int(rank), int(world_size), int(device), process_group
+        self.batch_global, self.batch_local = int(batch_global), int(batch_global) // int(world_size)
+        self.P = param_count(obs_dim, num_actions, self.hidden)
+        cfg = _lib.DqnLbConfig()
+        cfg.struct_size = C.sizeof(_lib.DqnLbConfig)
+        cfg.device, cfg.obs_dim, cfg.num_actions = self.device, self.obs_dim, self.num_actions
+        cfg.hidden1, cfg.hidden2, cfg.batch_local = int(hidden[0]), int(hidden[1]), self.batch_local
+        cfg.gemm_mode, cfg.buffer_size, cfg.gamma = GEMM_MODES[gemm_mode], int(buffer_size), float(gamma)
+        cfg.opt_kind = _lib.DQN_OPT_ADAMW if optimizer.kind == "adamw" else _lib.DQN_OPT_ADAM
+        cfg.lr, cfg.b1, cfg.b2 = optimizer.learning_rate, optimizer.b1, optimizer.b2
+        cfg.eps, cfg.eps_root, cfg.weight_decay = optimizer.eps, optimizer.eps_root, optimizer.weight_decay
+        cfg.seed, cfg.rank, cfg.world = int(seed) & 0xFFFFFFFFFFFFFFFF, self.rank, self.world
+        nbytes = C.c_uint64(0)
+        _lib.check(self.lib.dqn_lb_arena_bytes(C.byref(cfg), C.byref(nbytes)))
+        with torch.cuda.device(self.device):
+            self._arena = torch.empty(int(nbytes.value) + 256, dtype=torch.uint8, device=f"cuda:{self.device}")
+            base = (self._arena.data_ptr() + 255) & ~255
+            cfg.arena, cfg.arena_bytes = base, int(nbytes.value)
+            cfg.stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.arena_bytes = int(nbytes.value)
+        h = C.c_void_p()
+        _lib.check(self.lib.dqn_lb_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        ptr, cnt = C.c_void_p(), C.c_int64(0)
+        _lib.check(self.lib.dqn_lb_grads(self.h, C.byref(ptr), C.byref(cnt)))
+        off = ptr.value - self._arena.data_ptr()
+        self.grads = self._arena[off:off + 4 * cnt.value].view(torch.float32)     # P gradients + loss, for the collective
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dqn_lb_destroy(self.h)
+            self.h, self._arena, self.grads = None, None, None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state ----------------------------------------------------------------------------------------
+    def set_params(self, tree, which=0):
+        flat = flatten_tree(tree, self.obs_dim, self.num_actions, self.hidden)
+        _lib.check(self.lib.dqn_lb_set_params(self.h, which, _lib.ptr(flat), flat.size))
+
+    def get_params(self, which=0):
+        out = np.empty(self.P, np.float32)
+        _lib.check(self.lib.dqn_lb_get_params(self.h, which, _lib.ptr(out), out.size))
+        return unflatten_tree(out, self.obs_dim, self.num_actions, self.hidden)
+
+    def get_opt_state(self):
+        mu, nu, cnt = np.empty(self.P, np.float32), np.empty(self.P, np.float32), C.c_int32(0)
+        _lib.check(self.lib.dqn_lb_get_opt_state(self.h, C.byref(cnt), _lib.ptr(mu), _lib.ptr(nu), self.P))
+        return (np.int32(cnt.value), unflatten_tree(mu, self.obs_dim, self.num_actions, self.hidden),
+                unflatten_tree(nu, self.obs_dim, self.num_actions, self.hidden))
+
+    def store(self, s, a, r, s2, done):
+        s, s2, r = (np.ascontiguousarray(x, dtype=np.float32) for x in (s, s2, r))
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        done = np.ascontiguousarray(done, dtype=np.bool_)
+        _lib.check(self.lib.dqn_lb_store(self.h, a.shape[0], _lib.ptr(s), _lib.ptr(a), _lib.ptr(r), _lib.ptr(s2), _lib.ptr(done)))
+
+    def store_device(self, s, a, r, s2, done):
+        """Device tensors (torch): f32[n,D], i64[n], f32[n], f32[n,D], u8[n]."""
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(self.lib.dqn_lb_store_device(self.h, a.shape[0], p(s), p(a), p(r), p(s2), p(done)))
+
+    # -- one train step ---------------------------------------------------------------------------------
+    def forward_backward(self, indices=None, debug=False):
+        idx = None
+        if indices is not None:          # global index list of the step; this rank takes its contiguous slice
+            idx = np.ascontiguousarray(indices, dtype=np.int64)
+            if idx.shape == (self.batch_global,):
+                idx = np.ascontiguousarray(idx[self.rank * self.batch_local:(self.rank + 1) * self.batch_local])
+            elif idx.shape != (self.batch_local,):
+                raise ValueError("indices must have batch_global or batch_local entries")
+        _lib.check(self.lib.dqn_lb_forward_backward(self.h, _lib.ptr(idx), 1 if debug else 0))
+
+    def all_reduce(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def apply(self):
+        _lib.check(self.lib.dqn_lb_apply(self.h))
+
+    def step(self, indices=None):
+        self.forward_backward(indices)
+        self.all_reduce()
+        self.apply()
+
+    def sync_target(self):
+        _lib.check(self.lib.dqn_lb_sync_target(self.h))
+
+    def loss(self):
+        out = C.c_float(0)
+        _lib.check(self.lib.dqn_lb_get_loss(self.h, C.byref(out)))
+        return float(out.value)
+
+    def synchronize(self):
+        _lib.check(self.lib.dqn_lb_synchronize(self.h))
+
+    def debug_read(self):
+        """Intermediates of the last forward_backward(debug=True) as numpy (parity tests)."""
+        B, A = self.batch_local, self.num_actions
+        q = np.empty((3 * B, A), np.float32)
+        tg, ma = np.empty((B, A), np.float32), np.empty(B, np.int32)
+        g, ix = np.empty(self.P + 1, np.float32), np.empty(B, np.int64)
+        for what, arr in ((0, q), (1, tg), (2, ma), (3, g), (4, ix)):
+            _lib.check(self.lib.dqn_lb_debug_read(self.h, what, _lib.ptr(arr), arr.nbytes))
+        return dict(q=q[:B], next_q=q[B:2 * B], next_q_tm=q[2 * B:], targets=tg, max_actions=ma, indices=ix,
+                    loss=float(g[-1]), grads_flat=g[:-1],
+                    grads=unflatten_tree(g[:-1], self.obs_dim, self.num_actions, self.hidden))

@@ -174,6 +174,58 @@ DQN_API int dqn_act(dqn_handle* h, int32_t agent, const float* state, int32_t* a
 /* Batched: agents [agent_begin, agent_end), one state each (host f32[n_sel*D] -> i32[n_sel]). */
 DQN_API int dqn_act_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* states, int32_t* actions_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Large-batch data-parallel mode (BASELINE configs[3]: batch 65536, hidden 1024x1024).  Same update as
+ * Agent._step (q_agent.py:146-169) for ONE agent whose minibatch is split over `world` ranks: every rank
+ * holds replicas of theta / theta^- / Adam state and of the replay ring, runs forward+backward on its
+ * slice [rank*B_local, (rank+1)*B_local) of the global minibatch with gradients pre-scaled by 1/B_global,
+ * the caller all-reduces (sum) the P+1 floats at dqn_lb_grads() -- P gradients + the loss -- over NCCL,
+ * then dqn_lb_apply() runs the identical Adam update on every rank.  world = 1 needs no collective.
+ * hidden1 / hidden2 / batch_local must be multiples of 128 (hidden >= 128).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dqn_lb_config {
+  int32_t struct_size, device;
+  int32_t obs_dim, num_actions, hidden1, hidden2;
+  int32_t batch_local;    /* rows of the minibatch this rank processes */
+  int32_t gemm_mode;      /* 0: fp32 FFMA2 tiles (exact fp32)   1: tcgen05 tensor cores, 3xTF32 split */
+  int64_t buffer_size;
+  float gamma;
+  int32_t opt_kind;
+  float lr, b1, b2, eps, eps_root, weight_decay;
+  uint64_t seed;
+  int32_t rank, world;
+  void* stream;
+  void* arena;
+  uint64_t arena_bytes;
+} dqn_lb_config;
+
+typedef struct dqn_lb_handle dqn_lb_handle;
+enum { DQN_LB_READ_Q = 0, DQN_LB_READ_TARGETS = 1, DQN_LB_READ_MAX_ACTIONS = 2, DQN_LB_READ_GRADS = 3, DQN_LB_READ_INDICES = 4 };
+
+DQN_API int dqn_lb_arena_bytes(const dqn_lb_config* cfg, uint64_t* bytes_out);
+DQN_API int dqn_lb_create(const dqn_lb_config* cfg, dqn_lb_handle** out);
+DQN_API int dqn_lb_destroy(dqn_lb_handle* h);
+DQN_API int dqn_lb_param_count(const dqn_lb_handle* h, int32_t* p_out);
+DQN_API int dqn_lb_set_params(dqn_lb_handle* h, int32_t which, const float* host_flat, int32_t n);
+DQN_API int dqn_lb_get_params(dqn_lb_handle* h, int32_t which, float* host_flat, int32_t n);
+DQN_API int dqn_lb_set_opt_state(dqn_lb_handle* h, int32_t count, const float* mu, const float* nu, int32_t n);
+DQN_API int dqn_lb_get_opt_state(dqn_lb_handle* h, int32_t* count, float* mu, float* nu, int32_t n);
+/* ReplayBuffer.add, vectorised (host / device pointers) -- same ring as the small-batch path. */
+DQN_API int dqn_lb_store(dqn_lb_handle* h, int64_t n, const float* s, const int64_t* a, const float* r, const float* s2, const uint8_t* done);
+DQN_API int dqn_lb_store_device(dqn_lb_handle* h, int64_t n, const float* s, const int64_t* a, const float* r, const float* s2, const uint8_t* done);
+DQN_API int dqn_lb_buffer_state(dqn_lb_handle* h, int64_t* size_out, int64_t* counter_out);
+/* sample (Philox slice of the global draw, or `idx` = host i64[batch_local]) -> targets -> loss -> backward.
+ * Leaves the local gradient (already divided by the global batch) and loss share at dqn_lb_grads(). */
+DQN_API int dqn_lb_forward_backward(dqn_lb_handle* h, const int64_t* idx, int32_t debug);
+DQN_API int dqn_lb_grads(dqn_lb_handle* h, void** dev_ptr_out, int64_t* count_out);
+/* optimizer.update + apply_updates (q_learning_functions.py:24-25) with whatever is in the gradient buffer. */
+DQN_API int dqn_lb_apply(dqn_lb_handle* h);
+DQN_API int dqn_lb_sync_target(dqn_lb_handle* h);
+DQN_API int dqn_lb_get_loss(dqn_lb_handle* h, float* loss_out);
+/* parity taps after dqn_lb_forward_backward(debug = 1): `what` = DQN_LB_READ_*; Q is [3*B][A] (q | next_q | next_q_tm). */
+DQN_API int dqn_lb_debug_read(dqn_lb_handle* h, int32_t what, void* host_out, uint64_t nbytes);
+DQN_API int dqn_lb_synchronize(dqn_lb_handle* h);
+
 #ifdef __cplusplus
 }
 #endif
