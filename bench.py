@@ -456,6 +456,81 @@ def run_population(args):
         dist.destroy_process_group()
 
 
+def run_dp(args):
+    """BASELINE configs[3]: large-batch data-parallel DDQN, global batch 65536, hidden 1024x1024, D=8, A=4.
+    Each rank: forward+backward on B/world rows -> ONE NCCL all-reduce of P+1 floats -> identical Adam.
+    `value` = global train steps/s (strong scaling: the global batch is fixed)."""
+    import ctypes as C
+    import torch
+    import dqn_b200
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    Bg, H, ring = args.batch, (args.hidden, args.hidden), 1_000_000
+    tr = dqn_b200.LargeBatchTrainer(D, A, H, Bg, ring, GAMMA, dqn_b200.adamw(LR), rank=rank, world_size=world, seed=3,
+                                    device=local, gemm_mode=args.gemm)
+    params = dqn_b200.Model(A, hidden=H).init(np.random.default_rng(0), np.zeros((1, D), np.float32)) if False else None
+    rng = np.random.default_rng(0)
+    tree = {}
+    for name, (fi, fo) in zip(dqn_b200.pkg.specs.MODULES, dqn_b200.pkg.specs.layer_shapes(D, A, H)):
+        tree[name] = {"w": (rng.standard_normal((fi, fo)) / np.sqrt(fi)).clip(-2 / np.sqrt(fi), 2 / np.sqrt(fi)).astype(np.float32),
+                      "b": np.zeros(fo, np.float32)}
+    tr.set_params(tree, 0)
+    tr.set_params(tree, 1)
+    g = torch.Generator(device=device)
+    g.manual_seed(1234)                                  # every rank holds the same ring replica
+    s = torch.randn(ring, D, generator=g, device=device); s2 = torch.randn(ring, D, generator=g, device=device)
+    r = 2.0 * torch.randn(ring, generator=g, device=device)
+    a = torch.randint(0, A, (ring,), generator=g, device=device, dtype=torch.int64)
+    d = (torch.rand(ring, generator=g, device=device) < 0.01).to(torch.uint8)
+    tr.store_device(s, a, r, s2, d)
+    del s, s2, r, a, d
+    for _ in range(max(args.warmup, 3)):
+        tr.step()
+    flush_l2(torch, device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            tr.step()
+        e1.record()
+        torch.cuda.synchronize(device)
+    secs = e0.elapsed_time(e1) * 1e-3
+    t = torch.tensor([secs], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs_max = float(t.item())
+    loss = tr.loss()
+    if rank == 0:
+        flop_per_sample = 3 * 2 * (D * H[0] + H[0] * H[1] + H[1] * (1 + A)) + (2 * (D * H[0] + H[0] * H[1] + H[1] * (1 + A)) + 2 * (H[0] * H[1] + H[1] * (1 + A)))
+        tflops = Bg * flop_per_sample * args.steps / secs_max / 1e12
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        mode_factor = {"fp32": None, "tc3xtf32": 6.0}[args.gemm]      # tf32 = 1/2 of bf16, 3 MMAs per product
+        peak = pk["bf16_tflops_sustained"] * world
+        print(json.dumps({
+            "metric": "train_steps_per_sec", "value": args.steps / secs_max, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else "f32 via 3xTF32 tensor-core split", "data": "synthetic",
+            "config": {"workload": "configs[3]: large-batch data-parallel DDQN, global batch %d, hidden %dx%d" % (Bg, H[0], H[1]),
+                       "obs_dim": D, "num_actions": A, "batch_local": Bg // world, "gemm": args.gemm, "collective": "NCCL all-reduce of %d floats" % (tr.P + 1),
+                       "l2": "activations %.1f GB per rank >> L2" % (3 * 2 * (Bg // world) * H[0] * 4 / 1e9)},
+            "clocks": clk.summary(), "gpu_launches": None, "replay_samples_per_sec": Bg * args.steps / secs_max, "loss": loss,
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
+                         "note": "peak = measured sustained dense bf16 (MEASURED_PEAKS.json); fp32-exact modes run at 1/%s of it at best (%s)"
+                                 % ("n/a" if mode_factor is None else int(mode_factor), "FFMA pipe, 74 TF/GPU" if mode_factor is None else "tf32 = 1/2 bf16, x3 split"),
+                         "flop_per_step": Bg * flop_per_sample}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -464,7 +539,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid (ncu): only the fused timed region, no e2e / extras / cpu baseline; not a bench value")
-    ap.add_argument("--workload", default="single", choices=["single", "population"])
+    ap.add_argument("--workload", default="single", choices=["single", "population", "dp"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--hidden", type=int, default=1024)
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tc3xtf32"])
     ap.add_argument("--agents", type=int, default=1024)
     ap.add_argument("--steps-per-launch", type=int, default=16)
     args = ap.parse_args()
@@ -476,10 +554,13 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--workload", args.workload, "--agents", str(args.agents), "--steps-per-launch", str(args.steps_per_launch)]
+               "--workload", args.workload, "--agents", str(args.agents), "--steps-per-launch", str(args.steps_per_launch),
+               "--batch", str(args.batch), "--hidden", str(args.hidden), "--gemm", args.gemm]
         sys.exit(subprocess.call(cmd))
     if args.workload == "population":
         return run_population(args)
+    if args.workload == "dp":
+        return run_dp(args)
     run_single(args)
 
 

@@ -1,13 +1,306 @@
 // gemm_tc.cu -- tcgen05 (5th-gen tensor core) GEMMs for the large-batch path, 3xTF32 error-compensated.
+//
+//   C[M,N] = op(A) * op(B)   with  a = a_hi + a_lo (a_hi = tf32(a), a_lo = a - a_hi exactly), same for b:
+//   C += a_hi*b_lo + a_lo*b_hi + a_hi*b_hi   (three kind::tf32 MMAs per k-step, fp32 accumulation in TMEM)
+//
+// which restores ~2^-21 relative accuracy per product -- the fp32 parity bar -- at 1/3 of the TF32 rate.
+// One CTA computes a 128 x 128 tile with one tcgen05.mma (M=128, N=128, K=8) per 8 reduction elements:
+//   warps 0-3  producers: global fp32 -> registers -> {hi, lo} split -> shared memory in the UMMA
+//              canonical no-swizzle layout (K-major or MN-major core matrices), 3-stage mbarrier ring;
+//              the split IS the reason operands are staged by threads instead of TMA
+//   warps 4-7  epilogue: tcgen05.ld of the 128x128 fp32 accumulator (one TMEM lane per output row),
+//              fused bias+relu / relu'-mask / split-K partial store
+//   warp 8     TMEM allocation + single-thread MMA issue, tcgen05.commit onto the stage / accumulator barriers
+// Operand layouts follow the reference data as it lies in HBM, so no transposes are materialised:
+//   NN  h2 = h1 . W2        A K-major  (h1 [M][K]),   B MN-major (W2 [K][N])
+//   NT  dh1 = dh2 . W2^T    A K-major  (dh2 [M][K]),  B K-major  (W2 [N][K])
+//   TN  dW2 = h1^T . dh2    A MN-major (h1 [K][M]),   B MN-major (dh2 [K][N]), split-K over the batch
 #include "common.cuh"
 #include "kernels.h"
 #include "large.h"
 
 namespace dqn {
 
+namespace {
+
+constexpr int TM = 128, TN = 128, TK = 32;     // CTA tile; TK fp32 per pipeline stage (4 MMA k-steps of 8)
+constexpr int kStages = 3;
+constexpr int kTileK = TM * TK * 4;            // bytes of a K-major operand tile: 16 (8-row groups) x 8 (k core matrices) x 128 B
+// MN-major fp32/tf32 operands must use the SWIZZLE_128B_BASE32B canonical layout (the only MN-major layout the
+// tensor core accepts for 32-bit types): atoms of 4 k-rows x 128 B (32 MN elements), 32-byte chunks XOR-swizzled
+// by the k-row.  Tile = [8 k-atoms][4 mn-atoms][512 B].
+constexpr int kLboMN = 512;                    // stride between atoms along MN
+constexpr int kSboMN = 4 * kLboMN;             // stride between atoms along K (2048 B)
+constexpr int kTileMN = (TK / 4) * kSboMN;     // 16384 B
+constexpr int kNumThreads = 288;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, version 1 (Blackwell).  layout_type 0 = no swizzle, 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+// instruction descriptor: D = F32, A = B = TF32, M = 128, N = 128, majorness per operand
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(TN >> 3) << 17) |
+         ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+  uint32_t h0, h1, h2, h3;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(x.x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(x.y));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h2) : "f"(x.z));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h3) : "f"(x.w));
+  hi = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+  lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+}
+
+// Fill one operand tile (hi and lo copies) for the reduction range [k0, k0 + TK).
+//   KMAJOR:  G[mn][k] row-major (ld); smem byte (mn, k) = (mn/8)*1024 + (k/4)*128 + (mn%8)*16 + (k%4)*4
+//   MNMAJOR: G[k][mn] row-major (ld); smem byte (k, mn) = (k/4)*2048 + (mn/32)*512 + (k%4)*128 + swz32((mn%32)*4, k%4)
+template <bool MNMAJOR>
+__device__ __forceinline__ void fill_tile(const float* __restrict__ G, int ld, int mn0, int k0, uint8_t* s_hi, uint8_t* s_lo, int p) {
+  if (!MNMAJOR) {
+    const int mn = p;                                  // 128 producer threads: one operand row each
+    const float* src = G + (size_t)(mn0 + mn) * ld + k0;
+    const int base = (mn >> 3) * 1024 + (mn & 7) * 16;
+    float4 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(src + 4 * q);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 hi, lo;
+      split_tf32(v[q], hi, lo);
+      *reinterpret_cast<float4*>(s_hi + base + q * 128) = hi;
+      *reinterpret_cast<float4*>(s_lo + base + q * 128) = lo;
+    }
+  } else {
+    const int mq = p & 31, kb = p >> 5;                // a warp reads one full 512-byte row segment per k
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(G + (size_t)(k0 + kb + 4 * i) * ld + mn0 + 4 * mq);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kb + 4 * i, u = mq & 7;           // u = 16-byte unit inside the 128-byte row of atom (mq >> 3)
+      const int off = (k >> 2) * kSboMN + (mq >> 3) * kLboMN + (k & 3) * 128 + ((((u >> 1) ^ (k & 3)) << 5) | ((u & 1) << 4));
+      float4 hi, lo;
+      split_tf32(v[i], hi, lo);
+      *reinterpret_cast<float4*>(s_hi + off) = hi;
+      *reinterpret_cast<float4*>(s_lo + off) = lo;
+    }
+  }
+}
+
+// tcgen05.ld of 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+      "%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// The tensor core accumulates in fp32 with truncation, so the error of a long reduction grows linearly
+// with K (measured: ~5e-9 * K * |C|).  The accumulator is therefore promoted every kChunkK reduction
+// elements: two TMEM accumulators (2 x 128 columns) alternate; while the MMAs of chunk c+1 run, the
+// epilogue warps pull chunk c out of TMEM and add it to fp32 registers with round-to-nearest.
+constexpr int kChunkK = 128;
+constexpr int kStagesPerChunk = kChunkK / TK;
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+               const float* __restrict__ aux, int ldaux, int k_per_split) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kATile = A_MN ? kTileMN : kTileK, kBTile = B_MN ? kTileMN : kTileK;
+  constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
+  uint8_t* const tiles = smem;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);   // full[3], empty[3], tfull[2], tempty[2]
+  uint64_t* const full = bars, *const empty = bars + kStages, *const tfull = bars + 2 * kStages, *const tempty = bars + 2 * kStages + 2;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int nk = k_per_split / TK;
+  const int nchunks = nk / kStagesPerChunk;
+  if (EPI == kEpiSplitK) C += (size_t)blockIdx.z * M * ldc;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), 128);              // every producer thread arrives
+      mbar_init(smem_u32(&empty[s]), 1);               // one tcgen05.commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull[b]), 1);               // accumulator chunk complete (tcgen05.commit)
+      mbar_init(smem_u32(&tempty[b]), 128);            // every epilogue thread has read it
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {                                     // TMEM: 2 accumulators x 128 fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % kStages;
+      if (kt >= kStages) mbar_wait(smem_u32(&empty[s]), ((kt / kStages) - 1) & 1);   // slot drained by the MMAs
+      uint8_t* st = tiles + s * kStageBytes;
+      const int k0 = kbeg + kt * TK;
+      fill_tile<A_MN>(A, lda, m0, k0, st, st + kATile, tid);
+      fill_tile<B_MN>(B, ldb, n0, k0, st + 2 * kATile, st + 2 * kATile + kBTile, tid);
+      fence_async_smem();                              // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&full[s]));
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+      for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % kStages;
+        const int chunk = kt / kStagesPerChunk, b = chunk & 1;
+        const bool chunk_start = (kt % kStagesPerChunk) == 0;
+        if (chunk_start && chunk >= 2) {               // the epilogue must have drained this accumulator
+          mbar_wait(smem_u32(&tempty[b]), ((chunk >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(&full[s]), (kt / kStages) & 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_d + (uint32_t)(b * TN);
+        const uint32_t a_hi = smem_u32(tiles + s * kStageBytes), a_lo = a_hi + kATile;
+        const uint32_t b_hi = a_hi + 2 * kATile, b_lo = b_hi + kBTile;
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          // K-major (no swizzle): 2 core matrices (256 B) per k-step, LBO = 128 (next k core matrix), SBO = 1024 (next 8 rows)
+          // MN-major (128B_BASE32B): 2 k-atoms (4096 B) per k-step, LBO = 512 (next mn atom), SBO = 2048 (next k atom)
+          const uint32_t aoff = A_MN ? ks * 2 * kSboMN : ks * 256, boff = B_MN ? ks * 2 * kSboMN : ks * 256;
+          const uint64_t dah = A_MN ? make_desc(a_hi + aoff, kLboMN, kSboMN, 1) : make_desc(a_hi + aoff, 128, 1024, 0);
+          const uint64_t dal = A_MN ? make_desc(a_lo + aoff, kLboMN, kSboMN, 1) : make_desc(a_lo + aoff, 128, 1024, 0);
+          const uint64_t dbh = B_MN ? make_desc(b_hi + boff, kLboMN, kSboMN, 1) : make_desc(b_hi + boff, 128, 1024, 0);
+          const uint64_t dbl = B_MN ? make_desc(b_lo + boff, kLboMN, kSboMN, 1) : make_desc(b_lo + boff, 128, 1024, 0);
+          umma_tf32(acc, dah, dbl, idesc, (chunk_start && ks == 0) ? 0u : 1u);      // small cross terms first
+          umma_tf32(acc, dal, dbh, idesc, 1u);
+          umma_tf32(acc, dah, dbh, idesc, 1u);
+        }
+        umma_commit(smem_u32(&empty[s]));                               // frees the smem slot when these MMAs retire
+        if ((kt % kStagesPerChunk) == kStagesPerChunk - 1) umma_commit(smem_u32(&tfull[b]));   // chunk accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 4..7 own TMEM lanes 32*(warp-4) .. +31) =====================
+    const int q = warp - 4;
+    const int m = m0 + 32 * q + lane;
+    float acc[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int b = chunk & 1;
+      mbar_wait(smem_u32(&tfull[b]), (chunk >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * TN);
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);      // fp32 round-to-nearest promotion
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty[b]));
+    }
+    float* crow = C + (size_t)m * ldc + n0;
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      if (EPI == kEpiBiasRelu) {
+        const float4 bb = *reinterpret_cast<const float4*>(aux + n0 + j);
+        v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f); v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
+      } else if (EPI == kEpiReluMask) {
+        const float4 h = *reinterpret_cast<const float4*>(aux + (size_t)m * ldaux + n0 + j);
+        v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(crow + j) = v;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
+  }
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+cudaError_t launch_tc(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                      const float* aux, int ldaux, int splitk) {
+  constexpr int kATile = A_MN ? kTileMN : kTileK, kBTile = B_MN ? kTileMN : kTileK;
+  constexpr int smem = kStages * (2 * kATile + 2 * kBTile) + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(N / TN, M / TM, splitk);
+  gemm_tc_kernel<A_MN, B_MN, EPI><<<grid, kNumThreads, smem, st>>>(M, N, A, lda, B, ldb, C, ldc, aux, ldaux, K / splitk);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
 cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                        float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws) {
-  return cudaErrorNotSupported;   // filled in below once validated against the FFMA path
+  (void)ws;
+  if (M % TM || N % TN || (K / splitk) % kChunkK) return cudaErrorInvalidValue;
+  switch (kind) {
+    case kGemmNN_BiasRelu: return launch_tc<false, true, kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
+    case kGemmNT_ReluMask: return launch_tc<false, false, kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
+    case kGemmTN_SplitK: return launch_tc<true, true, kEpiSplitK>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, splitk);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace dqn

@@ -77,6 +77,11 @@ class LargeBatchTrainer:
         _lib.check(self.lib.dqn_lb_get_params(self.h, which, _lib.ptr(out), out.size))
         return unflatten_tree(out, self.obs_dim, self.num_actions, self.hidden)
 
+    def set_opt_state(self, count, mu_tree, nu_tree):
+        mu = flatten_tree(mu_tree, self.obs_dim, self.num_actions, self.hidden)
+        nu = flatten_tree(nu_tree, self.obs_dim, self.num_actions, self.hidden)
+        _lib.check(self.lib.dqn_lb_set_opt_state(self.h, int(count), _lib.ptr(mu), _lib.ptr(nu), mu.size))
+
     def get_opt_state(self):
         mu, nu, cnt = np.empty(self.P, np.float32), np.empty(self.P, np.float32), C.c_int32(0)
         _lib.check(self.lib.dqn_lb_get_opt_state(self.h, C.byref(cnt), _lib.ptr(mu), _lib.ptr(nu), self.P))
