@@ -11,6 +11,10 @@
 //   warps 4-7  epilogue: tcgen05.ld of the 128x128 fp32 accumulator (one TMEM lane per output row),
 //              fused bias+relu / relu'-mask / split-K partial store
 //   warp 8     TMEM allocation + single-thread MMA issue, tcgen05.commit onto the stage / accumulator barriers
+// K-major A operands never touch shared memory: each producer thread owns one row of the A tile and writes its
+// hi / lo values straight into TMEM (tcgen05.st, lane = row), and the MMA takes A from TMEM (.ts form).  A 128x128x8
+// tf32 MMA with both operands in shared memory reads 8 KB per 64 cycles = the whole 128 B/clk shared-memory
+// bandwidth of the SM (ncu: l1tex 76 %, tensor pipe 17 %); with A in TMEM only B streams through shared memory.
 // Operand layouts follow the reference data as it lies in HBM, so no transposes are materialised:
 //   NN  h2 = h1 . W2        A K-major  (h1 [M][K]),   B MN-major (W2 [K][N])
 //   NT  dh1 = dh2 . W2^T    A K-major  (dh2 [M][K]),  B K-major  (W2 [N][K])
@@ -24,7 +28,6 @@ namespace dqn {
 namespace {
 
 constexpr int TM = 128, TN = 128, TK = 32;     // CTA tile; TK fp32 per pipeline stage (4 MMA k-steps of 8)
-constexpr int kStages = 3;
 constexpr int kTileK = TM * TK * 4;            // bytes of a K-major operand tile: 16 (8-row groups) x 8 (k core matrices) x 128 B
 // MN-major fp32/tf32 operands must use the SWIZZLE_128B_BASE32B canonical layout (the only MN-major layout the
 // tensor core accepts for 32-bit types): atoms of 4 k-rows x 128 B (32 MN elements), 32-byte chunks XOR-swizzled
@@ -72,6 +75,31 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand in tensor memory (.ts form): D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,"
+      "%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -89,15 +117,29 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
 // Fill one operand tile (hi and lo copies) for the reduction range [k0, k0 + TK).
 //   KMAJOR:  G[mn][k] row-major (ld); smem byte (mn, k) = (mn/8)*1024 + (k/4)*128 + (mn%8)*16 + (k%4)*4
 //   MNMAJOR: G[k][mn] row-major (ld); smem byte (k, mn) = (k/4)*2048 + (mn/32)*512 + (k%4)*128 + swz32((mn%32)*4, k%4)
+// Operand staging is split into a load half (global -> registers) and a store half (registers -> {hi, lo} ->
+// TMEM / shared memory) so that the loads of stage kt+1 are in flight while the producer waits for its slot.
+//   K-major:  G[mn][k] row-major (ld); thread p owns row mn0 + p (32 consecutive k values = 8 float4)
+//             smem byte (mn, k) = (mn/8)*1024 + (k/4)*128 + (mn%8)*16 + (k%4)*4;  TMEM: lane = row, column = k
+//   MN-major: G[k][mn] row-major (ld); a warp reads one full 512-byte row segment per k (kb + 4 i)
+//             smem byte (k, mn) = (k/4)*2048 + (mn/32)*512 + (k%4)*128 + swz32((mn%32)*4, k%4)
 template <bool MNMAJOR>
-__device__ __forceinline__ void fill_tile(const float* __restrict__ G, int ld, int mn0, int k0, uint8_t* s_hi, uint8_t* s_lo, int p) {
+__device__ __forceinline__ void ld_tile(const float* __restrict__ G, int ld, int mn0, int k0, int p, float4 (&v)[8]) {
   if (!MNMAJOR) {
-    const int mn = p;                                  // 128 producer threads: one operand row each
-    const float* src = G + (size_t)(mn0 + mn) * ld + k0;
-    const int base = (mn >> 3) * 1024 + (mn & 7) * 16;
-    float4 v[8];
+    const float* src = G + (size_t)(mn0 + p) * ld + k0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(src + 4 * q);
+  } else {
+    const int mq = p & 31, kb = p >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(G + (size_t)(k0 + kb + 4 * i) * ld + mn0 + 4 * mq);
+  }
+}
+
+template <bool MNMAJOR>
+__device__ __forceinline__ void st_tile(const float4 (&v)[8], uint8_t* s_hi, uint8_t* s_lo, int p) {
+  if (!MNMAJOR) {
+    const int base = (p >> 3) * 1024 + (p & 7) * 16;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float4 hi, lo;
@@ -106,10 +148,7 @@ __device__ __forceinline__ void fill_tile(const float* __restrict__ G, int ld, i
       *reinterpret_cast<float4*>(s_lo + base + q * 128) = lo;
     }
   } else {
-    const int mq = p & 31, kb = p >> 5;                // a warp reads one full 512-byte row segment per k
-    float4 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(G + (size_t)(k0 + kb + 4 * i) * ld + mn0 + 4 * mq);
+    const int mq = p & 31, kb = p >> 5;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int k = kb + 4 * i, u = mq & 7;           // u = 16-byte unit inside the 128-byte row of atom (mq >> 3)
@@ -120,6 +159,25 @@ __device__ __forceinline__ void fill_tile(const float* __restrict__ G, int ld, i
       *reinterpret_cast<float4*>(s_lo + off) = lo;
     }
   }
+}
+
+// K-major A rows straight into tensor memory, 16 columns at a time to keep the register peak low
+__device__ __forceinline__ void st_a_tmem(const float4 (&v)[8], uint32_t t_hi, uint32_t t_lo, int p) {
+  const uint32_t lane_base = (uint32_t)(p & ~31) << 16;     // warp w writes lanes 32w .. 32w+31
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t rh[16], rl[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 h, l;
+      split_tf32(v[4 * half + q], h, l);
+      rh[4 * q] = __float_as_uint(h.x); rh[4 * q + 1] = __float_as_uint(h.y); rh[4 * q + 2] = __float_as_uint(h.z); rh[4 * q + 3] = __float_as_uint(h.w);
+      rl[4 * q] = __float_as_uint(l.x); rl[4 * q + 1] = __float_as_uint(l.y); rl[4 * q + 2] = __float_as_uint(l.z); rl[4 * q + 3] = __float_as_uint(l.w);
+    }
+    tmem_st16(t_hi + lane_base + 16u * half, rh);
+    tmem_st16(t_lo + lane_base + 16u * half, rl);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // tcgen05.ld of 32 consecutive fp32 columns of this thread's TMEM lane
@@ -147,10 +205,13 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                const float* __restrict__ aux, int ldaux, int k_per_split) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int kATile = A_MN ? kTileMN : kTileK, kBTile = B_MN ? kTileMN : kTileK;
+  constexpr bool A_TMEM = !A_MN;                       // K-major A lives in tensor memory, not shared memory
+  constexpr int kStages = A_TMEM ? 4 : 3;
+  constexpr int kATile = A_TMEM ? 0 : kTileMN, kBTile = B_MN ? kTileMN : kTileK;
   constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
+  constexpr uint32_t kTmemCols = A_TMEM ? 512u : 256u; // 2 accumulators x 128 (+ 4 stages x (32 hi + 32 lo) columns of A)
   uint8_t* const tiles = smem;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);   // full[3], empty[3], tfull[2], tempty[2]
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);   // full[S], empty[S], tfull[2], tempty[2]
   uint64_t* const full = bars, *const empty = bars + kStages, *const tfull = bars + 2 * kStages, *const tempty = bars + 2 * kStages + 2;
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
@@ -172,8 +233,8 @@ gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {                                     // TMEM: 2 accumulators x 128 fp32 columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+  if (warp == 8) {                                     // TMEM: 2 accumulators x 128 fp32 columns x 128 lanes (+ the A stages)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -183,15 +244,30 @@ gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* 
 
   if (warp < 4) {
     // ===================== producers =====================
-    for (int kt = 0; kt < nk; ++kt) {
+    // Two register sets alternate: the global loads of stage kt+2 are issued as soon as stage kt has been staged,
+    // so load latency (~1 us under load) overlaps the split / store work and the slot waits of the other set.
+    float4 va0[8], vb0[8], va1[8], vb1[8];
+    auto stage_out = [&](int kt, const float4 (&va)[8], const float4 (&vb)[8]) {
       const int s = kt % kStages;
       if (kt >= kStages) mbar_wait(smem_u32(&empty[s]), ((kt / kStages) - 1) & 1);   // slot drained by the MMAs
       uint8_t* st = tiles + s * kStageBytes;
-      const int k0 = kbeg + kt * TK;
-      fill_tile<A_MN>(A, lda, m0, k0, st, st + kATile, tid);
-      fill_tile<B_MN>(B, ldb, n0, k0, st + 2 * kATile, st + 2 * kATile + kBTile, tid);
+      if constexpr (A_TMEM) st_a_tmem(va, tmem_d + 256u + (uint32_t)(s * 64), tmem_d + 256u + (uint32_t)(s * 64 + 32), tid);
+      else st_tile<true>(va, st, st + kATile, tid);
+      st_tile<B_MN>(vb, st + 2 * kATile, st + 2 * kATile + kBTile, tid);
       fence_async_smem();                              // generic-proxy stores -> visible to the tensor core (async proxy)
+      tc_fence_before();                               // orders the tcgen05.st of A before the barrier hand-off
       mbar_arrive(smem_u32(&full[s]));
+    };
+    ld_tile<A_MN>(A, lda, m0, kbeg, tid, va0);
+    ld_tile<B_MN>(B, ldb, n0, kbeg, tid, vb0);
+    if (nk > 1) { ld_tile<A_MN>(A, lda, m0, kbeg + TK, tid, va1); ld_tile<B_MN>(B, ldb, n0, kbeg + TK, tid, vb1); }
+    for (int kt = 0; kt < nk; kt += 2) {
+      stage_out(kt, va0, vb0);
+      if (kt + 2 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 2) * TK, tid, va0); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 2) * TK, tid, vb0); }
+      if (kt + 1 < nk) {
+        stage_out(kt + 1, va1, vb1);
+        if (kt + 3 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 3) * TK, tid, va1); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 3) * TK, tid, vb1); }
+      }
     }
   } else if (warp == 8) {
     // ===================== MMA issuer (one thread) =====================
@@ -210,18 +286,26 @@ gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* 
         const uint32_t acc = tmem_d + (uint32_t)(b * TN);
         const uint32_t a_hi = smem_u32(tiles + s * kStageBytes), a_lo = a_hi + kATile;
         const uint32_t b_hi = a_hi + 2 * kATile, b_lo = b_hi + kBTile;
+        const uint32_t ta_hi = tmem_d + 256u + (uint32_t)(s * 64), ta_lo = ta_hi + 32u;
 #pragma unroll
         for (int ks = 0; ks < TK / 8; ++ks) {
-          // K-major (no swizzle): 2 core matrices (256 B) per k-step, LBO = 128 (next k core matrix), SBO = 1024 (next 8 rows)
+          // K-major B (no swizzle): 2 core matrices (256 B) per k-step, LBO = 128 (next k core matrix), SBO = 1024 (next 8 rows)
           // MN-major (128B_BASE32B): 2 k-atoms (4096 B) per k-step, LBO = 512 (next mn atom), SBO = 2048 (next k atom)
-          const uint32_t aoff = A_MN ? ks * 2 * kSboMN : ks * 256, boff = B_MN ? ks * 2 * kSboMN : ks * 256;
-          const uint64_t dah = A_MN ? make_desc(a_hi + aoff, kLboMN, kSboMN, 1) : make_desc(a_hi + aoff, 128, 1024, 0);
-          const uint64_t dal = A_MN ? make_desc(a_lo + aoff, kLboMN, kSboMN, 1) : make_desc(a_lo + aoff, 128, 1024, 0);
+          const uint32_t boff = B_MN ? ks * 2 * kSboMN : ks * 256;
           const uint64_t dbh = B_MN ? make_desc(b_hi + boff, kLboMN, kSboMN, 1) : make_desc(b_hi + boff, 128, 1024, 0);
           const uint64_t dbl = B_MN ? make_desc(b_lo + boff, kLboMN, kSboMN, 1) : make_desc(b_lo + boff, 128, 1024, 0);
-          umma_tf32(acc, dah, dbl, idesc, (chunk_start && ks == 0) ? 0u : 1u);      // small cross terms first
-          umma_tf32(acc, dal, dbh, idesc, 1u);
-          umma_tf32(acc, dah, dbh, idesc, 1u);
+          const uint32_t first = (chunk_start && ks == 0) ? 0u : 1u;
+          if constexpr (A_TMEM) {                      // A from tensor memory: 8 columns per k-step
+            umma_tf32_ts(acc, ta_hi + 8u * ks, dbl, idesc, first);                  // small cross terms first
+            umma_tf32_ts(acc, ta_lo + 8u * ks, dbh, idesc, 1u);
+            umma_tf32_ts(acc, ta_hi + 8u * ks, dbh, idesc, 1u);
+          } else {
+            const uint32_t aoff = ks * 2 * kSboMN;
+            const uint64_t dah = make_desc(a_hi + aoff, kLboMN, kSboMN, 1), dal = make_desc(a_lo + aoff, kLboMN, kSboMN, 1);
+            umma_tf32(acc, dah, dbl, idesc, first);
+            umma_tf32(acc, dal, dbh, idesc, 1u);
+            umma_tf32(acc, dah, dbh, idesc, 1u);
+          }
         }
         umma_commit(smem_u32(&empty[s]));                               // frees the smem slot when these MMAs retire
         if ((kt % kStagesPerChunk) == kStagesPerChunk - 1) umma_commit(smem_u32(&tfull[b]));   // chunk accumulator complete
@@ -269,15 +353,15 @@ gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* 
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
   }
 }
 
 template <bool A_MN, bool B_MN, int EPI>
 cudaError_t launch_tc(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                       const float* aux, int ldaux, int splitk) {
-  constexpr int kATile = A_MN ? kTileMN : kTileK, kBTile = B_MN ? kTileMN : kTileK;
-  constexpr int smem = kStages * (2 * kATile + 2 * kBTile) + 128;
+  constexpr int kATile = A_MN ? kTileMN : 0, kBTile = B_MN ? kTileMN : kTileK;
+  constexpr int smem = (A_MN ? 3 : 4) * (2 * kATile + 2 * kBTile) + 128;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
