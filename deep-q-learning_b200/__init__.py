@@ -22,9 +22,10 @@ from .agent import Agent
 from .hyperparams import ParamAgent, optimize, generate_util_func, SWEEP_BOUNDS, sample_sweep_point
 from .population import Population, shard_range, sweep_hparams
 from .large_batch import LargeBatchTrainer
+from .per import PrioritizedSampler
 from .checkpoint import generate_saving, generate_loading, load_pickle
 
 __all__ = ["Agent", "ParamAgent", "ReplayBuffer", "sample_batch", "Model", "Optimizer", "adam", "adamw",
-           "DqnEngine", "DqnError", "Population", "LargeBatchTrainer", "shard_range", "sweep_hparams", "optimize",
+           "DqnEngine", "DqnError", "Population", "LargeBatchTrainer", "PrioritizedSampler", "shard_range", "sweep_hparams", "optimize",
            "generate_util_func", "generate_saving", "generate_loading", "load_pickle", "flatten_tree",
            "unflatten_tree", "param_count", "SWEEP_BOUNDS", "sample_sweep_point", "ScaleByAdamState", "EmptyState"]

@@ -107,6 +107,18 @@ PROTOTYPES = {
     "dqn_lb_get_loss": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "dqn_lb_debug_read": (C.c_int, [_H, _i32, _P, C.c_uint64]),
     "dqn_lb_synchronize": (C.c_int, [_H]),
+    # prioritized replay
+    "dqn_per_arena_bytes": (C.c_int, [_i64, C.POINTER(C.c_uint64)]),
+    "dqn_per_create": (C.c_int, [_i32, _i64, C.c_float, C.c_float, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(_H)]),
+    "dqn_per_destroy": (C.c_int, [_H]),
+    "dqn_per_update": (C.c_int, [_H, _P, _P, _i32, _i32]),
+    "dqn_per_update_host": (C.c_int, [_H, _P, _P, _i32, _i32]),
+    "dqn_per_fill": (C.c_int, [_H, _P, _i64]),
+    "dqn_per_sample": (C.c_int, [_H, _i64, _i32, _P, _P]),
+    "dqn_per_sample_host": (C.c_int, [_H, _i64, _i32, _P, _P]),
+    "dqn_per_total": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "dqn_per_read_nodes": (C.c_int, [_H, _i64, _i64, _P]),
+    "dqn_per_leaf_base": (C.c_int, [_H, C.POINTER(_i64)]),
 }
 
 _lib = None

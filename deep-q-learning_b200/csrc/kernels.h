@@ -56,4 +56,11 @@ cudaError_t launch_act(cudaStream_t st, const float* params, const Dims& d, int 
                        float* q_out /* device [n_sel][A] or nullptr */);
 cudaError_t launch_sync_target(cudaStream_t st, float* params, const Dims& d, int agent_begin, int n_sel);
 
+// prioritized replay (per.cu)
+cudaError_t launch_per_update(cudaStream_t st, float* tree, long long L, int levels, const long long* idx, const float* val, int n,
+                              int is_td, float alpha, float eps);
+cudaError_t launch_per_rebuild(cudaStream_t st, float* tree, long long L);
+cudaError_t launch_per_sample(cudaStream_t st, const float* tree, long long L, int levels, int batch, uint64_t seed, long long step,
+                              long long* idx_out, float* prio_out);
+
 }  // namespace dqn

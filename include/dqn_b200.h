@@ -226,6 +226,31 @@ DQN_API int dqn_lb_get_loss(dqn_lb_handle* h, float* loss_out);
 DQN_API int dqn_lb_debug_read(dqn_lb_handle* h, int32_t what, void* host_out, uint64_t nbytes);
 DQN_API int dqn_lb_synchronize(dqn_lb_handle* h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Prioritized replay (BASELINE configs[4]): sum-tree proportional sampler + priority update.  The reference
+ * has no prioritized replay (its sampler is uniform, General/Base/replay_buffer.py:68-85), so this is a
+ * self-specified extension with its own oracle (oracle/per_oracle.py); indices it returns can be fed to
+ * dqn_train_step / dqn_sample_batch as explicit indices.  All array arguments are DEVICE pointers unless
+ * the name says host.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dqn_per_handle dqn_per_handle;
+DQN_API int dqn_per_arena_bytes(int64_t capacity, uint64_t* bytes_out);
+DQN_API int dqn_per_create(int32_t device, int64_t capacity, float alpha, float eps, uint64_t seed, void* stream,
+                           void* arena, uint64_t arena_bytes, dqn_per_handle** out);
+DQN_API int dqn_per_destroy(dqn_per_handle* h);
+/* leaves[idx[i]] = prio[i] (is_td = 0) or (|prio[i]| + eps)^alpha (is_td = 1); parents recomputed. */
+DQN_API int dqn_per_update(dqn_per_handle* h, const int64_t* idx_dev, const float* val_dev, int32_t n, int32_t is_td);
+DQN_API int dqn_per_update_host(dqn_per_handle* h, const int64_t* idx, const float* val, int32_t n, int32_t is_td);
+/* set leaves [0, n) from a device array and rebuild the whole tree (bulk initialisation). */
+DQN_API int dqn_per_fill(dqn_per_handle* h, const float* prio_dev, int64_t n);
+/* B stratified proportional samples for `step` -> indices (i64[B]) and their priorities (f32[B]). */
+DQN_API int dqn_per_sample(dqn_per_handle* h, int64_t step, int32_t batch, int64_t* idx_dev, float* prio_dev);
+DQN_API int dqn_per_sample_host(dqn_per_handle* h, int64_t step, int32_t batch, int64_t* idx, float* prio);
+DQN_API int dqn_per_total(dqn_per_handle* h, float* total_out);
+/* debug: copy tree nodes [first, first + n) to host (node 1 = root, leaves start at dqn_per_leaf_base). */
+DQN_API int dqn_per_read_nodes(dqn_per_handle* h, int64_t first, int64_t n, float* host_out);
+DQN_API int dqn_per_leaf_base(dqn_per_handle* h, int64_t* leaf_base_out);
+
 #ifdef __cplusplus
 }
 #endif
