@@ -179,6 +179,7 @@ def workload_config():
     return {"workload": "configs[1]: single-agent fused dueling double-DQN train step, 1M-transition synthetic replay, batch 64",
             "obs_dim": D, "num_actions": A, "hidden": [32, 64], "batch": B, "ring_slots": N_RING, "gamma": GAMMA,
             "optimizer": "adamw(2e-4, wd 1e-4)", "steps_per_launch": STEPS_PER_LAUNCH,
+            "step_kernel": os.environ.get("DQN_B200_STEP_KERNEL", "auto"),
             "multi_gpu": "replicas only (single agent does not shard)",
             "l2": "ring 96 MB < 126 MB L2: L2 flushed (512 MB write) before each timed region; every step gathers 64 random, mostly first-touch records"}
 
@@ -311,13 +312,16 @@ def run_single(args):
     sm_hz = (clocks["sm_mhz"] or 1965) * 1e6
     fp32_one_sm = 128 * 2 * sm_hz / 1e9
     flops = B * FLOP_PER_SAMPLE / (secs / args.steps) / 1e9
+    cluster = args.step_kernel in ("auto", "cluster")
+    n_sm = 4 if cluster else 1
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "dqn_train_fused_kernel<4>", "peak_source": peak_src,
+                "traffic": None, "kernel": "dqn_train_cluster_kernel<4>" if cluster else "dqn_train_fused_kernel<4>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": launch_s * 1e3,
-                "note": "latency-bound by construction: one agent = one CTA on one SM; theta/theta^-/grads stay in shared memory, "
-                        "so the only HBM traffic is 64 gathered records per step (prefetched one step ahead)",
-                "fp32": {"achieved_gflops": flops, "one_sm_ffma_peak_gflops": fp32_one_sm, "frac_of_one_sm": flops / fp32_one_sm,
-                         "flop_per_step": B * FLOP_PER_SAMPLE}}
+                "note": "latency-bound by construction: one agent's steps are a serial chain (step t+1 needs theta_t) on %s; "
+                        "theta/theta^-/grads stay in shared memory, so the only HBM traffic is 64 gathered records per step "
+                        "(prefetched one step ahead)" % ("a 4-CTA cluster (4 of 148 SMs)" if cluster else "one CTA (1 of 148 SMs)"),
+                "fp32": {"achieved_gflops": flops, "sms_used": n_sm, "ffma_peak_gflops_of_sms_used": n_sm * fp32_one_sm,
+                         "frac_of_sms_used": flops / (n_sm * fp32_one_sm), "flop_per_step": B * FLOP_PER_SAMPLE}}
 
     # ---- K=1 launches (launch-bound variant) and replay-gather throughput, for the record -----------
     extras = {}
@@ -590,7 +594,11 @@ def main():
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tc3xtf32"])
     ap.add_argument("--agents", type=int, default=1024)
     ap.add_argument("--steps-per-launch", type=int, default=16)
+    ap.add_argument("--step-kernel", default="auto", choices=["auto", "cta", "cluster"],
+                    help="train-step kernel of the single/population workloads: one CTA per agent, or one agent over a 4-CTA cluster "
+                         "(auto = cluster while 4 * agents <= SMs)")
     args = ap.parse_args()
+    os.environ["DQN_B200_STEP_KERNEL"] = args.step_kernel
     if args.impl == "reference":
         return run_reference(args)
     _, world, _ = dist_env()
@@ -600,7 +608,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
                "--workload", args.workload, "--agents", str(args.agents), "--steps-per-launch", str(args.steps_per_launch),
-               "--batch", str(args.batch), "--hidden", str(args.hidden), "--gemm", args.gemm]
+               "--batch", str(args.batch), "--hidden", str(args.hidden), "--gemm", args.gemm, "--step-kernel", args.step_kernel]
         sys.exit(subprocess.call(cmd))
     if args.workload == "population":
         return run_population(args)

@@ -13,6 +13,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dqn_b200.h")
 
 DQN_OPT_ADAM, DQN_OPT_ADAMW = 0, 1
 DQN_PARAMS_ONLINE, DQN_PARAMS_TARGET = 0, 1
+DQN_STEP_AUTO, DQN_STEP_CTA, DQN_STEP_CLUSTER = 0, 1, 2
+STEP_KERNELS = {"auto": DQN_STEP_AUTO, "cta": DQN_STEP_CTA, "cluster": DQN_STEP_CLUSTER}
 DQN_MAX_BATCH, DQN_MAX_OBS_DIM, DQN_MAX_ACTIONS = 1024, 16, 7
 LOSS_RING = 4096
 
@@ -31,7 +33,7 @@ class DqnConfig(C.Structure):
         ("gamma", C.c_float), ("opt_kind", C.c_int32),
         ("lr", C.c_float), ("b1", C.c_float), ("b2", C.c_float), ("eps", C.c_float),
         ("eps_root", C.c_float), ("weight_decay", C.c_float),
-        ("seed", C.c_uint64), ("agent_id_base", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p), ("arena", C.c_void_p), ("arena_bytes", C.c_uint64),
+        ("seed", C.c_uint64), ("agent_id_base", C.c_int32), ("step_kernel", C.c_int32), ("stream", C.c_void_p), ("arena", C.c_void_p), ("arena_bytes", C.c_uint64),
     ]
 
 
@@ -75,6 +77,7 @@ PROTOTYPES = {
     "dqn_get_opt_state": (C.c_int, [_H, _i32, C.POINTER(_i32), _P, _P, _i32]),
     "dqn_set_hparams": (C.c_int, [_H, _i32, C.POINTER(DqnHparams)]),
     "dqn_get_hparams": (C.c_int, [_H, _i32, C.POINTER(DqnHparams)]),
+    "dqn_set_step_kernel": (C.c_int, [_H, _i32]),
     "dqn_store": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P]),
     "dqn_store_device": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P]),
     "dqn_buffer_state": (C.c_int, [_H, _i32, C.POINTER(_i64), C.POINTER(_i64)]),

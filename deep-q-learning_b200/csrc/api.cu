@@ -106,6 +106,7 @@ int validate(const dqn_config* cfg, Dims* d) {
 
 struct dqn_handle {
   dqn_config cfg;
+  int step_kernel, sm_count;
   Dims dims;
   cudaStream_t stream;
   uint8_t* arena;
@@ -230,6 +231,13 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   // zero parameters / moments / rings / losses (ReplayBuffer.__init__ zero-fills, replay_buffer.py:26-30)
   e = cudaMemsetAsync(h->arena, 0, h->cv.stage, h->stream);
   if (e == cudaSuccess) e = train_fused_prepare(d);
+  if (e == cudaSuccess) e = train_cluster_prepare(d);
+  h->step_kernel = cfg->step_kernel;
+  {
+    int sms = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    h->sm_count = sms;
+  }
   AgentCtl c;
   memset(&c, 0, sizeof c);
   c.gamma = cfg->gamma; c.lr = cfg->lr; c.b1 = cfg->b1; c.b2 = cfg->b2; c.eps = cfg->eps;
@@ -353,6 +361,13 @@ DQN_API int dqn_get_hparams(dqn_handle* h, int32_t agent, dqn_hparams* hp) {
   const AgentCtl& c = h->hctl[agent];
   hp->gamma = c.gamma; hp->batch_size = c.batch_size; hp->lr = c.lr; hp->b1 = c.b1; hp->b2 = c.b2;
   hp->eps = c.eps; hp->eps_root = c.eps_root; hp->weight_decay = c.wd;
+  return DQN_OK;
+}
+
+DQN_API int dqn_set_step_kernel(dqn_handle* h, int32_t step_kernel) {
+  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
+  if (step_kernel < DQN_STEP_AUTO || step_kernel > DQN_STEP_CLUSTER) return fail(DQN_E_INVALID, "dqn_set_step_kernel: unknown kernel id");
+  h->step_kernel = step_kernel;
   return DQN_OK;
 }
 
@@ -521,7 +536,11 @@ int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, d
     ta.taps.loss = (float*)(t + h->to.loss);
     ta.taps.grads = (float*)(t + h->to.grads);
   }
-  CU(launch_train_fused(h->stream, ta));
+  // one agent per CTA fills the chip once there are >= ~SMs agents; below that an agent's step is a serial
+  // latency chain on one SM, so the minibatch rows are spread over a 4-CTA cluster instead
+  const bool cluster = h->step_kernel == DQN_STEP_CLUSTER || (h->step_kernel == DQN_STEP_AUTO && 4 * n_sel <= h->sm_count);
+  if (cluster) CU(launch_train_cluster(h->stream, ta));
+  else CU(launch_train_fused(h->stream, ta));
   for (int ag = b; ag < e; ++ag) {
     AgentCtl& c = h->hctl[ag];
     c.train_steps += K;

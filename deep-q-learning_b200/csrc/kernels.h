@@ -50,6 +50,10 @@ cudaError_t launch_replay_gather(cudaStream_t st, const uint32_t* ring, const Di
 size_t train_fused_smem_bytes(const Dims& d);
 cudaError_t train_fused_prepare(const Dims& d);   // cudaFuncSetAttribute for the instantiation
 cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args);
+// the same step with one agent spread over a 4-CTA thread-block cluster (train_cluster.cu)
+size_t train_cluster_smem_bytes(const Dims& d);
+cudaError_t train_cluster_prepare(const Dims& d);
+cudaError_t launch_train_cluster(cudaStream_t st, const TrainArgs& args);
 
 cudaError_t launch_act(cudaStream_t st, const float* params, const Dims& d, int agent_begin, int n_sel,
                        const float* states /* device [n_sel][D] */, int* actions_out /* device [n_sel] */,

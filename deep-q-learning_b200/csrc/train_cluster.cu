@@ -1,0 +1,522 @@
+// train_cluster.cu -- the fused train step for ONE agent spread over a 4-CTA thread-block cluster.
+//
+// The single-CTA kernel (train_fused.cu) is latency-bound: one agent's step is a serial chain of small phases on one
+// SM.  Steps cannot overlap (step t+1 needs theta_t), so the only parallelism left is inside the minibatch: here the
+// 64 rows of each tile are split over the 4 CTAs of a cluster (16 rows each, data-parallel inside the cluster):
+//
+//   every CTA   gathers its 16 transitions (cp.async, one step ahead), runs the three forwards on its rows
+//               (48 "forward rows": (theta,s) | (theta,s') | (theta^-,s')), targets / Huber, and the whole backward,
+//               producing a FULL-SIZE partial gradient in its own shared memory;
+//   cluster     barrier -> reduce-scatter over distributed shared memory: CTA r sums slice r of the four partial
+//               gradients (fixed order 0..3: deterministic), applies Adam to its slice (mu / nu of the slice live in
+//               its registers) and stores the new weights into the shared-memory replica of ALL four CTAs
+//               -> barrier -> next step.
+// theta and theta^- stay replicated in every CTA's shared memory; HBM sees only the gathered records and the loss.
+// Same arithmetic and same Philox sampling as train_fused.cu; summation orders differ, results agree to fp32 round-off.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tile_ops.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace dqn {
+
+namespace {
+
+using namespace tile;
+
+constexpr int NT = 256;
+constexpr int CS = 4;             // CTAs per cluster
+constexpr int BT = 64;            // rows per tile (whole cluster)
+constexpr int R = BT / CS;        // 16 rows per CTA per tile
+constexpr int FR = 3 * R;         // 48 forward rows: [0,16) (theta,s) | [16,32) (theta,s') | [32,48) (theta^-,s')
+constexpr int XS = 2 * R + 4;     // 36: row stride of X [d][col], cols [0,16) = s, [16,32) = s'
+constexpr int HS = FR + 4;        // 52: row stride of H1 / H2 [unit][forward row]
+constexpr int RS = R + 4;         // 20: row stride of the k-major backward buffers
+constexpr int DRS = kH2 + 4;      // 68: row stride of Dh2R [row][unit]
+constexpr int HC = 8;
+constexpr int WS2 = kH2 + 4;      // 68
+constexpr int NPC = 4;            // slice parameters per thread: ceil(ceil(3308 / 4) / 256)
+
+struct CLay {
+  int pW2, pWh, PS, SL;
+  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oScr, oMeta, oDummy, oRed, oStage, total;
+};
+
+__host__ __device__ inline CLay make_clayout(int D, int recw) {
+  CLay L;
+  L.pW2 = (D + 1) * kH1;
+  L.pWh = L.pW2 + (kH1 + 1) * WS2;
+  L.PS = L.pWh + (kH2 + 1) * HC;
+  L.SL = (((L.PS + CS - 1) / CS) + 3) & ~3;
+  const int PSa = (L.PS + 3) & ~3;
+  int o = 0;
+  L.oW = o; o += PSa;
+  L.oWt = o; o += PSa;
+  L.oG = o; o += PSa;
+  L.oX = o; o += (D + 1) * XS;
+  L.oH1 = o; o += kH1 * HS;
+  L.oH2 = o; o += (kH2 + 1) * HS;
+  L.oDh2T = o; o += kH2 * RS;
+  L.oDh2R = o; o += R * DRS;
+  L.oDh1T = o; o += kH1 * RS;
+  L.oDhdT = o; o += HC * RS;
+  L.oScr = o; o += 4 * HC * FR;
+  L.oMeta = o; o += R * 4;
+  L.oDummy = o; o += 4;
+  L.oRed = o; o += 64;
+  L.oStage = o; o += R * recw;
+  L.total = o;
+  return L;
+}
+
+__device__ __forceinline__ int csmem_to_flat(int p, int D, int A, const CLay& L) {
+  if (p < L.pW2) return p;
+  const int offWv = L.pW2 + (kH1 + 1) * kH2;
+  if (p < L.pWh) {
+    const int q = p - L.pW2;
+    const int row = q / WS2, col = q - row * WS2;
+    return col < kH2 ? L.pW2 + row * kH2 + col : -1;
+  }
+  const int q = p - L.pWh;
+  const int k = q >> 3, c = q & 7;
+  const int offbv = offWv + kH2, offWa = offbv + 1, offba = offWa + kH2 * A;
+  if (c > A) return -1;
+  if (k < kH2) return c == 0 ? offWv + k : offWa + k * A + (c - 1);
+  return c == 0 ? offbv : offba + (c - 1);
+}
+
+template <int A>
+__global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArgs args) {
+  extern __shared__ __align__(16) float sm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int sel = blockIdx.x / CS;
+  const int agent = args.agent_begin + sel;
+  const int D = args.dims.D, recw = args.dims.recw, PF = args.dims.PF;
+  const CLay L = make_clayout(D, recw);
+
+  float* const W = sm + L.oW;
+  float* const Wt = sm + L.oWt;
+  float* const G = sm + L.oG;
+  float* const X = sm + L.oX;         // [D+1][36]
+  float* const H1 = sm + L.oH1;       // [32][52]
+  float* const H2 = sm + L.oH2;       // [65][52]   row 64 = ones
+  float* const Dh2T = sm + L.oDh2T;   // [64 j][20]
+  float* const Dh2R = sm + L.oDh2R;   // [16 r][68]
+  float* const Dh1T = sm + L.oDh1T;   // [32 k][20]
+  float* const DhdT = sm + L.oDhdT;   // [8 c][20]
+  float* const Scr = sm + L.oScr;     // [4 parts][8 c][48 forward rows]
+  float* const Meta = sm + L.oMeta;   // [16][4]
+  float* const Red = sm + L.oRed;     // [0..3] loss partial per rank (valid in rank 0), [8..11] Adam bias corrections, [16..31] head-bias partials
+  float* const Stage = sm + L.oStage;
+
+  float* const gW = args.params + (size_t)agent * 4 * PF;
+  float* const gWt = gW + PF;
+  float* const gM = gW + 2 * PF;
+  float* const gV = gW + 3 * PF;
+  AgentCtl* const ctl = args.ctl + agent;
+  const uint32_t* const ring = args.rings + (size_t)agent * args.dims.N * recw;
+
+  // ---- one-time: full theta / theta^- replicas into smem; mu / nu of this CTA's slice into registers ----
+  for (int p = t; p < L.PS; p += NT) {
+    const int f = csmem_to_flat(p, D, A, L);
+    W[p] = f >= 0 ? gW[f] : 0.f;
+    Wt[p] = f >= 0 ? gWt[f] : 0.f;
+    G[p] = 0.f;
+  }
+  float mreg[NPC], vreg[NPC];
+#pragma unroll
+  for (int i = 0; i < NPC; ++i) {
+    const int q = t + i * NT, p = rank * L.SL + q;
+    mreg[i] = 0.f; vreg[i] = 0.f;
+    if (q < L.SL && p < L.PS) {
+      const int f = csmem_to_flat(p, D, A, L);
+      if (f >= 0) { mreg[i] = gM[f]; vreg[i] = gV[f]; }
+    }
+  }
+  for (int r = t; r < XS; r += NT) X[D * XS + r] = 1.f;
+  for (int r = t; r < HS; r += NT) H2[kH2 * HS + r] = 1.f;
+
+  const float gamma = ctl->gamma, lr = ctl->lr, b1 = ctl->b1, b2 = ctl->b2;
+  const float eps = ctl->eps, eps_root = ctl->eps_root, wd = ctl->wd;
+  const int B = ctl->batch_size;
+  const long long step0 = ctl->train_steps;
+  const int count0 = ctl->adam_count;
+  const long long rc = ctl->ring_counter;
+  const long long size = rc < args.dims.N ? rc : args.dims.N;
+  const int ntiles = (B + BT - 1) / BT;
+  const float fB = (float)B;
+  const int cpr = recw >> 2;
+
+  // remote views of the replicated / partial buffers
+  float* Wr[CS];
+  const float* Gr[CS];
+#pragma unroll
+  for (int c = 0; c < CS; ++c) { Wr[c] = cluster.map_shared_rank(W, c); Gr[c] = cluster.map_shared_rank(G, c); }
+  float* const Red0 = cluster.map_shared_rank(Red, 0);
+
+  // staged-record word -> smem destination (threads 0..63: 4 lanes per row)
+  const int urow = t >> 2, ul4 = t & 3;
+  int udst[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const int wd = 4 * (ul4 + 4 * (q >> 2)) + (q & 3);
+    int o = L.oDummy;
+    if (t < 4 * R) {
+      if (wd < D) o = L.oX + wd * XS + urow;
+      else if (wd < 2 * D) o = L.oX + (wd - D) * XS + R + urow;
+      else if (wd < 2 * D + 4) o = L.oMeta + urow * 4 + (wd - 2 * D);
+    }
+    udst[q] = o;
+  }
+
+  auto prefetch = [&](int kstep, int tile) {
+    if (t < 4 * R) {
+      const int i = tile * BT + rank * R + urow;
+      float* dst = Stage + urow * recw;
+      if (i < B) {
+        long long slot;
+        if (args.idx) slot = args.idx[((size_t)sel * args.K + kstep) * B + i];
+        else slot = philox_index(args.seed, args.agent_id_base + agent, step0 + kstep, i, size);
+        const uint32_t* src = ring + slot * recw;
+        for (int c = ul4; c < cpr; c += 4) cp_async16(dst + 4 * c, src + 4 * c);
+        if (args.taps.enabled && ul4 == 0 && args.taps.indices) args.taps.indices[i] = slot;
+      } else {
+        for (int c = ul4; c < cpr; c += 4) st4(dst + 4 * c, 0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    cp_async_commit();
+  };
+
+  double pb1 = 1.0, pb2 = 1.0;
+  if (t == 0) { pb1 = pow((double)b1, (double)count0); pb2 = pow((double)b2, (double)count0); }
+
+  prefetch(0, 0);
+  cluster.sync();       // every CTA's smem is initialised before anyone writes into it remotely
+
+  for (int kstep = 0; kstep < args.K; ++kstep) {
+    if (t == 0) {
+      if (count0 + kstep < 0x7fffffff) { pb1 *= (double)b1; pb2 *= (double)b2; }
+      Red[8 + 2 * (kstep & 1)] = 1.0f - (float)pb1;
+      Red[9 + 2 * (kstep & 1)] = 1.0f - (float)pb2;
+    }
+    float loss_acc = 0.f;    // warp 0 only
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+      // ---- unpack ----
+      cp_async_wait_all();
+      __syncthreads();
+      if (t < 4 * R) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const int c = ul4 + 4 * cc;
+          if (c < cpr) {
+            const float4 v = ld4(Stage + urow * recw + 4 * c);
+            sm[udst[4 * cc + 0]] = v.x; sm[udst[4 * cc + 1]] = v.y; sm[udst[4 * cc + 2]] = v.z; sm[udst[4 * cc + 3]] = v.w;
+          }
+        }
+      }
+      __syncthreads();
+      if (tile + 1 < ntiles) prefetch(kstep, tile + 1);
+      else if (kstep + 1 < args.K) prefetch(kstep + 1, 0);
+
+      // ---- forward, all 48 forward rows at once (threads 0..191: 12 row tiles x 16 column tiles) ----
+      const int ct = t & 15, rt = t >> 4;
+      const bool fwd = rt < FR / 4;
+      const float* Wsel = rt < 8 ? W : Wt;                 // forward rows 32..47 use theta^-
+      const int xcol = rt < 8 ? 4 * rt : 4 * (rt - 4);     // forward rows 32..47 read the s' columns again
+      if (fwd) {   // layer 1: 4 rows x 2 units
+        u64 acc[4][1];
+        op_init<2>(Wsel + D * kH1 + 2 * ct, acc);
+        op_tile4<2>(X + xcol, XS, Wsel + 2 * ct, kH1, D, acc);
+        op_store_relu<2>(H1 + (2 * ct) * HS + 4 * rt, HS, acc);
+      }
+      __syncthreads();
+      if (fwd) {   // layer 2: 4 rows x 4 units
+        u64 acc[4][2];
+        op_init<4>(Wsel + L.pW2 + kH1 * WS2 + 4 * ct, acc);
+        op_tile4<4>(H1 + 4 * rt, HS, Wsel + L.pW2 + 4 * ct, WS2, kH1, acc);
+        op_store_relu<4>(H2 + (4 * ct) * HS + 4 * rt, HS, acc);
+      }
+      __syncthreads();
+      if (t < 4 * FR) {   // head: split-K over 4 thread groups, forward row fr = t % 48
+        const int fr = t % FR, part = t / FR;
+        const float* wh = (fr < 2 * R ? W : Wt) + L.pWh;
+        constexpr int NP = (A + 2) / 2;
+        u64 acc2[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc2[q] = part == 0 ? ld64(wh + kH2 * HC + 2 * q) : 0ull;
+#pragma unroll 8
+        for (int k = 16 * part; k < 16 * part + 16; ++k) {
+          const float h = H2[k * HS + fr];
+          const u64 hh = pack2(h, h);
+          const u64x2 w0 = ld2x64(wh + k * HC);
+          ffma2(acc2[0], hh, w0.lo);
+          if constexpr (NP > 1) ffma2(acc2[1], hh, w0.hi);
+          if constexpr (NP > 2) { const u64x2 w1 = ld2x64(wh + k * HC + 4); ffma2(acc2[2], hh, w1.lo); if constexpr (NP > 3) ffma2(acc2[3], hh, w1.hi); }
+        }
+        float acc[2 * NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) unpack2(acc2[q], acc[2 * q], acc[2 * q + 1]);
+#pragma unroll
+        for (int c = 0; c <= A; ++c) Scr[(part * HC + c) * FR + fr] = acc[c];
+      }
+      __syncthreads();
+      if (t < R) {   // targets / Huber / d(head) for this CTA's 16 samples (half of warp 0)
+        const int i = t;
+        float hd[3][1 + A];
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+          for (int c = 0; c <= A; ++c) {
+            float v = Scr[(0 * HC + c) * FR + g * R + i];
+#pragma unroll
+            for (int p = 1; p < 4; ++p) v += Scr[(p * HC + c) * FR + g * R + i];
+            hd[g][c] = v;
+          }
+        float q[A], nq[A], nqt[A];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          float ms = 0.f;
+#pragma unroll
+          for (int j = 1; j <= A; ++j) ms += hd[g][j];
+          ms = ms / (float)A;
+#pragma unroll
+          for (int j = 0; j < A; ++j) {
+            const float v = hd[g][0] + hd[g][1 + j] - ms;
+            if (g == 0) q[j] = v; else if (g == 1) nq[j] = v; else nqt[j] = v;
+          }
+        }
+        int astar = 0; float best = nq[0];
+#pragma unroll
+        for (int j = 1; j < A; ++j) if (nq[j] > best) { best = nq[j]; astar = j; }
+        const float4 meta = ld4(Meta + 4 * i);
+        int a = __float_as_int(meta.x);
+        a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+        const float rew = meta.z;
+        const float done = __float_as_uint(meta.w) ? 1.f : 0.f;
+        float qa = q[0], nt = nqt[0];
+#pragma unroll
+        for (int j = 1; j < A; ++j) { if (j == a) qa = q[j]; if (j == astar) nt = nqt[j]; }
+        const float tv = rew + (1.0f - done) * (gamma * nt - qa);
+        const float tgt = qa + tv;
+        const float e = qa - tgt;
+        const float ae = fabsf(e), quad = fminf(ae, 1.0f);
+        const int grow = tile * BT + rank * R + i;
+        const bool valid = grow < B;
+        const float l = valid ? 0.5f * quad * quad + (ae - quad) : 0.f;
+        const float gi = valid ? fminf(fmaxf(e, -1.0f), 1.0f) / fB : 0.f;
+        DhdT[0 * RS + i] = gi;
+        float dsum[1 + A];
+        dsum[0] = gi;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+          const float dadv = (j == a ? gi : 0.f) - gi / (float)A;
+          DhdT[(1 + j) * RS + i] = dadv;
+          dsum[1 + j] = dadv;
+        }
+        float lsum = l;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {      // reduce over the 16 active lanes
+          lsum += __shfl_xor_sync(0x0000ffffu, lsum, o);
+#pragma unroll
+          for (int c = 0; c <= A; ++c) dsum[c] += __shfl_xor_sync(0x0000ffffu, dsum[c], o);
+        }
+        loss_acc += lsum;
+        if (i == 0) {
+#pragma unroll
+          for (int c = 0; c <= A; ++c) Red[16 + c] = dsum[c];
+        }
+        if (args.taps.enabled && valid) {
+#pragma unroll
+          for (int j = 0; j < A; ++j) {
+            if (args.taps.q) args.taps.q[grow * A + j] = q[j];
+            if (args.taps.next_q) args.taps.next_q[grow * A + j] = nq[j];
+            if (args.taps.next_q_tm) args.taps.next_q_tm[grow * A + j] = nqt[j];
+            if (args.taps.targets) args.taps.targets[grow * A + j] = (j == a) ? tgt : q[j];
+          }
+          if (args.taps.max_actions) args.taps.max_actions[grow] = astar;
+        }
+      }
+      __syncthreads();
+
+      // ---- backward ----
+      {  // dh2 (16 rows x 64 units): thread = row r, 4 units
+        const int r = t & 15, jt = t >> 4;
+        if (t <= A) G[L.pWh + kH2 * HC + t] += Red[16 + t];
+        float dh[1 + A];
+#pragma unroll
+        for (int c = 0; c <= A; ++c) dh[c] = DhdT[c * RS + r];
+        float o[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * jt + jj;
+          const float4 w0 = ld4(W + L.pWh + j * HC), w1 = ld4(W + L.pWh + j * HC + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float v = 0.f;
+#pragma unroll
+          for (int c = 0; c <= A; ++c) v = fmaf(dh[c], wv[c], v);
+          o[jj] = H2[j * HS + r] > 0.f ? v : 0.f;
+          Dh2T[j * RS + r] = o[jj];
+        }
+        st4(Dh2R + r * DRS + 4 * jt, o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+          for (int s = 8; s > 0; s >>= 1) o[jj] += __shfl_xor_sync(0xffffffffu, o[jj], s);
+        }
+        if (r == 0) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) G[L.pW2 + kH1 * WS2 + 4 * jt + jj] += o[jj];
+        }
+      }
+      __syncthreads();
+      {  // dW2: warp = 16 x 16 block, reduction over this CTA's 16 rows
+        const int mi = lane & 7, ni = lane >> 3, k0 = 16 * (warp & 1) + mi, j0 = 16 * (warp >> 1) + ni;
+        const float* ap[2] = {H1 + k0 * HS, H1 + (k0 + 8) * HS};
+        const float* bp[4] = {Dh2T + j0 * RS, Dh2T + (j0 + 4) * RS, Dh2T + (j0 + 8) * RS, Dh2T + (j0 + 12) * RS};
+        float acc[2][4];
+        dot_tile<2, 4, 4>(ap, bp, acc);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) G[L.pW2 + (k0 + 8 * i) * WS2 + j0 + 4 * j] += acc[i][j];
+      }
+      {  // dWh: 4-way split over the 16 rows inside a warp
+        const int j = warp * 8 + (lane & 7), part = lane >> 3;
+        const float* ap[1] = {H2 + j * HS + 4 * part};
+        const float* bp[1 + A];
+#pragma unroll
+        for (int c = 0; c <= A; ++c) bp[c] = DhdT + c * RS + 4 * part;
+        float acc[1][1 + A];
+        dot_tile<1, 1 + A, 1>(ap, bp, acc);
+#pragma unroll
+        for (int c = 0; c <= A; ++c) {
+          float v = acc[0][c];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (part == 0) G[L.pWh + j * HC + c] += v;
+        }
+      }
+      {  // dh1 (16 rows x 32 units), reduction over 64 units
+        const int r = t & 15, kk = t >> 4;
+        const float* ap[1] = {Dh2R + r * DRS};
+        const float* bp[2] = {W + L.pW2 + kk * WS2, W + L.pW2 + (kk + 16) * WS2};
+        float acc[1][2];
+        dot_tile<1, 2, 16>(ap, bp, acc);
+        Dh1T[kk * RS + r] = H1[kk * HS + r] > 0.f ? acc[0][0] : 0.f;
+        Dh1T[(kk + 16) * RS + r] = H1[(kk + 16) * HS + r] > 0.f ? acc[0][1] : 0.f;
+      }
+      __syncthreads();
+      {  // [dW1; db1]
+        const int hcol = t & 31, mt = t >> 5;
+        const int d1 = mt + 8 <= D ? mt + 8 : D, d2 = mt + 16 <= D ? mt + 16 : D;
+        const float* bp[1] = {Dh1T + hcol * RS};
+        const float* ap[3] = {X + mt * XS, X + d1 * XS, X + d2 * XS};
+        float acc[3][1];
+        dot_tile<3, 1, 4>(ap, bp, acc);
+        if (mt <= D) G[mt * kH1 + hcol] += acc[0][0];
+        if (mt + 8 <= D) G[(mt + 8) * kH1 + hcol] += acc[1][0];
+        if (mt + 16 <= D) G[(mt + 16) * kH1 + hcol] += acc[2][0];
+      }
+    }  // tiles
+
+    if (t == 0) Red0[rank] = loss_acc;       // this CTA's share of the loss -> rank 0
+    cluster.sync();                          // all partial gradients (and loss shares) are complete and visible
+
+    // ---- reduce-scatter + Adam on this CTA's slice + all-gather of the new weights (DSMEM) ----
+    {
+      const float c1 = Red[8 + 2 * (kstep & 1)], c2 = Red[9 + 2 * (kstep & 1)];
+      const float rc1 = 1.0f / c1, rc2 = 1.0f / c2;
+      const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+#pragma unroll
+      for (int i = 0; i < NPC; ++i) {
+        const int q = t + i * NT, p = rank * L.SL + q;
+        if (q < L.SL && p < L.PS) {
+          const float g = ((Gr[0][p] + Gr[1][p]) + Gr[2][p]) + Gr[3][p];
+          if (args.taps.enabled && args.taps.grads) { const int f = csmem_to_flat(p, D, A, L); if (f >= 0) args.taps.grads[f] = g; }
+          const float m = b1 * mreg[i] + omb1 * g;
+          const float v = b2 * vreg[i] + omb2 * (g * g);
+          mreg[i] = m; vreg[i] = v;
+          const float u = (m * rc1) * fast_rcp(fast_sqrt(v * rc2 + eps_root) + eps);
+          const float th = W[p];
+          const float nw = th - lr * (u + wd * th);
+#pragma unroll
+          for (int c = 0; c < CS; ++c) Wr[c][p] = nw;
+        }
+      }
+    }
+    if (rank == 0 && t == 0) {
+      const float loss = (((Red[0] + Red[1]) + Red[2]) + Red[3]) / fB;
+      args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
+      if (kstep == args.K - 1) args.loss_mailbox[agent] = loss;
+      if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
+    }
+    cluster.sync();                          // every replica holds theta_{t+1}; nobody reads the old partial gradients any more
+    for (int p = t; p < L.PS; p += NT) G[p] = 0.f;
+  }  // steps
+
+  // ---- write back this CTA's slice ----
+#pragma unroll
+  for (int i = 0; i < NPC; ++i) {
+    const int q = t + i * NT, p = rank * L.SL + q;
+    if (q < L.SL && p < L.PS) {
+      const int f = csmem_to_flat(p, D, A, L);
+      if (f >= 0) { gW[f] = W[p]; gM[f] = mreg[i]; gV[f] = vreg[i]; }
+    }
+  }
+  if (rank == 0 && t == 0) {
+    ctl->train_steps = step0 + args.K;
+    const long long c = (long long)count0 + args.K;
+    ctl->adam_count = c > 0x7fffffffLL ? 0x7fffffff : (int)c;
+  }
+  cluster.sync();   // no CTA may exit while its shared memory can still be addressed remotely
+}
+
+typedef void (*ClusterKernel)(const TrainArgs);
+ClusterKernel pick_cluster_kernel(int A) {
+  switch (A) {
+    case 2: return dqn_train_cluster_kernel<2>;
+    case 3: return dqn_train_cluster_kernel<3>;
+    case 4: return dqn_train_cluster_kernel<4>;
+    case 5: return dqn_train_cluster_kernel<5>;
+    case 6: return dqn_train_cluster_kernel<6>;
+    case 7: return dqn_train_cluster_kernel<7>;
+    default: return nullptr;
+  }
+}
+
+}  // namespace
+
+size_t train_cluster_smem_bytes(const Dims& d) { return (size_t)make_clayout(d.D, d.recw).total * sizeof(float); }
+
+cudaError_t train_cluster_prepare(const Dims& d) {
+  ClusterKernel k = pick_cluster_kernel(d.A);
+  if (!k) return cudaErrorInvalidValue;
+  return cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_cluster_smem_bytes(d));
+}
+
+cudaError_t launch_train_cluster(cudaStream_t st, const TrainArgs& args) {
+  ClusterKernel k = pick_cluster_kernel(args.dims.A);
+  if (!k) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(args.n_sel * CS));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = train_cluster_smem_bytes(args.dims);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, args);
+}
+
+}  // namespace dqn

@@ -5,6 +5,7 @@ device, whose ``data_ptr()`` is handed to ``dqn_create``) and naming the stream 
 enqueued on (so ``torch.cuda.Event`` timing sees them).  All arithmetic is in ``libdqn_b200.so``.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -18,7 +19,7 @@ def _f32(a):
 
 class DqnEngine:
     def __init__(self, obs_dim, num_actions, buffer_size, batch_size, gamma, optimizer, n_agents=1,
-                 seed=0, device=0, hidden=(32, 64), agent_id_base=0):
+                 seed=0, device=0, hidden=(32, 64), agent_id_base=0, step_kernel=None):
         import torch   # allocator + stream only
 
         self.lib = _lib.load()
@@ -39,6 +40,11 @@ class DqnEngine:
         cfg.eps, cfg.eps_root, cfg.weight_decay = optimizer.eps, optimizer.eps_root, optimizer.weight_decay
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.agent_id_base = int(agent_id_base)
+        # which train-step kernel: "auto" (cluster while 4 * agents <= SMs), "cta" (one CTA per agent) or
+        # "cluster" (one agent over a 4-CTA cluster); DQN_B200_STEP_KERNEL overrides the default
+        step_kernel = step_kernel or os.environ.get("DQN_B200_STEP_KERNEL", "auto")
+        cfg.step_kernel = _lib.STEP_KERNELS[step_kernel]
+        self.step_kernel = step_kernel
         nbytes = C.c_uint64(0)
         _lib.check(self.lib.dqn_arena_bytes(C.byref(cfg), C.byref(nbytes)))
         with torch.cuda.device(self.device):

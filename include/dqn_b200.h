@@ -49,6 +49,10 @@ enum {
 
 enum { DQN_OPT_ADAM = 0, DQN_OPT_ADAMW = 1 };
 enum { DQN_PARAMS_ONLINE = 0, DQN_PARAMS_TARGET = 1 };
+/* Train-step kernel: one CTA per agent (throughput form, used for populations), or one agent spread over a
+ * 4-CTA thread-block cluster (latency form, used for a single agent).  AUTO = cluster while 4*agents <= SMs.
+ * Both compute the same update; summation orders differ (results agree to fp32 round-off). */
+enum { DQN_STEP_AUTO = 0, DQN_STEP_CTA = 1, DQN_STEP_CLUSTER = 2 };
 
 /* Construction-time configuration == the part of `Agent.__init__` (q_agent.py:61-118) that shapes
  * the hot path.  `network` becomes (obs_dim, hidden1, hidden2, num_actions) -- the dueling MLP of
@@ -70,7 +74,8 @@ typedef struct dqn_config {
   float lr, b1, b2, eps, eps_root, weight_decay;
   uint64_t seed;         /* Philox key for minibatch indices */
   int32_t agent_id_base; /* global id of local agent 0: the Philox counter uses (agent_id_base + agent), */
-  int32_t reserved0;     /*   so a sharded population draws the same indices as the unsharded one       */
+  int32_t step_kernel;   /*   so a sharded population draws the same indices as the unsharded one       */
+                         /* step_kernel: DQN_STEP_AUTO / _CTA / _CLUSTER (which train-step kernel, see below) */
   void* stream;          /* cudaStream_t to enqueue on (NULL = default stream) */
   void* arena;           /* optional caller-allocated device memory (e.g. a torch tensor's  */
   uint64_t arena_bytes;  /*   data_ptr()); NULL => the library allocates dqn_arena_bytes() itself */
@@ -125,6 +130,7 @@ DQN_API int dqn_set_opt_state(dqn_handle* h, int32_t agent, int32_t count, const
 DQN_API int dqn_get_opt_state(dqn_handle* h, int32_t agent, int32_t* count, float* mu, float* nu, int32_t n);
 DQN_API int dqn_set_hparams(dqn_handle* h, int32_t agent, const dqn_hparams* hp);
 DQN_API int dqn_get_hparams(dqn_handle* h, int32_t agent, dqn_hparams* hp);
+DQN_API int dqn_set_step_kernel(dqn_handle* h, int32_t step_kernel);   /* DQN_STEP_* */
 
 /* ReplayBuffer.add (replay_buffer.py:58-65), vectorised: equivalent to n scalar add() calls in order
  * into agent's ring (slot (counter+i) % N).  Host pointers: s/s2 f32[n*D], a i64[n], r f32[n],

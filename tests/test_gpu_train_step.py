@@ -15,6 +15,14 @@ from oracle.replay_oracle import synthetic_transitions
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["cta", "cluster"])
+def step_kernel(request, monkeypatch):
+    """Every test of this module runs against both train-step kernels: one CTA per agent (train_fused.cu) and
+    one agent over a 4-CTA cluster (train_cluster.cu)."""
+    monkeypatch.setenv("DQN_B200_STEP_KERNEL", request.param)
+    return request.param
+
+
 def make_pair(D=9, A=4, B=64, N=2000, n_fill=1500, kind="adamw", lr=2e-4, gamma=0.99, seed=0, params=None,
               done_p=0.2, perturb_target=True):
     rng = np.random.default_rng(seed)
