@@ -37,7 +37,7 @@ GAMMA, LR = 0.99, 2e-4
 TRAIN_FREQUENCY = 4                      # Test/lunar_lander.py:30 -- env transitions stored per train step
 REC_BYTES_ALGO = 2 * 4 * D + 8 + 4 + 1   # 77 B per sampled transition in the reference's dtypes
 FLOP_PER_SAMPLE = 25728                  # D=8, H=(32,64): 3 forwards + backward
-STEPS_PER_LAUNCH = 500
+STEPS_PER_LAUNCH = int(os.environ.get("DQN_BENCH_KPL", "500"))   # train steps fused into one persistent launch
 
 
 def measured_peaks():

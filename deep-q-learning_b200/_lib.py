@@ -86,6 +86,7 @@ PROTOTYPES = {
     "dqn_sample_batch": (C.c_int, [_H, _i32, _P, _i64, _i32, _P, _P, _P, _P, _P]),
     "dqn_sample_batch_device": (C.c_int, [_H, _i32, _P, _i64, _i32, _P, _P, _P, _P, _P]),
     "dqn_train_step": (C.c_int, [_H, _i32, _i32, _i32, _P, C.POINTER(DqnDebugTaps)]),
+    "dqn_store_train_step": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P, _i32, _P]),
     "dqn_train_step_device_idx": (C.c_int, [_H, _i32, _i32, _i32, _P]),
     "dqn_get_losses": (C.c_int, [_H, _i32, _i32, _P, C.POINTER(_i64)]),
     "dqn_sync_target": (C.c_int, [_H, _i32, _i32]),

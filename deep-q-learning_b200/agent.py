@@ -146,10 +146,14 @@ class Agent:
     def _step(self, indices=None):
         """One fused train step (sample -> preprocess -> targets -> grad -> adam).  ``indices``
         (optional, i64[batch_size]) replaces the Philox draw -- the hook parity runs use."""
-        self._replay_buffer.flush()
+        rb = self._replay_buffer
         if indices is None:
-            _lib.check(self._lib.dqn_train_step(self._h, 0, 1, 1, None, None))
+            # the add()s staged since the last step (train_frequency of them, q_agent.py:182-187) ride in the
+            # kernel's parameter buffer: one launch, no H2D copy (falls back to store + train for > 16)
+            n, rb._pending = rb._pending, 0
+            _lib.check(self._lib.dqn_store_train_step(self._h, 0, n, *rb._ptrs, 1, None))
         else:
+            rb.flush()
             self._engine.train_steps(1, indices=indices, agent_begin=0, agent_end=1)
 
     def _steps(self, k):

@@ -17,14 +17,13 @@ dqn_act_kernel(const float* __restrict__ params, Dims d, int agent_begin, int n_
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= n_sel) return;
   const int D = d.D, A = d.A;
-  const float* W1 = params + (size_t)(agent_begin + item) * 4 * d.PF;
+  // packed layout (common.cuh): [W1;b1] | [W2;b2] rows of 68 | head 65 x 8 (col 0 = V, 1..A = advantage)
+  const float* W1 = params + (size_t)(agent_begin + item) * 4 * d.PK;
   const float* b1 = W1 + D * kH1;
-  const float* W2 = b1 + kH1;
-  const float* b2 = W2 + kH1 * kH2;
-  const float* Wv = b2 + kH2;
-  const float* bv = Wv + kH2;
-  const float* Wa = bv + 1;
-  const float* ba = Wa + kH2 * A;
+  const float* W2 = W1 + packed_w2(D);
+  const float* b2 = W2 + kH1 * kW2Stride;
+  const float* Wh = W1 + packed_head(D);
+  const float* bh = Wh + kH2 * kHeadCols;
   const float* x = states + (size_t)item * D;
 
   float z = b1[lane];
@@ -34,23 +33,22 @@ dqn_act_kernel(const float* __restrict__ params, Dims d, int agent_begin, int n_
 #pragma unroll 8
   for (int k = 0; k < kH1; ++k) {
     const float hk = __shfl_sync(0xffffffffu, h1, k);
-    z0 = fmaf(hk, W2[k * kH2 + lane], z0);
-    z1 = fmaf(hk, W2[k * kH2 + lane + 32], z1);
+    z0 = fmaf(hk, W2[k * kW2Stride + lane], z0);
+    z1 = fmaf(hk, W2[k * kW2Stride + lane + 32], z1);
   }
   const float h20 = fmaxf(z0, 0.f), h21 = fmaxf(z1, 0.f);
   float head[1 + kMaxA];
-  head[0] = h20 * Wv[lane] + h21 * Wv[lane + 32];
-  for (int j = 0; j < kMaxA; ++j)
-    head[1 + j] = j < A ? h20 * Wa[lane * A + j] + h21 * Wa[(lane + 32) * A + j] : 0.f;
+  for (int c = 0; c <= kMaxA; ++c)      // packed head columns > A are zero
+    head[c] = h20 * Wh[lane * kHeadCols + c] + h21 * Wh[(lane + 32) * kHeadCols + c];
 #pragma unroll
   for (int c = 0; c <= kMaxA; ++c) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) head[c] += __shfl_xor_sync(0xffffffffu, head[c], o);
   }
   if (lane == 0) {
-    const float val = head[0] + bv[0];
+    const float val = head[0] + bh[0];
     float msum = 0.f;
-    for (int j = 0; j < A; ++j) { head[1 + j] += ba[j]; msum += head[1 + j]; }
+    for (int j = 0; j < A; ++j) { head[1 + j] += bh[1 + j]; msum += head[1 + j]; }
     const float mean = msum / (float)A;
     int best = 0; float bq = 0.f;
     for (int j = 0; j < A; ++j) {
@@ -63,9 +61,9 @@ dqn_act_kernel(const float* __restrict__ params, Dims d, int agent_begin, int n_
 }
 
 __global__ void __launch_bounds__(256)
-dqn_sync_target_kernel(float* __restrict__ params, int PF, int agent_begin) {
-  float4* base = reinterpret_cast<float4*>(params + (size_t)(agent_begin + blockIdx.x) * 4 * PF);
-  const int n4 = PF >> 2;
+dqn_sync_target_kernel(float* __restrict__ params, int PK, int agent_begin) {
+  float4* base = reinterpret_cast<float4*>(params + (size_t)(agent_begin + blockIdx.x) * 4 * PK);
+  const int n4 = PK >> 2;
   for (int i = threadIdx.x; i < n4; i += blockDim.x) base[n4 + i] = base[i];
 }
 
@@ -78,7 +76,7 @@ cudaError_t launch_act(cudaStream_t st, const float* params, const Dims& d, int 
 
 cudaError_t launch_sync_target(cudaStream_t st, float* params, const Dims& d, int agent_begin, int n_sel) {
   if (n_sel <= 0) return cudaSuccess;
-  dqn_sync_target_kernel<<<n_sel, 256, 0, st>>>(params, d.PF, agent_begin);
+  dqn_sync_target_kernel<<<n_sel, 256, 0, st>>>(params, d.PK, agent_begin);
   return cudaGetLastError();
 }
 

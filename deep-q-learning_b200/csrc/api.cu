@@ -63,7 +63,7 @@ TapsOff taps_layout(const Dims& d) {
   t.tgt = o; o += align_up((size_t)DQN_MAX_BATCH * d.A * 4, 256);
   t.maxa = o; o += align_up((size_t)DQN_MAX_BATCH * 4, 256);
   t.loss = o; o += 256;
-  t.grads = o; o += align_up((size_t)d.PF * 4, 256);
+  t.grads = o; o += align_up((size_t)d.PK * 4, 256);
   t.bytes = o;
   return t;
 }
@@ -71,7 +71,7 @@ TapsOff taps_layout(const Dims& d) {
 Carve carve(const Dims& d, int n_agents) {
   Carve c;
   size_t o = 0;
-  c.params = o; o += align_up((size_t)n_agents * 4 * d.PF * 4, 256);
+  c.params = o; o += align_up((size_t)n_agents * 4 * d.PK * 4, 256);
   c.ctl = o; o += align_up((size_t)n_agents * sizeof(AgentCtl), 256);
   c.rings = o; o += align_up((size_t)n_agents * (size_t)d.N * d.recw * 4, 256);
   c.loss = o; o += align_up((size_t)n_agents * kLossCap * 4, 256);
@@ -96,7 +96,7 @@ int validate(const dqn_config* cfg, Dims* d) {
   d->D = cfg->obs_dim;
   d->A = cfg->num_actions;
   d->P = flat_param_count(d->D, d->A);
-  d->PF = (d->P + 3) & ~3;
+  d->PK = packed_count(d->D);
   d->recw = record_words(d->D);
   d->N = cfg->buffer_size;
   return DQN_OK;
@@ -121,8 +121,8 @@ struct dqn_handle {
   uint8_t* taps;
   uint8_t* pinned;
   uint8_t* bounce;              // pinned + kBounceOff
-  float* mailbox;               // mapped pinned host memory, [n_agents]: last loss of each agent's last launch
-  float* mailbox_dev;           // device alias of `mailbox`
+  volatile unsigned long long* mailbox;   // mapped pinned host memory, [n_agents]: (train_steps << 32) | loss bits of each
+  unsigned long long* mailbox_dev;        //   agent's last launch (one 8-byte store by the kernel); device alias
   cudaEvent_t slot_ev[kSlots];  // completion of the H2D copy that last used each pinned store slot
   int slot_next;
   std::vector<AgentCtl> hctl;   // host mirror of the per-agent control blocks
@@ -222,10 +222,10 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   if (e != cudaSuccess) { if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaMallocHost failed"); }
   h->bounce = h->pinned + kBounceOff;
   h->mailbox = nullptr; h->mailbox_dev = nullptr;
-  e = cudaHostAlloc((void**)&h->mailbox, sizeof(float) * cfg->n_agents, cudaHostAllocMapped);
-  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->mailbox_dev, h->mailbox, 0);
+  e = cudaHostAlloc((void**)&h->mailbox, sizeof(unsigned long long) * cfg->n_agents, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->mailbox_dev, (void*)h->mailbox, 0);
   if (e != cudaSuccess) { cudaFreeHost(h->pinned); if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaHostAlloc(mapped) failed"); }
-  memset(h->mailbox, 0, sizeof(float) * cfg->n_agents);
+  memset((void*)h->mailbox, 0, sizeof(unsigned long long) * cfg->n_agents);
   h->slot_next = 0;
   for (int i = 0; i < kSlots; ++i) cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming);
   // zero parameters / moments / rings / losses (ReplayBuffer.__init__ zero-fills, replay_buffer.py:26-30)
@@ -250,7 +250,7 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   if (e != cudaSuccess) {
     std::string m = std::string("dqn_create: device initialisation failed: ") + cudaGetErrorString(e);
     for (int i = 0; i < kSlots; ++i) cudaEventDestroy(h->slot_ev[i]);
-    cudaFreeHost(h->mailbox);
+    cudaFreeHost((void*)h->mailbox);
     cudaFreeHost(h->pinned);
     if (h->own_arena) cudaFree(h->arena);
     delete h;
@@ -265,7 +265,7 @@ DQN_API int dqn_destroy(dqn_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   for (int i = 0; i < kSlots; ++i) cudaEventDestroy(h->slot_ev[i]);
-  if (h->mailbox) cudaFreeHost(h->mailbox);
+  if (h->mailbox) cudaFreeHost((void*)h->mailbox);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_arena) cudaFree(h->arena);
   delete h;
@@ -285,13 +285,30 @@ DQN_API int dqn_synchronize(dqn_handle* h) {
   return DQN_OK;
 }
 
+namespace {
+// flat (include/dqn_b200.h) <-> packed (common.cuh) through the pinned bounce buffer; `slot` picks one of the
+// PK-float regions of the bounce so that several arrays can be in flight before one synchronisation
+float* bounce_slot(dqn_handle* h, int slot) { return (float*)h->bounce + (size_t)slot * h->dims.PK; }
+void pack_flat(const dqn_handle* h, const float* flat, float* packed) {
+  const int PK = h->dims.PK, D = h->dims.D, A = h->dims.A;
+  for (int p = 0; p < PK; ++p) { const int f = packed_to_flat(p, D, A); packed[p] = f >= 0 ? flat[f] : 0.f; }
+}
+void unpack_flat(const dqn_handle* h, const float* packed, float* flat) {
+  const int PK = h->dims.PK, D = h->dims.D, A = h->dims.A;
+  for (int p = 0; p < PK; ++p) { const int f = packed_to_flat(p, D, A); if (f >= 0) flat[f] = packed[p]; }
+}
+}  // namespace
+
 DQN_API int dqn_set_params(dqn_handle* h, int32_t agent, int32_t which, const float* host_flat, int32_t n) {
   if (int rc = check_agent(h, agent)) return rc;
   if ((which != DQN_PARAMS_ONLINE && which != DQN_PARAMS_TARGET) || !host_flat || n != h->dims.P)
     return fail(DQN_E_INVALID, "dqn_set_params: bad `which`, NULL pointer or n != dqn_param_count");
   CU(cudaSetDevice(h->cfg.device));
-  float* dst = h->params + ((size_t)agent * 4 + which) * h->dims.PF;
-  CU(cudaMemcpyAsync(dst, host_flat, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));     // the bounce buffer may still be in flight
+  const int PK = h->dims.PK;
+  pack_flat(h, host_flat, bounce_slot(h, 0));
+  float* dst = h->params + ((size_t)agent * 4 + which) * PK;
+  CU(cudaMemcpyAsync(dst, bounce_slot(h, 0), (size_t)PK * 4, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return DQN_OK;
 }
@@ -301,9 +318,11 @@ DQN_API int dqn_get_params(dqn_handle* h, int32_t agent, int32_t which, float* h
   if ((which != DQN_PARAMS_ONLINE && which != DQN_PARAMS_TARGET) || !host_flat || n != h->dims.P)
     return fail(DQN_E_INVALID, "dqn_get_params: bad `which`, NULL pointer or n != dqn_param_count");
   CU(cudaSetDevice(h->cfg.device));
-  const float* src = h->params + ((size_t)agent * 4 + which) * h->dims.PF;
-  CU(cudaMemcpyAsync(host_flat, src, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  const int PK = h->dims.PK;
+  const float* src = h->params + ((size_t)agent * 4 + which) * PK;
+  CU(cudaMemcpyAsync(bounce_slot(h, 0), src, (size_t)PK * 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  unpack_flat(h, bounce_slot(h, 0), host_flat);
   return DQN_OK;
 }
 
@@ -311,9 +330,12 @@ DQN_API int dqn_set_opt_state(dqn_handle* h, int32_t agent, int32_t count, const
   if (int rc = check_agent(h, agent)) return rc;
   if (!mu || !nu || n != h->dims.P || count < 0) return fail(DQN_E_INVALID, "dqn_set_opt_state: NULL pointer, n != dqn_param_count or count < 0");
   CU(cudaSetDevice(h->cfg.device));
-  float* base = h->params + (size_t)agent * 4 * h->dims.PF;
-  CU(cudaMemcpyAsync(base + 2 * h->dims.PF, mu, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(base + 3 * h->dims.PF, nu, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const int PK = h->dims.PK;
+  float* base = h->params + (size_t)agent * 4 * PK;
+  pack_flat(h, mu, bounce_slot(h, 0));
+  pack_flat(h, nu, bounce_slot(h, 1));
+  CU(cudaMemcpyAsync(base + 2 * PK, bounce_slot(h, 0), (size_t)2 * PK * 4, cudaMemcpyHostToDevice, h->stream));   // mu | nu are adjacent
   h->hctl[agent].adam_count = count;
   CU(cudaMemcpyAsync(&h->ctl[agent].adam_count, &h->hctl[agent].adam_count, 4, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -324,12 +346,14 @@ DQN_API int dqn_get_opt_state(dqn_handle* h, int32_t agent, int32_t* count, floa
   if (int rc = check_agent(h, agent)) return rc;
   if (n != h->dims.P) return fail(DQN_E_INVALID, "dqn_get_opt_state: n != dqn_param_count");
   CU(cudaSetDevice(h->cfg.device));
-  const float* base = h->params + (size_t)agent * 4 * h->dims.PF;
-  if (mu) CU(cudaMemcpyAsync(mu, base + 2 * h->dims.PF, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  if (nu) CU(cudaMemcpyAsync(nu, base + 3 * h->dims.PF, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  int32_t* pc = (int32_t*)h->bounce;
+  const int PK = h->dims.PK;
+  const float* base = h->params + (size_t)agent * 4 * PK;
+  CU(cudaMemcpyAsync(bounce_slot(h, 0), base + 2 * PK, (size_t)2 * PK * 4, cudaMemcpyDeviceToHost, h->stream));
+  int32_t* pc = (int32_t*)bounce_slot(h, 2);
   CU(cudaMemcpyAsync(pc, &h->ctl[agent].adam_count, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  if (mu) unpack_flat(h, bounce_slot(h, 0), mu);
+  if (nu) unpack_flat(h, bounce_slot(h, 1), nu);
   if (count) *count = *pc;
   return DQN_OK;
 }
@@ -514,10 +538,15 @@ DQN_API int dqn_sample_batch(dqn_handle* h, int32_t agent, const int64_t* idx, i
 }
 
 namespace {
-int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, dqn_debug_taps* taps) {
+// one agent per CTA fills the chip once there are ~SMs agents; below that, spread each agent over a 4-CTA cluster
+bool uses_cluster(const dqn_handle* h, int n_sel) {
+  return h->step_kernel == DQN_STEP_CLUSTER || (h->step_kernel == DQN_STEP_AUTO && 4 * n_sel <= h->sm_count);
+}
+
+int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, dqn_debug_taps* taps, const InlineStore* ist = nullptr) {
   const int n_sel = e - b;
   for (int ag = b; ag < e; ++ag) {
-    if (size_of(h, ag) == 0) return fail(DQN_E_INVALID, "dqn_train_step: replay ring of an agent is empty");
+    if (size_of(h, ag) == 0 && !(ist && ist->n > 0)) return fail(DQN_E_INVALID, "dqn_train_step: replay ring of an agent is empty");
   }
   TrainArgs ta;
   memset(&ta, 0, sizeof ta);
@@ -538,9 +567,11 @@ int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, d
   }
   // one agent per CTA fills the chip once there are >= ~SMs agents; below that an agent's step is a serial
   // latency chain on one SM, so the minibatch rows are spread over a 4-CTA cluster instead
-  const bool cluster = h->step_kernel == DQN_STEP_CLUSTER || (h->step_kernel == DQN_STEP_AUTO && 4 * n_sel <= h->sm_count);
-  if (cluster) CU(launch_train_cluster(h->stream, ta));
+  const bool cluster = uses_cluster(h, n_sel);
+  if (ist && !cluster) return fail(DQN_E_INVALID, "internal: inline store needs the cluster kernel");
+  if (cluster) CU(launch_train_cluster(h->stream, ta, ist));
   else CU(launch_train_fused(h->stream, ta));
+  if (ist) h->hctl[b].ring_counter += ist->n;
   for (int ag = b; ag < e; ++ag) {
     AgentCtl& c = h->hctl[ag];
     c.train_steps += K;
@@ -557,12 +588,76 @@ int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, d
     if (taps->targets) CU(cudaMemcpyAsync(taps->targets, t + h->to.tgt, (size_t)B * A * 4, cudaMemcpyDeviceToHost, h->stream));
     if (taps->max_actions) CU(cudaMemcpyAsync(taps->max_actions, t + h->to.maxa, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
     if (taps->loss) CU(cudaMemcpyAsync(taps->loss, t + h->to.loss, 4, cudaMemcpyDeviceToHost, h->stream));
-    if (taps->grads) CU(cudaMemcpyAsync(taps->grads, t + h->to.grads, (size_t)h->dims.P * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (taps->grads) CU(cudaMemcpyAsync(bounce_slot(h, 0), t + h->to.grads, (size_t)h->dims.PK * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (taps->grads) unpack_flat(h, bounce_slot(h, 0), taps->grads);
   }
   return DQN_OK;
 }
 }  // namespace
+
+namespace {
+// Loss of the agent's most recent launch without a stream synchronisation: the kernel's last store is
+// (train_steps << 32 | loss bits) into mapped pinned memory, so the host polls for the step count it expects.
+int wait_mailbox(dqn_handle* h, int agent, float* loss_out) {
+  const uint32_t want = (uint32_t)h->hctl[agent].train_steps;
+  volatile unsigned long long* mb = h->mailbox + agent;
+  for (unsigned long spin = 1;; ++spin) {
+    const unsigned long long v = *mb;
+    if ((uint32_t)(v >> 32) == want) {
+      const uint32_t bits = (uint32_t)v;
+      memcpy(loss_out, &bits, 4);
+      return DQN_OK;
+    }
+    if ((spin & 0xfff) == 0) {     // every 4096 polls make sure the stream is still alive (a faulted kernel never writes)
+      const cudaError_t e = cudaStreamQuery(h->stream);
+      if (e == cudaSuccess) {
+        // stream drained: the launch that produced `want` has completed; if the mailbox still disagrees the handle's
+        // state was edited between launches (e.g. counters restored) -- read the loss ring instead
+        if ((uint32_t)(*mb >> 32) == want) continue;
+        const size_t pos = (size_t)((h->hctl[agent].train_steps - 1) % kLossCap);
+        CU(cudaMemcpyAsync(h->bounce, h->loss_ring + (size_t)agent * kLossCap + pos, 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        memcpy(loss_out, h->bounce, 4);
+        return DQN_OK;
+      }
+      if (e != cudaErrorNotReady) return fail(DQN_E_CUDA, std::string("dqn_get_losses: ") + cudaGetErrorString(e));
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+}  // namespace
+
+DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a, const float* r,
+                                 const float* s2, const uint8_t* done, int32_t K, float* loss_out) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (K < 1) return fail(DQN_E_INVALID, "dqn_store_train_step: K must be >= 1");
+  if (n < 0 || (n > 0 && (!s || !a || !r || !s2 || !done))) return fail(DQN_E_INVALID, "dqn_store_train_step: negative n or NULL array");
+  CU(cudaSetDevice(h->cfg.device));
+  if (n > 0 && n <= kInlineMax && uses_cluster(h, 1)) {
+    // the transitions ride in the kernel-parameter buffer: no H2D copy, no store launch
+    InlineStore ist;
+    ist.n = (int)n;
+    const int D = h->dims.D, recw = h->dims.recw;
+    memset(ist.rec, 0, (size_t)n * recw * 4);
+    for (int i = 0; i < (int)n; ++i) {
+      uint32_t* rec = ist.rec + (size_t)i * recw;
+      memcpy(rec, s + (size_t)i * D, (size_t)D * 4);
+      memcpy(rec + D, s2 + (size_t)i * D, (size_t)D * 4);
+      memcpy(rec + 2 * D, a + i, 8);
+      memcpy(rec + 2 * D + 2, r + i, 4);
+      rec[2 * D + 3] = done[i] ? 1u : 0u;
+    }
+    if (int rc = train_common(h, agent, agent + 1, K, nullptr, nullptr, &ist)) return rc;
+  } else {
+    if (n > 0) if (int rc = dqn_store(h, agent, n, s, a, r, s2, done)) return rc;
+    if (int rc = train_common(h, agent, agent + 1, K, nullptr, nullptr)) return rc;
+  }
+  if (loss_out) return wait_mailbox(h, agent, loss_out);
+  return DQN_OK;
+}
 
 DQN_API int dqn_train_step(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K, const int64_t* idx, dqn_debug_taps* taps) {
   if (int rc = check_range(h, agent_begin, agent_end)) return rc;
@@ -601,11 +696,7 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
   if (n == 0) return DQN_OK;
   if (n < 0 || n > kLossCap || n > ts || !loss_out) return fail(DQN_E_INVALID, "dqn_get_losses: n must be <= min(train steps so far, 4096)");
   CU(cudaSetDevice(h->cfg.device));
-  if (n == 1) {   // the kernel wrote it straight into mapped host memory: one synchronisation, no copy
-    CU(cudaStreamSynchronize(h->stream));
-    loss_out[0] = h->mailbox[agent];
-    return DQN_OK;
-  }
+  if (n == 1) return wait_mailbox(h, agent, loss_out);   // the kernel wrote it straight into mapped host memory
   // the last n losses are at ring positions [(ts-n) % cap, ts % cap): at most two contiguous pieces
   const size_t first = (size_t)((ts - n) % kLossCap);
   const size_t n1 = first + (size_t)n <= (size_t)kLossCap ? (size_t)n : (size_t)kLossCap - first;

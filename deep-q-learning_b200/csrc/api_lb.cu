@@ -111,7 +111,7 @@ struct dqn_lb_handle {
 namespace {
 long long lb_size(const dqn_lb_handle* h) { return h->ring_counter < h->dims.N ? h->ring_counter : h->dims.N; }
 Dims ring_dims(const dqn_lb_handle* h) {
-  Dims d; d.D = h->dims.D; d.A = h->dims.A; d.P = h->dims.P; d.PF = h->dims.PF; d.recw = h->dims.recw; d.N = h->dims.N;
+  Dims d; d.D = h->dims.D; d.A = h->dims.A; d.P = h->dims.P; d.PK = 0; d.recw = h->dims.recw; d.N = h->dims.N;
   return d;
 }
 }  // namespace

@@ -1,8 +1,10 @@
 // common.cuh -- shared device/host definitions for libdqn_b200 (sm_100a).
 //
 // HBM data layout (see DESIGN.md "Data layout"):
-//   params   f32 [n_agents][4][PF]        online | target | mu | nu, each in the FLAT layout of
-//                                          include/dqn_b200.h; PF = P rounded up to 4 floats.
+//   params   f32 [n_agents][4][PK]        online | target | mu | nu, each in the PACKED layout below (the layout
+//                                          the train-step kernels keep in shared memory, so a launch starts with a
+//                                          straight 16-byte copy); the C ABI converts to / from the flat layout of
+//                                          include/dqn_b200.h in dqn_set_* / dqn_get_*.
 //   ctl      AgentCtl [n_agents]          per-agent hyper-parameters and counters.
 //   ring     u8  [n_agents][N][REC]       AoS replay records, REC = round_up((2D+4)*4, 32) bytes:
 //                                          words [0,D) s | [D,2D) s' | 2D,2D+1 action (i64) |
@@ -34,13 +36,40 @@ struct AgentCtl {
 struct Dims {
   int D, A;      // obs dim, actions
   int P;         // flat parameter count
-  int PF;        // P rounded up to a multiple of 4
+  int PK;        // packed (HBM / shared-memory) parameter count, a multiple of 4
   int recw;      // record stride in 32-bit words
   long long N;   // ring slots per agent
 };
 
 __host__ __device__ inline int flat_param_count(int D, int A) {
   return D * kH1 + kH1 + kH1 * kH2 + kH2 + kH2 + 1 + kH2 * A + A;
+}
+
+// Packed parameter layout ("augmented" matrices: the bias is the last row of each block, padding is 0):
+//   [W1;b1]  (D+1) x 32              at 0
+//   [W2;b2]  33 x 64, row stride 68  at packed_w2(D)      (68 = 4 mod 32 words: rows 4 banks apart in shared memory)
+//   head     65 x 8                  at packed_head(D)    (col 0 = V, cols 1..A = advantage, row 64 = biases)
+constexpr int kW2Stride = kH2 + 4;
+constexpr int kHeadCols = 8;
+__host__ __device__ inline int packed_w2(int D) { return (D + 1) * kH1; }
+__host__ __device__ inline int packed_head(int D) { return packed_w2(D) + (kH1 + 1) * kW2Stride; }
+__host__ __device__ inline int packed_count(int D) { return (packed_head(D) + (kH2 + 1) * kHeadCols + 3) & ~3; }
+// packed index -> flat index of include/dqn_b200.h (-1 = padding)
+__host__ __device__ inline int packed_to_flat(int p, int D, int A) {
+  const int pW2 = packed_w2(D), pWh = packed_head(D);
+  if (p < pW2) return p;                              // [W1;b1] is contiguous in both layouts
+  const int offWv = pW2 + (kH1 + 1) * kH2;            // flat offset of Wv = D*32 + 32 + 32*64 + 64
+  if (p < pWh) {
+    const int q = p - pW2;
+    const int row = q / kW2Stride, col = q - row * kW2Stride;
+    return col < kH2 ? pW2 + row * kH2 + col : -1;
+  }
+  const int q = p - pWh;
+  const int k = q >> 3, c = q & 7;
+  const int offbv = offWv + kH2, offWa = offbv + 1, offba = offWa + kH2 * A;
+  if (k > kH2 || c > A) return -1;
+  if (k < kH2) return c == 0 ? offWv + k : offWa + k * A + (c - 1);
+  return c == 0 ? offbv : offba + (c - 1);
 }
 __host__ __device__ inline int record_words(int D) { return (((2 * D + 4) * 4 + 31) / 32) * 8; }
 

@@ -16,16 +16,17 @@ struct TapsDev {
   int* max_actions;
   float* targets;
   float* loss;
-  float* grads;   // flat layout, P floats
+  float* grads;   // packed layout, PK floats
   int enabled;
 };
 
 struct TrainArgs {
-  float* params;              // [n_agents][4][PF]
+  float* params;              // [n_agents][4][PK], packed layout (common.cuh)
   AgentCtl* ctl;              // [n_agents]
-  const uint32_t* rings;      // [n_agents][N][recw]
+  uint32_t* rings;            // [n_agents][N][recw]
   float* loss_ring;           // [n_agents][kLossCap]
-  float* loss_mailbox;        // [n_agents] zero-copy (mapped pinned host memory): loss of the launch's last step
+  unsigned long long* loss_mailbox;   // [n_agents] zero-copy (mapped pinned host memory): (train_steps << 32) | loss bits
+                                      //   of the launch's last step, one 8-byte store -- the host can poll it
   const long long* idx;       // device i64 [n_sel][K][B] or nullptr (Philox)
   Dims dims;
   unsigned long long seed;
@@ -53,7 +54,16 @@ cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args);
 // the same step with one agent spread over a 4-CTA thread-block cluster (train_cluster.cu)
 size_t train_cluster_smem_bytes(const Dims& d);
 cudaError_t train_cluster_prepare(const Dims& d);
-cudaError_t launch_train_cluster(cudaStream_t st, const TrainArgs& args);
+// Transitions that ride in the kernel-parameter buffer (no H2D copy, no separate store launch): n records in the
+// ring's AoS layout with stride dims.recw words, written to slots (ring_counter + i) % N before the first gather.
+constexpr int kInlineMax = 16;
+constexpr int kInlineWords = 40;      // record words at D = 16
+struct InlineStore {
+  int n;
+  int pad[3];
+  uint32_t rec[kInlineMax * kInlineWords];
+};
+cudaError_t launch_train_cluster(cudaStream_t st, const TrainArgs& args, const InlineStore* ist /* or nullptr */);
 
 cudaError_t launch_act(cudaStream_t st, const float* params, const Dims& d, int agent_begin, int n_sel,
                        const float* states /* device [n_sel][D] */, int* actions_out /* device [n_sel] */,

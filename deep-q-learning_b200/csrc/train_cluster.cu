@@ -37,8 +37,8 @@ constexpr int XS = 2 * R + 4;     // 36: row stride of X [d][col], cols [0,16) =
 constexpr int HS = FR + 4;        // 52: row stride of H1 / H2 [unit][forward row]
 constexpr int RS = R + 4;         // 20: row stride of the k-major backward buffers
 constexpr int DRS = kH2 + 4;      // 68: row stride of Dh2R [row][unit]
-constexpr int HC = 8;
-constexpr int WS2 = kH2 + 4;      // 68
+constexpr int HC = kHeadCols;
+constexpr int WS2 = kW2Stride;    // 68
 constexpr int NPC = 4;            // slice parameters per thread: ceil(ceil(3308 / 4) / 256)
 
 struct CLay {
@@ -48,11 +48,11 @@ struct CLay {
 
 __host__ __device__ inline CLay make_clayout(int D, int recw) {
   CLay L;
-  L.pW2 = (D + 1) * kH1;
-  L.pWh = L.pW2 + (kH1 + 1) * WS2;
-  L.PS = L.pWh + (kH2 + 1) * HC;
+  L.pW2 = packed_w2(D);
+  L.pWh = packed_head(D);
+  L.PS = packed_count(D);          // the shared-memory weight layout IS the packed HBM layout (common.cuh)
   L.SL = (((L.PS + CS - 1) / CS) + 3) & ~3;
-  const int PSa = (L.PS + 3) & ~3;
+  const int PSa = L.PS;
   int o = 0;
   L.oW = o; o += PSa;
   L.oWt = o; o += PSa;
@@ -73,31 +73,15 @@ __host__ __device__ inline CLay make_clayout(int D, int recw) {
   return L;
 }
 
-__device__ __forceinline__ int csmem_to_flat(int p, int D, int A, const CLay& L) {
-  if (p < L.pW2) return p;
-  const int offWv = L.pW2 + (kH1 + 1) * kH2;
-  if (p < L.pWh) {
-    const int q = p - L.pW2;
-    const int row = q / WS2, col = q - row * WS2;
-    return col < kH2 ? L.pW2 + row * kH2 + col : -1;
-  }
-  const int q = p - L.pWh;
-  const int k = q >> 3, c = q & 7;
-  const int offbv = offWv + kH2, offWa = offbv + 1, offba = offWa + kH2 * A;
-  if (c > A) return -1;
-  if (k < kH2) return c == 0 ? offWv + k : offWa + k * A + (c - 1);
-  return c == 0 ? offbv : offba + (c - 1);
-}
-
 template <int A>
-__global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArgs args) {
+__global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArgs args, const InlineStore ist) {
   extern __shared__ __align__(16) float sm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int sel = blockIdx.x / CS;
   const int agent = args.agent_begin + sel;
-  const int D = args.dims.D, recw = args.dims.recw, PF = args.dims.PF;
+  const int D = args.dims.D, recw = args.dims.recw, PK = args.dims.PK;
   const CLay L = make_clayout(D, recw);
 
   float* const W = sm + L.oW;
@@ -115,29 +99,26 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   float* const Red = sm + L.oRed;     // [0..3] loss partial per rank (valid in rank 0), [8..11] Adam bias corrections, [16..31] head-bias partials
   float* const Stage = sm + L.oStage;
 
-  float* const gW = args.params + (size_t)agent * 4 * PF;
-  float* const gWt = gW + PF;
-  float* const gM = gW + 2 * PF;
-  float* const gV = gW + 3 * PF;
+  float* const gW = args.params + (size_t)agent * 4 * PK;
+  float* const gWt = gW + PK;
+  float* const gM = gW + 2 * PK;
+  float* const gV = gW + 3 * PK;
   AgentCtl* const ctl = args.ctl + agent;
-  const uint32_t* const ring = args.rings + (size_t)agent * args.dims.N * recw;
+  uint32_t* const ring = args.rings + (size_t)agent * args.dims.N * recw;
 
   // ---- one-time: full theta / theta^- replicas into smem; mu / nu of this CTA's slice into registers ----
-  for (int p = t; p < L.PS; p += NT) {
-    const int f = csmem_to_flat(p, D, A, L);
-    W[p] = f >= 0 ? gW[f] : 0.f;
-    Wt[p] = f >= 0 ? gWt[f] : 0.f;
-    G[p] = 0.f;
+  for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) {   // straight 16-byte copies of the packed layout
+    const float4 w = reinterpret_cast<const float4*>(gW)[p4], wt = reinterpret_cast<const float4*>(gWt)[p4];
+    st4(W + 4 * p4, w.x, w.y, w.z, w.w);
+    st4(Wt + 4 * p4, wt.x, wt.y, wt.z, wt.w);
+    st4(G + 4 * p4, 0.f, 0.f, 0.f, 0.f);
   }
   float mreg[NPC], vreg[NPC];
 #pragma unroll
   for (int i = 0; i < NPC; ++i) {
     const int q = t + i * NT, p = rank * L.SL + q;
     mreg[i] = 0.f; vreg[i] = 0.f;
-    if (q < L.SL && p < L.PS) {
-      const int f = csmem_to_flat(p, D, A, L);
-      if (f >= 0) { mreg[i] = gM[f]; vreg[i] = gV[f]; }
-    }
+    if (q < L.SL && p < L.PS) { mreg[i] = gM[p]; vreg[i] = gV[p]; }     // padding entries are 0 and stay 0
   }
   for (int r = t; r < XS; r += NT) X[D * XS + r] = 1.f;
   for (int r = t; r < HS; r += NT) H2[kH2 * HS + r] = 1.f;
@@ -147,7 +128,17 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   const int B = ctl->batch_size;
   const long long step0 = ctl->train_steps;
   const int count0 = ctl->adam_count;
-  const long long rc = ctl->ring_counter;
+  // ReplayBuffer.add x ist.n (replay_buffer.py:58-65) for transitions that arrived in the parameter buffer: rank 0
+  // writes them to the ring; the cluster barrier below orders the writes before every CTA's first gather
+  const long long rc0 = ctl->ring_counter;
+  if (ist.n > 0 && rank == 0) {
+    for (int w = t; w < ist.n * recw; w += NT) {
+      const int i = w / recw, c = w - i * recw;
+      ring[(size_t)((rc0 + i) % args.dims.N) * recw + c] = ist.rec[w];
+    }
+    __threadfence();
+  }
+  const long long rc = rc0 + ist.n;
   const long long size = rc < args.dims.N ? rc : args.dims.N;
   const int ntiles = (B + BT - 1) / BT;
   const float fB = (float)B;
@@ -196,8 +187,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   double pb1 = 1.0, pb2 = 1.0;
   if (t == 0) { pb1 = pow((double)b1, (double)count0); pb2 = pow((double)b2, (double)count0); }
 
-  prefetch(0, 0);
+  if (ist.n == 0) prefetch(0, 0);
   cluster.sync();       // every CTA's smem is initialised before anyone writes into it remotely
+  if (ist.n > 0) prefetch(0, 0);      // ... and the inline-stored records are visible
 
   for (int kstep = 0; kstep < args.K; ++kstep) {
     if (t == 0) {
@@ -439,7 +431,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         const int q = t + i * NT, p = rank * L.SL + q;
         if (q < L.SL && p < L.PS) {
           const float g = ((Gr[0][p] + Gr[1][p]) + Gr[2][p]) + Gr[3][p];
-          if (args.taps.enabled && args.taps.grads) { const int f = csmem_to_flat(p, D, A, L); if (f >= 0) args.taps.grads[f] = g; }
+          if (args.taps.enabled && args.taps.grads) args.taps.grads[p] = g;
           const float m = b1 * mreg[i] + omb1 * g;
           const float v = b2 * vreg[i] + omb2 * (g * g);
           mreg[i] = m; vreg[i] = v;
@@ -454,7 +446,8 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     if (rank == 0 && t == 0) {
       const float loss = (((Red[0] + Red[1]) + Red[2]) + Red[3]) / fB;
       args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
-      if (kstep == args.K - 1) args.loss_mailbox[agent] = loss;
+      if (kstep == args.K - 1)
+        args.loss_mailbox[agent] = ((unsigned long long)(uint32_t)(step0 + args.K) << 32) | __float_as_uint(loss);
       if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
     }
     cluster.sync();                          // every replica holds theta_{t+1}; nobody reads the old partial gradients any more
@@ -465,20 +458,18 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
 #pragma unroll
   for (int i = 0; i < NPC; ++i) {
     const int q = t + i * NT, p = rank * L.SL + q;
-    if (q < L.SL && p < L.PS) {
-      const int f = csmem_to_flat(p, D, A, L);
-      if (f >= 0) { gW[f] = W[p]; gM[f] = mreg[i]; gV[f] = vreg[i]; }
-    }
+    if (q < L.SL && p < L.PS) { gW[p] = W[p]; gM[p] = mreg[i]; gV[p] = vreg[i]; }
   }
   if (rank == 0 && t == 0) {
     ctl->train_steps = step0 + args.K;
+    if (ist.n > 0) ctl->ring_counter = rc;
     const long long c = (long long)count0 + args.K;
     ctl->adam_count = c > 0x7fffffffLL ? 0x7fffffff : (int)c;
   }
   cluster.sync();   // no CTA may exit while its shared memory can still be addressed remotely
 }
 
-typedef void (*ClusterKernel)(const TrainArgs);
+typedef void (*ClusterKernel)(const TrainArgs, const InlineStore);
 ClusterKernel pick_cluster_kernel(int A) {
   switch (A) {
     case 2: return dqn_train_cluster_kernel<2>;
@@ -501,7 +492,8 @@ cudaError_t train_cluster_prepare(const Dims& d) {
   return cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_cluster_smem_bytes(d));
 }
 
-cudaError_t launch_train_cluster(cudaStream_t st, const TrainArgs& args) {
+cudaError_t launch_train_cluster(cudaStream_t st, const TrainArgs& args, const InlineStore* ist) {
+  static const InlineStore none = {};
   ClusterKernel k = pick_cluster_kernel(args.dims.A);
   if (!k) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg = {};
@@ -516,7 +508,7 @@ cudaError_t launch_train_cluster(cudaStream_t st, const TrainArgs& args) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k, args);
+  return cudaLaunchKernelEx(&cfg, k, args, ist ? *ist : none);
 }
 
 }  // namespace dqn

@@ -36,8 +36,8 @@ constexpr int NT = 256;          // threads per CTA
 constexpr int BT = 64;           // batch rows per tile
 constexpr int RS2 = 2 * BT + 4;  // 132
 constexpr int RS1 = BT + 4;      // 68
-constexpr int HC = 8;            // padded head width
-constexpr int WS2 = kH2 + 4;     // row stride of the [W2;b2] block in smem (68: rows 4 banks apart)
+constexpr int HC = kHeadCols;    // padded head width
+constexpr int WS2 = kW2Stride;   // row stride of the [W2;b2] block (68: rows 4 banks apart)
 constexpr int NPT = 13;
           // ceil(max smem-layout params / NT), D = 16: (17*32 + 33*64 + 65*8) = 3176
 
@@ -48,10 +48,10 @@ struct Lay {   // offsets in floats
 
 __host__ __device__ inline Lay make_layout(int D, int recw) {
   Lay L;
-  L.pW2 = (D + 1) * kH1;
-  L.pWh = L.pW2 + (kH1 + 1) * WS2;
-  L.PS = L.pWh + (kH2 + 1) * HC;
-  const int PSa = (L.PS + 3) & ~3;
+  L.pW2 = packed_w2(D);
+  L.pWh = packed_head(D);
+  L.PS = packed_count(D);          // the shared-memory weight layout IS the packed HBM layout (common.cuh)
+  const int PSa = L.PS;
   int o = 0;
   L.oW = o; o += PSa;
   L.oWt = o; o += PSa;
@@ -73,25 +73,6 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
   return L;
 }
 
-// smem-layout index -> flat-layout index (-1 = padding)
-__device__ __forceinline__ int smem_to_flat(int p, int D, int A, const Lay& L) {
-  if (p < L.pW2) return p;   // [W1;b1] is contiguous in both layouts
-  const int offWv = L.pW2 + (kH1 + 1) * kH2;   // flat offset of Wv = D*32+32+32*64+64
-  if (p < L.pWh) {           // [W2;b2]: smem rows are padded to WS2
-    const int q = p - L.pW2;
-    const int row = q / WS2, col = q - row * WS2;
-    return col < kH2 ? L.pW2 + row * kH2 + col : -1;
-  }
-  const int q = p - L.pWh;
-  const int k = q >> 3, c = q & 7;
-  const int offbv = offWv + kH2;
-  const int offWa = offbv + 1;
-  const int offba = offWa + kH2 * A;
-  if (c > A) return -1;
-  if (k < kH2) return c == 0 ? offWv + k : offWa + k * A + (c - 1);
-  return c == 0 ? offbv : offba + (c - 1);
-}
-
 template <int A>
 __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs args) {
   extern __shared__ __align__(16) float sm[];
@@ -104,7 +85,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   const int agent = args.agent_begin + sel;
   const int D = args.dims.D;
   const int recw = args.dims.recw;
-  const int PF = args.dims.PF;
+  const int PK = args.dims.PK;
   const Lay L = make_layout(D, recw);
 
   float* const W = sm + L.oW;       // theta      (smem layout)
@@ -123,10 +104,10 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   float* const Red = sm + L.oRed;   // [0..1] loss partials, [8..11] Adam bias corrections, [16..31] head-bias partials
   float* const Stage = sm + L.oStage;
 
-  float* const gW = args.params + (size_t)agent * 4 * PF;
-  float* const gWt = gW + PF;
-  float* const gM = gW + 2 * PF;
-  float* const gV = gW + 3 * PF;
+  float* const gW = args.params + (size_t)agent * 4 * PK;
+  float* const gWt = gW + PK;
+  float* const gM = gW + 2 * PK;
+  float* const gV = gW + 3 * PK;
   AgentCtl* const ctl = args.ctl + agent;
   const uint32_t* const ring = args.rings + (size_t)agent * args.dims.N * recw;
 
@@ -136,13 +117,13 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   for (int i = 0; i < NPT; ++i) {
     const int p = t + i * NT;
     mreg[i] = 0.f; vreg[i] = 0.f;
-    if (p < L.PS) {
-      const int f = smem_to_flat(p, D, A, L);
-      W[p] = f >= 0 ? gW[f] : 0.f;
-      Wt[p] = f >= 0 ? gWt[f] : 0.f;
-      G[p] = 0.f;
-      if (f >= 0) { mreg[i] = gM[f]; vreg[i] = gV[f]; }
-    }
+    if (p < L.PS) { mreg[i] = gM[p]; vreg[i] = gV[p]; }      // padding entries are 0 and stay 0 (zero gradient)
+  }
+  for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) {   // theta | theta^- : straight 16-byte copies of the packed layout
+    const float4 w = reinterpret_cast<const float4*>(gW)[p4], wt = reinterpret_cast<const float4*>(gWt)[p4];
+    st4(W + 4 * p4, w.x, w.y, w.z, w.w);
+    st4(Wt + 4 * p4, wt.x, wt.y, wt.z, wt.w);
+    st4(G + 4 * p4, 0.f, 0.f, 0.f, 0.f);
   }
   for (int r = t; r < RS2; r += NT) { X[D * RS2 + r] = 1.f; H2[kH2 * RS2 + r] = 1.f; }
 
@@ -532,7 +513,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
     __syncthreads();
 
     if (args.taps.enabled && args.taps.grads) {
-      for (int p = t; p < L.PS; p += NT) { const int f = smem_to_flat(p, D, A, L); if (f >= 0) args.taps.grads[f] = G[p]; }
+      for (int p = t; p < L.PS; p += NT) args.taps.grads[p] = G[p];
     }
     // ================= optimiser: optax adam / adamw (q_learning_functions.py:24-25) ==========
     // mu/nu are updated in full precision; the bias-corrected quotient uses the SFU reciprocal / sqrt
@@ -559,7 +540,8 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
     if (t == 0) {
       const float loss = (Red[0] + Red[1]) / fB;
       args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
-      if (kstep == args.K - 1) args.loss_mailbox[agent] = loss;   // host-visible without a D2H copy
+      if (kstep == args.K - 1)   // host-visible without a D2H copy; the step count makes it pollable
+        args.loss_mailbox[agent] = ((unsigned long long)(uint32_t)(step0 + args.K) << 32) | __float_as_uint(loss);
       if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
     }
     // next step's first barrier (top of tile loop) orders W/G/Red before reuse
@@ -570,10 +552,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     const int p = t + i * NT;
-    if (p < L.PS) {
-      const int f = smem_to_flat(p, D, A, L);
-      if (f >= 0) { gW[f] = W[p]; gM[f] = mreg[i]; gV[f] = vreg[i]; }
-    }
+    if (p < L.PS) { gW[p] = W[p]; gM[p] = mreg[i]; gV[p] = vreg[i]; }
   }
   if (t == 0) {
     ctl->train_steps = step0 + args.K;

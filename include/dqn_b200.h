@@ -165,6 +165,14 @@ DQN_API int dqn_sample_batch_device(dqn_handle* h, int32_t agent, const int64_t*
  * (unless taps are requested). */
 DQN_API int dqn_train_step(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K,
                    const int64_t* idx, dqn_debug_taps* taps);
+/* The reference's inner loop between two train steps (q_agent.py:182-187) as ONE launch: n ReplayBuffer.add calls
+ * (host arrays as in dqn_store) followed by K Agent._step()s of `agent`.  For n <= DQN_MAX_INLINE_STORE with the
+ * cluster kernel the transitions travel in the kernel's parameter buffer (no H2D copy, no store launch); otherwise
+ * this is dqn_store + dqn_train_step.  `loss_out` (host, optional): wait for the launch -- polling the zero-copy
+ * loss mailbox, no stream synchronisation -- and return the loss of the last step. */
+#define DQN_MAX_INLINE_STORE 16
+DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a, const float* r,
+                                 const float* s2, const uint8_t* done, int32_t K, float* loss_out);
 /* Same, explicit indices already on the device (i64[n_sel*K*B]) -- no host copy, enqueue only. */
 DQN_API int dqn_train_step_device_idx(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K,
                               const int64_t* idx_dev);

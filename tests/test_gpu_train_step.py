@@ -150,6 +150,39 @@ def test_fused_k_steps_equal_k_single_launches_bitwise():
     assert np.array_equal(eng1.losses(37), eng2.losses(37))
 
 
+def test_store_and_train_in_one_launch_equals_store_then_train():
+    """dqn_store_train_step: n add()s + one _step() as ONE launch (transitions in the kernel-parameter buffer) ==
+    dqn_store followed by dqn_train_step, bit for bit -- ring contents (incl. wrap-around), parameters, losses."""
+    _lib = dqn_b200.pkg._lib
+    D, A, N, B = 9, 4, 50, 32
+    rng = np.random.default_rng(12)
+    theta = O.init_params(rng, D, A, bias_std=0.05)
+    engs = [dqn_b200.DqnEngine(D, A, N, B, 0.99, dqn_b200.adamw(1e-3), seed=77) for _ in range(2)]
+    ora = OracleAgent(theta, O.init_opt_state(theta), O.OptSpec("adamw", 1e-3), N, D, 0.99, B, seed=77)
+    for e in engs:
+        e.set_params(theta, 0, 0)
+        e.set_params(theta, 0, 1)
+    loss = np.zeros(1, np.float32)
+    for it, n in enumerate([3, 1, 16, 4, 4, 7, 16, 16, 2, 17, 4, 0, 5]):      # 17 > DQN_MAX_INLINE_STORE -> fallback path
+        s, a, r, s2, d = synthetic_transitions(rng, max(n, 1), D, A, done_p=0.2)
+        s, a, r, s2, d = s[:n], a[:n], r[:n], s2[:n], d[:n]
+        if n:
+            engs[0].store(s, a, r, s2, d)
+            ora.replay.add_many(s, a, r, s2, d)
+        engs[0].train_steps(1)
+        ora.step()
+        d8 = np.ascontiguousarray(d, dtype=np.bool_)
+        _lib.check(engs[1].lib.dqn_store_train_step(engs[1].h, 0, n, _lib.ptr(s), _lib.ptr(a), _lib.ptr(r), _lib.ptr(s2),
+                                                    _lib.ptr(d8), 1, _lib.ptr(loss)))
+        assert loss[0] == engs[0].last_loss(), f"iteration {it}"
+        assert engs[1].buffer_state() == engs[0].buffer_state()
+    assert np.array_equal(engs[0].get_params_flat(), engs[1].get_params_flat())
+    for x, y, z in zip(engs[0].buffer_export(), engs[1].buffer_export(),
+                       (ora.replay.states, ora.replay.actions, ora.replay.rewards, ora.replay.observations, ora.replay.dones)):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    compare_state(engs[1], ora, "store+train fused", rtol=2e-5)
+
+
 def test_greedy_actions_bit_exact():
     eng, ora, rng = make_pair(seed=9)
     states = rng.standard_normal((2000, 9)).astype(np.float32)
