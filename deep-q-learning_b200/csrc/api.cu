@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of include/dqn_b200.h: handle management, host<->device staging, launches.
 // No compute happens on the host; every entry point either moves bytes or launches a kernel.
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -243,6 +244,7 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   c.gamma = cfg->gamma; c.lr = cfg->lr; c.b1 = cfg->b1; c.b2 = cfg->b2; c.eps = cfg->eps;
   c.eps_root = cfg->eps_root; c.wd = cfg->opt_kind == DQN_OPT_ADAMW ? cfg->weight_decay : 0.f;
   c.batch_size = cfg->batch_size;
+  c.pb1 = 1.0; c.pb2 = 1.0;
   h->hctl.assign(cfg->n_agents, c);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(h->ctl, h->hctl.data(), sizeof(AgentCtl) * cfg->n_agents, cudaMemcpyHostToDevice, h->stream);
@@ -299,6 +301,17 @@ void unpack_flat(const dqn_handle* h, const float* packed, float* flat) {
 }
 }  // namespace
 
+namespace {
+// AgentCtl.pb1 / pb2 = b1**count, b2**count (optax's bias-correction powers), re-seeded from the host mirror
+int seed_decay_powers(dqn_handle* h, int agent) {
+  AgentCtl& c = h->hctl[agent];
+  c.pb1 = pow((double)c.b1, (double)c.adam_count);
+  c.pb2 = pow((double)c.b2, (double)c.adam_count);
+  CU(cudaMemcpyAsync(&h->ctl[agent].pb1, &c.pb1, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return DQN_OK;
+}
+}  // namespace
+
 DQN_API int dqn_set_params(dqn_handle* h, int32_t agent, int32_t which, const float* host_flat, int32_t n) {
   if (int rc = check_agent(h, agent)) return rc;
   if ((which != DQN_PARAMS_ONLINE && which != DQN_PARAMS_TARGET) || !host_flat || n != h->dims.P)
@@ -338,6 +351,7 @@ DQN_API int dqn_set_opt_state(dqn_handle* h, int32_t agent, int32_t count, const
   CU(cudaMemcpyAsync(base + 2 * PK, bounce_slot(h, 0), (size_t)2 * PK * 4, cudaMemcpyHostToDevice, h->stream));   // mu | nu are adjacent
   h->hctl[agent].adam_count = count;
   CU(cudaMemcpyAsync(&h->ctl[agent].adam_count, &h->hctl[agent].adam_count, 4, cudaMemcpyHostToDevice, h->stream));
+  if (int rc = seed_decay_powers(h, agent)) return rc;
   CU(cudaStreamSynchronize(h->stream));
   return DQN_OK;
 }
@@ -375,6 +389,7 @@ DQN_API int dqn_set_hparams(dqn_handle* h, int32_t agent, const dqn_hparams* hp)
   // only the hyper-parameter prefix: the counters behind it are owned by the device
   memcpy(h->bounce, &c, offsetof(AgentCtl, adam_count));
   CU(cudaMemcpyAsync(&h->ctl[agent], h->bounce, offsetof(AgentCtl, adam_count), cudaMemcpyHostToDevice, h->stream));
+  if (int rc = seed_decay_powers(h, agent)) return rc;
   CU(cudaStreamSynchronize(h->stream));
   return DQN_OK;
 }

@@ -31,6 +31,8 @@ struct AgentCtl {
   int pad0;
   long long ring_counter;  // ReplayBuffer._counter (total adds)
   long long train_steps;   // number of _step() calls so far == Philox step counter
+  double pb1, pb2;         // b1**adam_count, b2**adam_count carried in double (one DMUL per step instead of a pow() per
+                           //   launch); the host re-seeds them whenever it sets the count or the decay rates
 };
 
 struct Dims {

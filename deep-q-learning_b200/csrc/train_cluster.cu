@@ -39,7 +39,7 @@ constexpr int RS = R + 4;         // 20: row stride of the k-major backward buff
 constexpr int DRS = kH2 + 4;      // 68: row stride of Dh2R [row][unit]
 constexpr int HC = kHeadCols;
 constexpr int WS2 = kW2Stride;    // 68
-constexpr int NPC = 4;            // slice parameters per thread: ceil(ceil(3308 / 4) / 256)
+constexpr int NPC = 4;            // slice parameters per thread: one 16-byte chunk (slice <= 828 floats = 207 chunks <= 256 threads)
 
 struct CLay {
   int pW2, pWh, PS, SL;
@@ -73,6 +73,13 @@ __host__ __device__ inline CLay make_clayout(int D, int recw) {
   return L;
 }
 
+#ifdef DQN_PHASE_CLOCKS   // profiling variant only (profiles/phase_clocks.py): SM-cycle stamps of rank 0, thread 0
+__device__ long long g_phase_clock[16];
+#define PHASE_CLOCK(i) do { if (rank == 0 && t == 0) g_phase_clock[i] = clock64(); } while (0)
+#else
+#define PHASE_CLOCK(i) do { } while (0)
+#endif
+
 template <int A>
 __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArgs args, const InlineStore ist) {
   extern __shared__ __align__(16) float sm[];
@@ -83,6 +90,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   const int agent = args.agent_begin + sel;
   const int D = args.dims.D, recw = args.dims.recw, PK = args.dims.PK;
   const CLay L = make_clayout(D, recw);
+  PHASE_CLOCK(0);
 
   float* const W = sm + L.oW;
   float* const Wt = sm + L.oWt;
@@ -113,12 +121,14 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     st4(Wt + 4 * p4, wt.x, wt.y, wt.z, wt.w);
     st4(G + 4 * p4, 0.f, 0.f, 0.f, 0.f);
   }
-  float mreg[NPC], vreg[NPC];
-#pragma unroll
-  for (int i = 0; i < NPC; ++i) {
-    const int q = t + i * NT, p = rank * L.SL + q;
-    mreg[i] = 0.f; vreg[i] = 0.f;
-    if (q < L.SL && p < L.PS) { mreg[i] = gM[p]; vreg[i] = gV[p]; }     // padding entries are 0 and stay 0
+  // Adam ownership: thread t owns the 16-byte chunk [rank * SL + 4 t, +4) of the packed parameters (mu / nu in registers)
+  const int pown = rank * L.SL + 4 * t;
+  const bool owner = 4 * t < L.SL && pown < L.PS;
+  float mreg[NPC] = {0.f, 0.f, 0.f, 0.f}, vreg[NPC] = {0.f, 0.f, 0.f, 0.f};
+  if (owner) {
+    const float4 m4 = *reinterpret_cast<const float4*>(gM + pown), v4 = *reinterpret_cast<const float4*>(gV + pown);
+    mreg[0] = m4.x; mreg[1] = m4.y; mreg[2] = m4.z; mreg[3] = m4.w;
+    vreg[0] = v4.x; vreg[1] = v4.y; vreg[2] = v4.z; vreg[3] = v4.w;
   }
   for (int r = t; r < XS; r += NT) X[D * XS + r] = 1.f;
   for (int r = t; r < HS; r += NT) H2[kH2 * HS + r] = 1.f;
@@ -184,12 +194,13 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     cp_async_commit();
   };
 
-  double pb1 = 1.0, pb2 = 1.0;
-  if (t == 0) { pb1 = pow((double)b1, (double)count0); pb2 = pow((double)b2, (double)count0); }
+  double pb1 = ctl->pb1, pb2 = ctl->pb2;    // b1**count, b2**count carried across launches (thread 0 uses them)
 
+  PHASE_CLOCK(1);
   if (ist.n == 0) prefetch(0, 0);
   cluster.sync();       // every CTA's smem is initialised before anyone writes into it remotely
   if (ist.n > 0) prefetch(0, 0);      // ... and the inline-stored records are visible
+  PHASE_CLOCK(2);
 
   for (int kstep = 0; kstep < args.K; ++kstep) {
     if (t == 0) {
@@ -203,6 +214,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       // ---- unpack ----
       cp_async_wait_all();
       __syncthreads();
+      if (kstep == 0 && tile == 0) PHASE_CLOCK(3);
       if (t < 4 * R) {
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
@@ -418,30 +430,33 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       }
     }  // tiles
 
+    if (kstep == args.K - 1) PHASE_CLOCK(4);
     if (t == 0) Red0[rank] = loss_acc;       // this CTA's share of the loss -> rank 0
-    cluster.sync();                          // all partial gradients (and loss shares) are complete and visible
+    cluster.sync();
+    if (kstep == args.K - 1) PHASE_CLOCK(5);                          // all partial gradients (and loss shares) are complete and visible
 
-    // ---- reduce-scatter + Adam on this CTA's slice + all-gather of the new weights (DSMEM) ----
-    {
+    // ---- reduce-scatter + Adam on this CTA's slice + all-gather of the new weights (DSMEM, 16-byte accesses) ----
+    if (owner) {
       const float c1 = Red[8 + 2 * (kstep & 1)], c2 = Red[9 + 2 * (kstep & 1)];
       const float rc1 = 1.0f / c1, rc2 = 1.0f / c2;
       const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+      const float4 g0 = ld4(Gr[0] + pown), g1 = ld4(Gr[1] + pown), g2 = ld4(Gr[2] + pown), g3 = ld4(Gr[3] + pown);
+      const float4 th4 = ld4(W + pown);
+      const float g[4] = {((g0.x + g1.x) + g2.x) + g3.x, ((g0.y + g1.y) + g2.y) + g3.y,      // fixed rank order: deterministic
+                          ((g0.z + g1.z) + g2.z) + g3.z, ((g0.w + g1.w) + g2.w) + g3.w};
+      const float th[4] = {th4.x, th4.y, th4.z, th4.w};
+      float nw[4];
 #pragma unroll
       for (int i = 0; i < NPC; ++i) {
-        const int q = t + i * NT, p = rank * L.SL + q;
-        if (q < L.SL && p < L.PS) {
-          const float g = ((Gr[0][p] + Gr[1][p]) + Gr[2][p]) + Gr[3][p];
-          if (args.taps.enabled && args.taps.grads) args.taps.grads[p] = g;
-          const float m = b1 * mreg[i] + omb1 * g;
-          const float v = b2 * vreg[i] + omb2 * (g * g);
-          mreg[i] = m; vreg[i] = v;
-          const float u = (m * rc1) * fast_rcp(fast_sqrt(v * rc2 + eps_root) + eps);
-          const float th = W[p];
-          const float nw = th - lr * (u + wd * th);
-#pragma unroll
-          for (int c = 0; c < CS; ++c) Wr[c][p] = nw;
-        }
+        const float m = b1 * mreg[i] + omb1 * g[i];
+        const float v = b2 * vreg[i] + omb2 * (g[i] * g[i]);
+        mreg[i] = m; vreg[i] = v;
+        const float u = (m * rc1) * fast_rcp(fast_sqrt(v * rc2 + eps_root) + eps);
+        nw[i] = th[i] - lr * (u + wd * th[i]);
       }
+#pragma unroll
+      for (int c = 0; c < CS; ++c) st4(Wr[c] + pown, nw[0], nw[1], nw[2], nw[3]);
+      if (args.taps.enabled && args.taps.grads) st4(args.taps.grads + pown, g[0], g[1], g[2], g[3]);
     }
     if (rank == 0 && t == 0) {
       const float loss = (((Red[0] + Red[1]) + Red[2]) + Red[3]) / fB;
@@ -451,22 +466,25 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
     }
     cluster.sync();                          // every replica holds theta_{t+1}; nobody reads the old partial gradients any more
-    for (int p = t; p < L.PS; p += NT) G[p] = 0.f;
+    if (kstep + 1 < args.K)
+      for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) st4(G + 4 * p4, 0.f, 0.f, 0.f, 0.f);
   }  // steps
+  PHASE_CLOCK(6);
 
-  // ---- write back this CTA's slice ----
-#pragma unroll
-  for (int i = 0; i < NPC; ++i) {
-    const int q = t + i * NT, p = rank * L.SL + q;
-    if (q < L.SL && p < L.PS) { gW[p] = W[p]; gM[p] = mreg[i]; gV[p] = vreg[i]; }
+  // ---- write back this CTA's slice (the last cluster barrier above was the last DSMEM access: CTAs may exit freely) ----
+  if (owner) {
+    *reinterpret_cast<float4*>(gW + pown) = ld4(W + pown);
+    *reinterpret_cast<float4*>(gM + pown) = make_float4(mreg[0], mreg[1], mreg[2], mreg[3]);
+    *reinterpret_cast<float4*>(gV + pown) = make_float4(vreg[0], vreg[1], vreg[2], vreg[3]);
   }
   if (rank == 0 && t == 0) {
     ctl->train_steps = step0 + args.K;
     if (ist.n > 0) ctl->ring_counter = rc;
     const long long c = (long long)count0 + args.K;
     ctl->adam_count = c > 0x7fffffffLL ? 0x7fffffff : (int)c;
+    ctl->pb1 = pb1; ctl->pb2 = pb2;
   }
-  cluster.sync();   // no CTA may exit while its shared memory can still be addressed remotely
+  PHASE_CLOCK(7);
 }
 
 typedef void (*ClusterKernel)(const TrainArgs, const InlineStore);
@@ -483,6 +501,12 @@ ClusterKernel pick_cluster_kernel(int A) {
 }
 
 }  // namespace
+
+#ifdef DQN_PHASE_CLOCKS
+extern "C" __attribute__((visibility("default"))) int dqn_debug_phase_clocks(long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, g_phase_clock, sizeof(long long) * 16);
+}
+#endif
 
 size_t train_cluster_smem_bytes(const Dims& d) { return (size_t)make_clayout(d.D, d.recw).total * sizeof(float); }
 

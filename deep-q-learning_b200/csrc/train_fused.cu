@@ -169,8 +169,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
     cp_async_commit();
   };
 
-  double pb1 = 1.0, pb2 = 1.0;   // b1**count, b2**count (thread 0 only)
-  if (t == 0) { pb1 = pow((double)b1, (double)count0); pb2 = pow((double)b2, (double)count0); }
+  double pb1 = ctl->pb1, pb2 = ctl->pb2;   // b1**count, b2**count carried across launches (thread 0 uses them)
 
   prefetch(0, 0);
 
@@ -558,6 +557,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
     ctl->train_steps = step0 + args.K;
     const long long c = (long long)count0 + args.K;
     ctl->adam_count = c > 0x7fffffffLL ? 0x7fffffff : (int)c;
+    ctl->pb1 = pb1; ctl->pb2 = pb2;
   }
 }
 
