@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   float* const DhdT = sm + L.oDhdT;   // [8 c][20]
   float* const Scr = sm + L.oScr;     // [4 parts][8 c][48 forward rows]
   float* const Meta = sm + L.oMeta;   // [16][4]
-  float* const Red = sm + L.oRed;     // [0..3] loss partial per rank (valid in rank 0), [8..11] Adam bias corrections, [16..31] head-bias partials
+  float* const Red = sm + L.oRed;     // [0] this CTA's loss share, [8..11] Adam bias corrections, [16..31] head-bias partials
   float* const Stage = sm + L.oStage;
 
   float* const gW = args.params + (size_t)agent * 4 * PK;
@@ -115,10 +115,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   uint32_t* const ring = args.rings + (size_t)agent * args.dims.N * recw;
 
   // ---- one-time: full theta / theta^- replicas into smem; mu / nu of this CTA's slice into registers ----
-  for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) {   // straight 16-byte copies of the packed layout
-    const float4 w = reinterpret_cast<const float4*>(gW)[p4], wt = reinterpret_cast<const float4*>(gWt)[p4];
-    st4(W + 4 * p4, w.x, w.y, w.z, w.w);
-    st4(Wt + 4 * p4, wt.x, wt.y, wt.z, wt.w);
+  for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) {   // packed layout: asynchronous 16-byte copies, awaited with the first gather
+    cp_async16(W + 4 * p4, gW + 4 * p4);
+    cp_async16(Wt + 4 * p4, gWt + 4 * p4);
     st4(G + 4 * p4, 0.f, 0.f, 0.f, 0.f);
   }
   // Adam ownership: thread t owns the 16-byte chunk [rank * SL + 4 t, +4) of the packed parameters (mu / nu in registers)
@@ -138,15 +137,17 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   const int B = ctl->batch_size;
   const long long step0 = ctl->train_steps;
   const int count0 = ctl->adam_count;
-  // ReplayBuffer.add x ist.n (replay_buffer.py:58-65) for transitions that arrived in the parameter buffer: rank 0
-  // writes them to the ring; the cluster barrier below orders the writes before every CTA's first gather
+  // ReplayBuffer.add x ist.n (replay_buffer.py:58-65) for transitions that arrived in the parameter buffer.  Every
+  // CTA of the cluster writes the same few hundred bytes (identical values, so the race is benign): its own gather
+  // below is then ordered behind its own writes by a fence + CTA barrier, without a cluster barrier.
   const long long rc0 = ctl->ring_counter;
-  if (ist.n > 0 && rank == 0) {
+  if (ist.n > 0) {
     for (int w = t; w < ist.n * recw; w += NT) {
       const int i = w / recw, c = w - i * recw;
       ring[(size_t)((rc0 + i) % args.dims.N) * recw + c] = ist.rec[w];
     }
     __threadfence();
+    __syncthreads();
   }
   const long long rc = rc0 + ist.n;
   const long long size = rc < args.dims.N ? rc : args.dims.N;
@@ -159,7 +160,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   const float* Gr[CS];
 #pragma unroll
   for (int c = 0; c < CS; ++c) { Wr[c] = cluster.map_shared_rank(W, c); Gr[c] = cluster.map_shared_rank(G, c); }
-  float* const Red0 = cluster.map_shared_rank(Red, 0);
+  const float* Redr[CS];
+#pragma unroll
+  for (int c = 0; c < CS; ++c) Redr[c] = cluster.map_shared_rank(Red, c);
 
   // staged-record word -> smem destination (threads 0..63: 4 lanes per row)
   const int urow = t >> 2, ul4 = t & 3;
@@ -197,9 +200,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   double pb1 = ctl->pb1, pb2 = ctl->pb2;    // b1**count, b2**count carried across launches (thread 0 uses them)
 
   PHASE_CLOCK(1);
-  if (ist.n == 0) prefetch(0, 0);
-  cluster.sync();       // every CTA's smem is initialised before anyone writes into it remotely
-  if (ist.n > 0) prefetch(0, 0);      // ... and the inline-stored records are visible
+  prefetch(0, 0);
+  // (no cluster barrier here: the first remote access comes after the first step's cluster barrier, which every CTA
+  //  reaches only after its own shared memory is initialised)
   PHASE_CLOCK(2);
 
   for (int kstep = 0; kstep < args.K; ++kstep) {
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     }  // tiles
 
     if (kstep == args.K - 1) PHASE_CLOCK(4);
-    if (t == 0) Red0[rank] = loss_acc;       // this CTA's share of the loss -> rank 0
+    if (t == 0) Red[0] = loss_acc;           // this CTA's share of the loss; rank 0 pulls the four shares after the barrier
     cluster.sync();
     if (kstep == args.K - 1) PHASE_CLOCK(5);                          // all partial gradients (and loss shares) are complete and visible
 
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       if (args.taps.enabled && args.taps.grads) st4(args.taps.grads + pown, g[0], g[1], g[2], g[3]);
     }
     if (rank == 0 && t == 0) {
-      const float loss = (((Red[0] + Red[1]) + Red[2]) + Red[3]) / fB;
+      const float loss = (((Redr[0][0] + Redr[1][0]) + Redr[2][0]) + Redr[3][0]) / fB;
       args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
       if (kstep == args.K - 1)
         args.loss_mailbox[agent] = ((unsigned long long)(uint32_t)(step0 + args.K) << 32) | __float_as_uint(loss);
