@@ -475,7 +475,7 @@ def run_dp(args):
     torch.cuda.set_device(device)
     Bg, H, ring = args.batch, (args.hidden, args.hidden), 1_000_000
     tr = dqn_b200.LargeBatchTrainer(D, A, H, Bg, ring, GAMMA, dqn_b200.adamw(LR), rank=rank, world_size=world, seed=3,
-                                    device=local, gemm_mode=args.gemm)
+                                    device=local, gemm_mode=args.gemm, collective=args.collective)
     params = dqn_b200.Model(A, hidden=H).init(np.random.default_rng(0), np.zeros((1, D), np.float32)) if False else None
     rng = np.random.default_rng(0)
     tree = {}
@@ -524,7 +524,9 @@ def run_dp(args):
             "warmup": max(args.warmup, 3), "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else "f32 via 3xTF32 tensor-core split", "data": "synthetic",
             "config": {"workload": "configs[3]: large-batch data-parallel DDQN, global batch %d, hidden %dx%d" % (Bg, H[0], H[1]),
-                       "obs_dim": D, "num_actions": A, "batch_local": Bg // world, "gemm": args.gemm, "collective": "NCCL all-reduce of %d floats" % (tr.P + 1),
+                       "obs_dim": D, "num_actions": A, "batch_local": Bg // world, "gemm": args.gemm,
+                       "collective": {"p2p": "own kernel over NVLink peer memory (csrc/comm_p2p.cu), %d floats", "nccl": "NCCL all-reduce of %d floats",
+                                      "none": "none (1 GPU), %d floats"}[tr.collective] % (tr.P + 1),
                        "l2": "activations %.1f GB per rank >> L2" % (3 * 2 * (Bg // world) * H[0] * 4 / 1e9)},
             "clocks": clk.summary(), "gpu_launches": None, "replay_samples_per_sec": Bg * args.steps / secs_max, "loss": loss,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
@@ -594,6 +596,8 @@ def main():
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tc3xtf32"])
     ap.add_argument("--agents", type=int, default=1024)
     ap.add_argument("--steps-per-launch", type=int, default=16)
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="dp workload: gradient all-reduce by the library's own peer-memory kernel (p2p) or by NCCL")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "cta", "cluster"],
                     help="train-step kernel of the single/population workloads: one CTA per agent, or one agent over a 4-CTA cluster "
                          "(auto = cluster while 4 * agents <= SMs)")
@@ -608,7 +612,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
                "--workload", args.workload, "--agents", str(args.agents), "--steps-per-launch", str(args.steps_per_launch),
-               "--batch", str(args.batch), "--hidden", str(args.hidden), "--gemm", args.gemm, "--step-kernel", args.step_kernel]
+               "--batch", str(args.batch), "--hidden", str(args.hidden), "--gemm", args.gemm, "--step-kernel", args.step_kernel,
+               "--collective", args.collective]
         sys.exit(subprocess.call(cmd))
     if args.workload == "population":
         return run_population(args)

@@ -106,6 +106,9 @@ PROTOTYPES = {
     "dqn_lb_buffer_state": (C.c_int, [_H, C.POINTER(_i64), C.POINTER(_i64)]),
     "dqn_lb_forward_backward": (C.c_int, [_H, _P, _i32]),
     "dqn_lb_grads": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(_i64)]),
+    "dqn_lb_comm_init": (C.c_int, [_H, _P, C.POINTER(C.c_void_p)]),
+    "dqn_lb_comm_connect": (C.c_int, [_H, _P, C.POINTER(C.c_void_p)]),
+    "dqn_lb_allreduce": (C.c_int, [_H]),
     "dqn_lb_apply": (C.c_int, [_H]),
     "dqn_lb_sync_target": (C.c_int, [_H]),
     "dqn_lb_get_loss": (C.c_int, [_H, C.POINTER(C.c_float)]),

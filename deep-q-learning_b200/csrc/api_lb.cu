@@ -106,6 +106,12 @@ struct dqn_lb_handle {
   long long train_steps;
   int adam_count;
   float* pinned;
+  // peer-memory all-reduce (dqn_lb_comm_*): the gradient lives in `window` instead of the arena once initialised
+  float* window;
+  CommPeers peers;
+  void* opened[kMaxWorld];     // cudaIpcOpenMemHandle results to close
+  bool connected;
+  unsigned epoch;
 };
 
 namespace {
@@ -161,6 +167,8 @@ DQN_API int dqn_lb_create(const dqn_lb_config* cfg, dqn_lb_handle** out) {
   h->taps.targets = (float*)(a + c.targets); h->taps.max_actions = (int*)(a + c.maxa); h->taps.enabled = 0;
   h->stage = a + c.stage;
   h->ring_counter = 0; h->train_steps = 0; h->adam_count = 0; h->pinned = nullptr;
+  h->window = nullptr; h->connected = false; h->epoch = 0;
+  memset(&h->peers, 0, sizeof h->peers); memset(h->opened, 0, sizeof h->opened);
   cudaError_t e = cudaMallocHost((void**)&h->pinned, 4096);
   if (e == cudaSuccess) e = cudaMemsetAsync(a, 0, c.s, h->stream);          // params, moments, grads, ctl, ring
   if (e == cudaSuccess) e = cudaMemsetAsync(a + c.dhd, 0, (size_t)d.B * 32, h->stream);
@@ -180,6 +188,8 @@ DQN_API int dqn_lb_destroy(dqn_lb_handle* h) {
   if (!h) return DQN_OK;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
+  for (int q = 0; q < kMaxWorld; ++q) if (h->opened[q]) cudaIpcCloseMemHandle(h->opened[q]);
+  if (h->window) cudaFree(h->window);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->own_arena) cudaFree(h->arena);
   delete h;
@@ -304,6 +314,67 @@ DQN_API int dqn_lb_grads(dqn_lb_handle* h, void** dev_ptr_out, int64_t* count_ou
   return DQN_OK;
 }
 
+DQN_API int dqn_lb_comm_init(dqn_lb_handle* h, void* ipc_handle_out, void** window_out) {
+  if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
+  if (h->window) return lbfail(DQN_E_INVALID, "dqn_lb_comm_init: already initialised");
+  const int W = h->cfg.world;
+  if (W != 2 && W != 4 && W != 8) return lbfail(DQN_E_INVALID, "dqn_lb_comm_init: the peer-memory all-reduce supports world = 2, 4 or 8");
+  CU(cudaSetDevice(h->cfg.device));
+  const int n4 = h->dims.PF / 4;
+  CU(cudaMalloc((void**)&h->window, comm_window_bytes(n4)));      // its own allocation: that is what cudaIpc shares
+  CU(cudaMemsetAsync(h->window, 0, comm_window_bytes(n4), h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->ws.grads = h->window;                                        // backward writes / Adam reads the window from now on
+  h->peers.win[h->cfg.rank] = h->window;
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, h->window));
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &mh, sizeof mh);
+  }
+  if (window_out) *window_out = h->window;
+  return DQN_OK;
+}
+
+DQN_API int dqn_lb_comm_connect(dqn_lb_handle* h, const void* ipc_handles, void* const* peer_windows) {
+  if (!h || !h->window) return lbfail(DQN_E_INVALID, "dqn_lb_comm_connect: call dqn_lb_comm_init first");
+  if (!ipc_handles == !peer_windows) return lbfail(DQN_E_INVALID, "dqn_lb_comm_connect: pass either IPC handles or same-process pointers");
+  CU(cudaSetDevice(h->cfg.device));
+  for (int q = 0; q < h->cfg.world; ++q) {
+    if (q == h->cfg.rank) continue;
+    if (ipc_handles) {
+      cudaIpcMemHandle_t mh;
+      memcpy(&mh, (const uint8_t*)ipc_handles + (size_t)q * sizeof mh, sizeof mh);
+      void* p = nullptr;
+      CU(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+      h->opened[q] = p;
+      h->peers.win[q] = (float*)p;
+    } else {
+      if (!peer_windows[q]) return lbfail(DQN_E_INVALID, "dqn_lb_comm_connect: NULL peer window");
+      cudaPointerAttributes at;
+      CU(cudaPointerGetAttributes(&at, peer_windows[q]));
+      if (at.device != h->cfg.device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        cudaGetLastError();
+      }
+      h->peers.win[q] = (float*)peer_windows[q];
+    }
+  }
+  h->connected = true;
+  return DQN_OK;
+}
+
+DQN_API int dqn_lb_allreduce(dqn_lb_handle* h) {
+  if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
+  if (h->cfg.world == 1) return DQN_OK;
+  if (!h->connected) return lbfail(DQN_E_INVALID, "dqn_lb_allreduce: dqn_lb_comm_connect has not been called");
+  CU(cudaSetDevice(h->cfg.device));
+  h->epoch += 1;
+  CU(lb_allreduce(h->stream, h->peers, h->cfg.world, h->cfg.rank, h->dims.PF / 4, h->epoch));
+  return DQN_OK;
+}
+
 DQN_API int dqn_lb_apply(dqn_lb_handle* h) {
   if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
   CU(cudaSetDevice(h->cfg.device));
@@ -330,8 +401,10 @@ DQN_API int dqn_lb_get_loss(dqn_lb_handle* h, float* loss_out) {
   if (!h || !loss_out) return lbfail(DQN_E_INVALID, "NULL argument");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaMemcpyAsync(h->pinned, h->ws.grads + h->dims.P, 4, cudaMemcpyDeviceToHost, h->stream));
+  if (h->window) CU(cudaMemcpyAsync(h->pinned + 1, &comm_flags(h->window, h->dims.PF / 4)->error, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   *loss_out = h->pinned[0];
+  if (h->window && ((const unsigned*)h->pinned)[1]) return lbfail(DQN_E_CUDA, "peer-memory all-reduce timed out waiting for a rank");
   return DQN_OK;
 }
 

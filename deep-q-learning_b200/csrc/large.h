@@ -36,6 +36,18 @@ struct LbWorkspace {
   float *tc_scratch;   // tcgen05 path: hi/lo operand splits
 };
 
+// ---- peer-memory gradient all-reduce (comm_p2p.cu) ----
+constexpr int kMaxWorld = 8;
+struct CommPeers { float* win[kMaxWorld]; };          // every rank's window, addressable from this GPU
+struct CommFlags {                                     // lives behind the n4 * 4 floats of a window
+  unsigned ready[kMaxWorld];                           // ready[q] = step number once rank q's gradient is complete
+  unsigned done[kMaxWorld];                            // done[q]  = step number once rank q has broadcast its slice
+  unsigned blocks_done, error;
+};
+__host__ __device__ inline CommFlags* comm_flags(float* win, int n4) { return reinterpret_cast<CommFlags*>(win + 4 * (size_t)n4); }
+inline size_t comm_window_bytes(int n4) { return (((size_t)n4 * 16 + sizeof(CommFlags)) + 255) / 256 * 256; }
+cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, unsigned epoch);
+
 cudaError_t lb_gemm_ffma(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                          float* C, int ldc, const float* aux, int ldaux, int splitk);
 cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,

@@ -3,10 +3,14 @@
 One agent, global minibatch ``B`` split contiguously over ``world_size`` ranks (one process per GPU).
 Per step every rank runs forward + backward on its ``B / world_size`` rows with gradients pre-scaled by
 ``1/B`` (the loss of ``q_learning_functions.py:36`` is a mean over the batch, so shard gradients add up),
-the flat gradient (+ the loss, riding in the last slot) is summed with ONE NCCL all-reduce, and every rank
-applies the identical Adam update -- replicas stay bit-identical because they all consume the same
-reduced buffer.  torch is used for the arena allocation and for ``torch.distributed.all_reduce`` on a
-tensor view of the gradient region; all arithmetic is in ``libdqn_b200.so``.
+the flat gradient (+ the loss, riding in the last slot) is summed, and every rank applies the identical Adam
+update -- replicas stay bit-identical because they all consume the same reduced buffer.
+
+The sum is the library's own kernel over NVLink peer memory (``collective="p2p"``, ``csrc/comm_p2p.cu``: flag
+barrier -> each rank reduces its slice of every rank's gradient window in rank order -> stores it into every
+window -> flag barrier; deterministic) for 2, 4 or 8 ranks of one node, with ``torch.distributed.all_reduce``
+(NCCL) as the comparison path (``collective="nccl"``).  torch is used for the arena allocation, for exchanging
+the 64-byte IPC handles at start-up and for the NCCL comparison; all arithmetic is in ``libdqn_b200.so``.
 """
 import ctypes as C
 
@@ -18,9 +22,17 @@ from .specs import flatten_tree, unflatten_tree, param_count
 GEMM_MODES = {"fp32": 0, "tc3xtf32": 1}
 
 
+class _DeviceFloats:
+    """A raw device pointer as a CUDA-array-interface object (so torch can view library-owned memory)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
 class LargeBatchTrainer:
     def __init__(self, obs_dim, num_actions, hidden, batch_global, buffer_size, gamma, optimizer, rank=0,
-                 world_size=1, seed=0, device=0, gemm_mode="fp32", process_group=None):
+                 world_size=1, seed=0, device=0, gemm_mode="fp32", process_group=None, collective="auto",
+                 connect=True):
         import torch
         self.torch, self.lib = torch, _lib.load()
         if not torch.cuda.is_available():
@@ -55,6 +67,33 @@ class LargeBatchTrainer:
         _lib.check(self.lib.dqn_lb_grads(self.h, C.byref(ptr), C.byref(cnt)))
         off = ptr.value - self._arena.data_ptr()
         self.grads = self._arena[off:off + 4 * cnt.value].view(torch.float32)     # P gradients + loss, for the collective
+        if collective == "auto":
+            collective = "p2p" if self.world in (2, 4, 8) else "nccl"
+        self.collective = collective if self.world > 1 else "none"
+        self.window = None
+        if self.collective == "p2p":
+            handle = np.zeros(64, np.uint8)
+            win = C.c_void_p()
+            _lib.check(self.lib.dqn_lb_comm_init(self.h, _lib.ptr(handle), C.byref(win)))
+            self.window = win.value
+            with torch.cuda.device(self.device):                                   # the gradient now lives in the window
+                self.grads = torch.as_tensor(_DeviceFloats(win.value, cnt.value), device=f"cuda:{self.device}")
+            if connect:                                                            # one process per GPU: swap IPC handles
+                import torch.distributed as dist
+                mine = torch.from_numpy(handle).to(f"cuda:{self.device}")
+                every = torch.empty(64 * self.world, dtype=torch.uint8, device=f"cuda:{self.device}")
+                dist.all_gather_into_tensor(every, mine, group=self.pg)
+                handles = np.ascontiguousarray(every.cpu().numpy())
+                _lib.check(self.lib.dqn_lb_comm_connect(self.h, _lib.ptr(handles), None))
+
+    @staticmethod
+    def connect_in_process(trainers):
+        """Ranks that live in ONE process (tests; several handles per GPU or one per visible GPU): exchange raw
+        window pointers instead of IPC handles.  Each trainer must enqueue on its own stream."""
+        world = len(trainers)
+        wins = (C.c_void_p * world)(*[t.window for t in sorted(trainers, key=lambda t: t.rank)])
+        for t in trainers:
+            _lib.check(t.lib.dqn_lb_comm_connect(t.h, None, wins))
 
     def close(self):
         if getattr(self, "h", None):
@@ -111,7 +150,9 @@ class LargeBatchTrainer:
         _lib.check(self.lib.dqn_lb_forward_backward(self.h, _lib.ptr(idx), 1 if debug else 0))
 
     def all_reduce(self):
-        if self.world > 1:
+        if self.collective == "p2p":
+            _lib.check(self.lib.dqn_lb_allreduce(self.h))      # enqueue only; every rank must call it once per step
+        elif self.collective == "nccl":
             import torch.distributed as dist
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
 

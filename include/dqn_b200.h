@@ -232,6 +232,16 @@ DQN_API int dqn_lb_buffer_state(dqn_lb_handle* h, int64_t* size_out, int64_t* co
  * Leaves the local gradient (already divided by the global batch) and loss share at dqn_lb_grads(). */
 DQN_API int dqn_lb_forward_backward(dqn_lb_handle* h, const int64_t* idx, int32_t debug);
 DQN_API int dqn_lb_grads(dqn_lb_handle* h, void** dev_ptr_out, int64_t* count_out);
+/* The gradient sum as ONE kernel over NVLink peer memory instead of a library collective (world = 2, 4 or 8 GPUs of a
+ * node): comm_init moves the gradient into a cudaMalloc'ed window and returns its 64-byte cudaIpcMemHandle_t; the caller
+ * gathers the handles of all ranks (any transport) and passes them to comm_connect -- or, for ranks living in ONE process,
+ * the raw window pointers.  dqn_lb_allreduce then enqueues: flag barrier -> rank r sums slice r of every rank's window in
+ * rank order -> stores it into every window -> flag barrier.  Deterministic; replicas receive bit-identical sums.  Every
+ * rank must enqueue it once per step; a rank that never arrives raises an error (reported by dqn_lb_get_loss), not a hang. */
+DQN_API int dqn_lb_comm_init(dqn_lb_handle* h, void* ipc_handle_out /* 64 bytes or NULL */, void** window_out /* or NULL */);
+DQN_API int dqn_lb_comm_connect(dqn_lb_handle* h, const void* ipc_handles /* world * 64 bytes, or NULL */,
+                                void* const* peer_windows /* world pointers, or NULL */);
+DQN_API int dqn_lb_allreduce(dqn_lb_handle* h);
 /* optimizer.update + apply_updates (q_learning_functions.py:24-25) with whatever is in the gradient buffer. */
 DQN_API int dqn_lb_apply(dqn_lb_handle* h);
 DQN_API int dqn_lb_sync_target(dqn_lb_handle* h);

@@ -14,12 +14,14 @@ pytestmark = pytest.mark.gpu
 HID = (256, 256)
 
 
-def make(B=256, world=1, rank=0, kind="adamw", lr=2e-4, gamma=0.99, seed=0, gemm_mode="fp32", D=8, A=4, N=3000, fill=2500):
+def make(B=256, world=1, rank=0, kind="adamw", lr=2e-4, gamma=0.99, seed=0, gemm_mode="fp32", D=8, A=4, N=3000, fill=2500,
+         collective="nccl", connect=True):
     rng = np.random.default_rng(seed)
     params = O.init_params(rng, D, A, hidden=HID, bias_std=0.05)
     target = O.tree_map(lambda x: (x + 0.01 * rng.standard_normal(x.shape)).astype(np.float32), params)
     opt = dqn_b200.adamw(lr) if kind == "adamw" else dqn_b200.adam(lr)
-    tr = dqn_b200.LargeBatchTrainer(D, A, HID, B, N, gamma, opt, rank=rank, world_size=world, seed=seed + 5, gemm_mode=gemm_mode)
+    tr = dqn_b200.LargeBatchTrainer(D, A, HID, B, N, gamma, opt, rank=rank, world_size=world, seed=seed + 5, gemm_mode=gemm_mode,
+                                    collective=collective, connect=connect)
     tr.set_params(params, 0)
     tr.set_params(target, 1)
     data = synthetic_transitions(rng, fill, D, A, done_p=0.2)
@@ -137,6 +139,47 @@ def test_two_rank_shards_sum_to_single_rank_gradient():
             assert np.array_equal(p0[m]["w"], p1[m]["w"]) and np.array_equal(p0[m]["b"], p1[m]["b"])   # replicas bit-identical
         assert_params_close(p0, ora, ill_dp, "dp")
         assert_params_close(one.get_params(), ora, ill_one, "single")
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_memory_allreduce_kernel(world):
+    """csrc/comm_p2p.cu: `world` ranks in this process (one stream each, raw window pointers instead of IPC handles --
+    the same kernel and flag protocol as one process per GPU).  The reduced window is bit-identical on every rank,
+    equals the rank-ordered sum of the shard gradients bit for bit, and the step matches the oracle."""
+    import torch
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    ranks = []
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            tr, ora = make(B=512, world=world, rank=r, collective="p2p", connect=False)
+        ranks.append(tr)
+    dqn_b200.LargeBatchTrainer.connect_in_process(ranks)
+    ill = IllConditioned()
+    for step in range(3):
+        for tr in ranks:
+            tr.forward_backward()
+        for tr in ranks:
+            tr.synchronize()
+        shards = [tr.grads.clone() for tr in ranks]
+        torch.cuda.synchronize()
+        for tr in ranks:
+            tr.all_reduce()                      # enqueue on every rank's stream before waiting on any of them
+        for tr in ranks:
+            tr.synchronize()
+        want = shards[0]
+        for g in shards[1:]:
+            want = want + g                      # rank order 0..W-1, the kernel's order
+        for tr in ranks:
+            assert torch.equal(tr.grads, want)
+        for tr in ranks:
+            tr.apply()
+        ref = ora.step()
+        assert abs(ranks[0].loss() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+        ps = [tr.get_params() for tr in ranks]
+        for p in ps[1:]:
+            for m in O.MODULES:
+                assert np.array_equal(ps[0][m]["w"], p[m]["w"]) and np.array_equal(ps[0][m]["b"], p[m]["b"])
+        assert_params_close(ps[0], ora, ill, f"p2p world {world} step {step}")
 
 
 def test_lb_config_validation():
