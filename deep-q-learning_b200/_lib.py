@@ -42,6 +42,19 @@ class DqnHparams(C.Structure):
                 ("b2", C.c_float), ("eps", C.c_float), ("eps_root", C.c_float), ("weight_decay", C.c_float)]
 
 
+class DqnEpisodeConfig(C.Structure):
+    _fields_ = [("epsilon", C.c_double), ("epsilon_decay_rate", C.c_double), ("min_epsilon", C.c_double),
+                ("reward_to_reach", C.c_double), ("max_episodes", C.c_int32), ("max_steps", C.c_int32),
+                ("training_start", C.c_int32), ("train_frequency", C.c_int32), ("replace_frequency", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class DqnEpisodeState(C.Structure):
+    _fields_ = [("epsilon", C.c_double), ("average_reward", C.c_double), ("last_episode_reward", C.c_double),
+                ("episode_reward", C.c_double), ("step_count", C.c_int64), ("policy_calls", C.c_int64),
+                ("episode", C.c_int32), ("step_in_episode", C.c_int32), ("window_len", C.c_int32), ("finished", C.c_int32)]
+
+
 class DqnDebugTaps(C.Structure):
     _fields_ = [("indices", C.c_void_p), ("q", C.c_void_p), ("next_q", C.c_void_p), ("next_q_tm", C.c_void_p),
                 ("max_actions", C.c_void_p), ("targets", C.c_void_p), ("loss", C.c_void_p), ("grads", C.c_void_p)]
@@ -92,6 +105,12 @@ PROTOTYPES = {
     "dqn_sync_target": (C.c_int, [_H, _i32, _i32]),
     "dqn_act": (C.c_int, [_H, _i32, _P, C.POINTER(_i32)]),
     "dqn_act_batch": (C.c_int, [_H, _i32, _i32, _P, _P]),
+    # episode-loop control on the device
+    "dqn_episode_configure": (C.c_int, [_H, _i32, _i32, C.POINTER(DqnEpisodeConfig), _i32]),
+    "dqn_policy_batch": (C.c_int, [_H, _i32, _i32, _P, _P]),
+    "dqn_observe_batch": (C.c_int, [_H, _i32, _i32, _P, _P, _P, _P, _P, _P]),
+    "dqn_train_flagged": (C.c_int, [_H, _i32, _i32]),
+    "dqn_episode_get_state": (C.c_int, [_H, _i32, C.POINTER(DqnEpisodeState)]),
     # large-batch data-parallel mode
     "dqn_lb_arena_bytes": (C.c_int, [C.POINTER(DqnLbConfig), C.POINTER(C.c_uint64)]),
     "dqn_lb_create": (C.c_int, [C.POINTER(DqnLbConfig), C.POINTER(_H)]),

@@ -7,57 +7,18 @@
 // sync: Agent._update_target_model (q_agent.py:143-144): theta^- := theta (exact copy).
 #include "common.cuh"
 #include "kernels.h"
+#include "act_device.cuh"
 
 namespace dqn {
 
 __global__ void __launch_bounds__(128)
 dqn_act_kernel(const float* __restrict__ params, Dims d, int agent_begin, int n_sel,
                const float* __restrict__ states, int* __restrict__ actions, float* __restrict__ q_out) {
-  const int lane = threadIdx.x & 31;
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= n_sel) return;
-  const int D = d.D, A = d.A;
-  // packed layout (common.cuh): [W1;b1] | [W2;b2] rows of 68 | head 65 x 8 (col 0 = V, 1..A = advantage)
-  const float* W1 = params + (size_t)(agent_begin + item) * 4 * d.PK;
-  const float* b1 = W1 + D * kH1;
-  const float* W2 = W1 + packed_w2(D);
-  const float* b2 = W2 + kH1 * kW2Stride;
-  const float* Wh = W1 + packed_head(D);
-  const float* bh = Wh + kH2 * kHeadCols;
-  const float* x = states + (size_t)item * D;
-
-  float z = b1[lane];
-  for (int k = 0; k < D; ++k) z = fmaf(x[k], W1[k * kH1 + lane], z);
-  const float h1 = fmaxf(z, 0.f);
-  float z0 = b2[lane], z1 = b2[lane + 32];
-#pragma unroll 8
-  for (int k = 0; k < kH1; ++k) {
-    const float hk = __shfl_sync(0xffffffffu, h1, k);
-    z0 = fmaf(hk, W2[k * kW2Stride + lane], z0);
-    z1 = fmaf(hk, W2[k * kW2Stride + lane + 32], z1);
-  }
-  const float h20 = fmaxf(z0, 0.f), h21 = fmaxf(z1, 0.f);
-  float head[1 + kMaxA];
-  for (int c = 0; c <= kMaxA; ++c)      // packed head columns > A are zero
-    head[c] = h20 * Wh[lane * kHeadCols + c] + h21 * Wh[(lane + 32) * kHeadCols + c];
-#pragma unroll
-  for (int c = 0; c <= kMaxA; ++c) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) head[c] += __shfl_xor_sync(0xffffffffu, head[c], o);
-  }
-  if (lane == 0) {
-    const float val = head[0] + bh[0];
-    float msum = 0.f;
-    for (int j = 0; j < A; ++j) { head[1 + j] += bh[1 + j]; msum += head[1 + j]; }
-    const float mean = msum / (float)A;
-    int best = 0; float bq = 0.f;
-    for (int j = 0; j < A; ++j) {
-      const float q = val + head[1 + j] - mean;
-      if (q_out) q_out[(size_t)item * A + j] = q;
-      if (j == 0 || q > bq) { bq = q; best = j; }
-    }
-    actions[item] = best;
-  }
+  const int best = warp_greedy_action(params + (size_t)(agent_begin + item) * 4 * d.PK, d.D, d.A, states + (size_t)item * d.D,
+                                      q_out ? q_out + (size_t)item * d.A : nullptr);
+  if ((threadIdx.x & 31) == 0) actions[item] = best;
 }
 
 __global__ void __launch_bounds__(256)

@@ -35,6 +35,21 @@ struct AgentCtl {
                            //   launch); the host re-seeds them whenever it sets the count or the decay rates
 };
 
+// Per-agent episode-loop state (episode.cu): what Agent._run_episode / training keep in Python attributes and locals
+// (General/QLearning/q_agent.py:96-107, :171-222).  epsilon / rewards are doubles like the Python floats they mirror.
+constexpr int kRewardWindow = 50;              // q_agent.py:125
+constexpr uint32_t kPolicyTag = 0x504F4C49u;   // 'POLI': Philox key tweak of the epsilon-greedy stream
+struct EpisodeCtl {
+  double epsilon, eps_decay, min_eps, reward_to_reach;
+  double epi_reward, last_epi_reward, avg_reward;
+  double window[kRewardWindow];
+  int window_len, window_pos;
+  int max_episodes, max_steps, training_start, train_frequency, replace_frequency;
+  int step_in_episode, episode;
+  int train_flag, sync_flag, finished;
+  long long step_count, policy_calls;
+};
+
 struct Dims {
   int D, A;      // obs dim, actions
   int P;         // flat parameter count

@@ -28,6 +28,7 @@ struct TrainArgs {
   unsigned long long* loss_mailbox;   // [n_agents] zero-copy (mapped pinned host memory): (train_steps << 32) | loss bits
                                       //   of the launch's last step, one 8-byte store -- the host can poll it
   const long long* idx;       // device i64 [n_sel][K][B] or nullptr (Philox)
+  const EpisodeCtl* gate;     // nullptr, or per-agent episode state: only agents with gate[agent].train_flag step
   Dims dims;
   unsigned long long seed;
   int agent_begin;
@@ -69,6 +70,13 @@ cudaError_t launch_act(cudaStream_t st, const float* params, const Dims& d, int 
                        const float* states /* device [n_sel][D] */, int* actions_out /* device [n_sel] */,
                        float* q_out /* device [n_sel][A] or nullptr */);
 cudaError_t launch_sync_target(cudaStream_t st, float* params, const Dims& d, int agent_begin, int n_sel);
+
+// episode-loop control on the device (episode.cu)
+cudaError_t launch_policy(cudaStream_t st, const float* params, const Dims& d, EpisodeCtl* ep, int agent_begin, int n_sel,
+                          int agent_id_base, unsigned long long seed, const float* states, int* actions);
+cudaError_t launch_observe(cudaStream_t st, uint32_t* rings, AgentCtl* ctl, EpisodeCtl* ep, const Dims& d, int agent_begin, int n_sel,
+                           const float* s, const int* a, const float* r, const float* s2, const uint8_t* done, uint8_t* episode_end);
+cudaError_t launch_episode_post(cudaStream_t st, float* params, const Dims& d, EpisodeCtl* ep, int agent_begin, int n_sel);
 
 // prioritized replay (per.cu)
 cudaError_t launch_per_update(cudaStream_t st, float* tree, long long L, int levels, const long long* idx, const float* val, int n,

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   const int agent = args.agent_begin + sel;
   const int D = args.dims.D, recw = args.dims.recw, PK = args.dims.PK;
   const CLay L = make_clayout(D, recw);
+  if (args.gate && !args.gate[agent].train_flag) return;   // episode gate closed (q_agent.py:186): uniform over the CTA / cluster
   PHASE_CLOCK(0);
 
   float* const W = sm + L.oW;

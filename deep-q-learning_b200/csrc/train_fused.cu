@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   const int recw = args.dims.recw;
   const int PK = args.dims.PK;
   const Lay L = make_layout(D, recw);
+  if (args.gate && !args.gate[agent].train_flag) return;   // episode gate closed (q_agent.py:186): uniform over the CTA / cluster
 
   float* const W = sm + L.oW;       // theta      (smem layout)
   float* const Wt = sm + L.oWt;     // theta^-

@@ -195,6 +195,56 @@ class DqnEngine:
         agent_end = self.n_agents if agent_end is None else agent_end
         _lib.check(self.lib.dqn_sync_target(self.h, agent_begin, agent_end))
 
+    # -- episode-loop control on the device (torch CUDA tensors in, torch CUDA tensors out; enqueue only) ----------
+    def configure_episodes(self, configs, agent_begin=0, reset_counters=True):
+        """``configs``: one dict per agent with the reference's kwarg names (epsilon, epsilon_decay_rate, min_epsilon,
+        reward_to_reach, max_episodes, max_steps, training_start, train_frequency, replace_frequency)."""
+        arr = (_lib.DqnEpisodeConfig * len(configs))()
+        for c, src in zip(arr, configs):
+            for k, _ in _lib.DqnEpisodeConfig._fields_:
+                if k != "reserved":
+                    setattr(c, k, src[k])
+        _lib.check(self.lib.dqn_episode_configure(self.h, agent_begin, agent_begin + len(configs), arr, 1 if reset_counters else 0))
+
+    def _dev(self, t, dtype, n):
+        torch = self.torch
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous() and t.numel() == n):
+            raise TypeError(f"expected a contiguous CUDA tensor of {n} x {dtype}")
+        return C.c_void_p(t.data_ptr())
+
+    def policy(self, states, actions_out=None, agent_begin=0, agent_end=None):
+        """Agent._policy for agents [agent_begin, agent_end): states f32[n, D] -> actions i32[n] (epsilon-greedy)."""
+        torch = self.torch
+        agent_end = self.n_agents if agent_end is None else agent_end
+        n = agent_end - agent_begin
+        if actions_out is None:
+            actions_out = torch.empty(n, dtype=torch.int32, device=states.device)
+        _lib.check(self.lib.dqn_policy_batch(self.h, agent_begin, agent_end, self._dev(states, torch.float32, n * self.obs_dim),
+                                             self._dev(actions_out, torch.int32, n)))
+        return actions_out
+
+    def observe(self, states, actions, rewards, observations, dones, episode_end_out=None, agent_begin=0, agent_end=None):
+        """One iteration of Agent._run_episode after env.step for every agent of the range; returns u8[n] episode-end flags."""
+        torch = self.torch
+        agent_end = self.n_agents if agent_end is None else agent_end
+        n = agent_end - agent_begin
+        if episode_end_out is None:
+            episode_end_out = torch.empty(n, dtype=torch.uint8, device=states.device)
+        _lib.check(self.lib.dqn_observe_batch(
+            self.h, agent_begin, agent_end, self._dev(states, torch.float32, n * self.obs_dim), self._dev(actions, torch.int32, n),
+            self._dev(rewards, torch.float32, n), self._dev(observations, torch.float32, n * self.obs_dim),
+            self._dev(dones, torch.uint8, n), self._dev(episode_end_out, torch.uint8, n)))
+        return episode_end_out
+
+    def train_flagged(self, agent_begin=0, agent_end=None):
+        agent_end = self.n_agents if agent_end is None else agent_end
+        _lib.check(self.lib.dqn_train_flagged(self.h, agent_begin, agent_end))
+
+    def episode_state(self, agent=0):
+        st = _lib.DqnEpisodeState()
+        _lib.check(self.lib.dqn_episode_get_state(self.h, agent, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _lib.DqnEpisodeState._fields_}
+
     def act(self, state, agent=0):
         st = _f32(state).reshape(-1)
         if st.size != self.obs_dim:

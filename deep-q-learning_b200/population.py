@@ -61,5 +61,24 @@ class Population:
     def sync_targets(self):
         self.engine.sync_target(0, self.n_local)
 
+    # -- the reference's episode loop, batched on the device (q_agent.py:171-222) -----------------
+    def configure_episodes(self, max_episodes, max_steps, training_start, reward_to_reach, reset_counters=True):
+        """Per-agent epsilon schedule / cadences from the sweep draw (hyperparameter_optimization.py:115-123), the rest
+        from the sweep script's constants (Test/lunar_lander_hyper_params.py:22-30)."""
+        cfgs = [dict(epsilon=hp["epsilon"], epsilon_decay_rate=hp["epsilon_decay_rate"], min_epsilon=hp["min_epsilon"],
+                     reward_to_reach=reward_to_reach, max_episodes=max_episodes, max_steps=max_steps,
+                     training_start=training_start, train_frequency=hp["train_frequency"],
+                     replace_frequency=hp["replace_frequency"]) for hp in self.hparams]
+        self.engine.configure_episodes(cfgs, 0, reset_counters)
+
+    def policy(self, states, actions_out=None):
+        return self.engine.policy(states, actions_out, 0, self.n_local)
+
+    def observe(self, states, actions, rewards, observations, dones, episode_end_out=None):
+        return self.engine.observe(states, actions, rewards, observations, dones, episode_end_out, 0, self.n_local)
+
+    def train_flagged(self):
+        self.engine.train_flagged(0, self.n_local)
+
     def params_flat(self, local):
         return self.engine.get_params_flat(local, 0)

@@ -189,6 +189,39 @@ DQN_API int dqn_act(dqn_handle* h, int32_t agent, const float* state, int32_t* a
 DQN_API int dqn_act_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* states, int32_t* actions_out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Episode-loop control on the device: the reference's per-env-step work around the train step,
+ * batched over the agents [agent_begin, agent_end) with no host round trip.  All array arguments are DEVICE pointers,
+ * one entry per agent of the range; every call only enqueues.
+ *   dqn_policy_batch   Agent._policy (q_agent.py:137-141): epsilon < uniform(0,1) ? argmax_a Q(theta, state) : randint(0, A);
+ *                      the two draws come from the handle's Philox stream (the reference's host RNGs are unseeded).
+ *   dqn_observe_batch  one iteration of Agent._run_episode after env.step (q_agent.py:174-203): done forced at max_steps,
+ *                      ReplayBuffer.add, reward accumulation, the train gate (size >= training_start and step_count %
+ *                      train_frequency == 0), and at an episode end: hard-sync cadence (episode % replace_frequency == 0),
+ *                      epsilon decay, the 50-episode reward window, the stop test of Agent.training (q_agent.py:211,:219).
+ *                      episode_end[i] = 1 tells the caller to reset environment i.
+ *   dqn_train_flagged  Agent._step() for the agents whose gate opened in the last observe (ONE launch, the others' CTAs
+ *                      exit at once), then theta^- := theta for agents whose episode ended on a sync episode.
+ * A `finished` agent is only reported (dqn_episode_get_state); the caller retires it (the reference returns from training()).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dqn_episode_config {          /* Agent.__init__ kwargs of the same names, q_agent.py:61-86 */
+  double epsilon, epsilon_decay_rate, min_epsilon, reward_to_reach;
+  int32_t max_episodes, max_steps, training_start, train_frequency, replace_frequency, reserved;
+} dqn_episode_config;
+typedef struct dqn_episode_state {
+  double epsilon, average_reward, last_episode_reward, episode_reward;
+  int64_t step_count, policy_calls;
+  int32_t episode, step_in_episode, window_len, finished;
+} dqn_episode_state;
+/* cfgs: HOST array, one per agent of the range.  reset_counters != 0 restarts episode / step counters (a new
+ * Agent.training() call); the reward window and the policy RNG position persist like the reference's attributes. */
+DQN_API int dqn_episode_configure(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const dqn_episode_config* cfgs, int32_t reset_counters);
+DQN_API int dqn_policy_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* states_dev, int32_t* actions_dev);
+DQN_API int dqn_observe_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* s_dev, const int32_t* a_dev,
+                              const float* r_dev, const float* s2_dev, const uint8_t* done_dev, uint8_t* episode_end_dev);
+DQN_API int dqn_train_flagged(dqn_handle* h, int32_t agent_begin, int32_t agent_end);
+DQN_API int dqn_episode_get_state(dqn_handle* h, int32_t agent, dqn_episode_state* out);   /* synchronises */
+
+/* ------------------------------------------------------------------------------------------------
  * Large-batch data-parallel mode (BASELINE configs[3]: batch 65536, hidden 1024x1024).  Same update as
  * Agent._step (q_agent.py:146-169) for ONE agent whose minibatch is split over `world` ranks: every rank
  * holds replicas of theta / theta^- / Adam state and of the replay ring, runs forward+backward on its
