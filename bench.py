@@ -460,6 +460,95 @@ def run_population(args):
         dist.destroy_process_group()
 
 
+def run_episodes(args):
+    """The reference's whole per-env-step loop (q_agent.py:174-203) for a population, on the device: epsilon-greedy policy ->
+    (synthetic vectorised env) -> observe (store + episode bookkeeping + train gate) -> gated train step + hard sync.
+    `value` = aggregate env steps/s; train steps happen on each agent's own train_frequency cadence (sweep draw, 2..15)."""
+    import torch
+    import dqn_b200
+    from threadpoolctl import threadpool_limits
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    n_global, ring, T = args.agents, 40_000, 64
+    pop = dqn_b200.Population(n_global, D, A, ring, dqn_b200.adam(1e-4), rank=rank, world_size=world, seed=1, device=local)
+    n = pop.n_local
+    pop.configure_episodes(max_episodes=10000, max_steps=1500, training_start=500, reward_to_reach=240.0)   # lunar_lander_hyper_params.py:22-30
+    g = torch.Generator(device=device); g.manual_seed(77 + rank)
+    obs = torch.randn(T, n, D, generator=g, device=device)
+    rew = 2.0 * torch.randn(T, n, generator=g, device=device)
+    done = (torch.rand(T, n, generator=g, device=device) < 0.01).to(torch.uint8)
+    act = torch.empty(n, dtype=torch.int32, device=device)
+    end = torch.empty(n, dtype=torch.uint8, device=device)
+
+    def env_steps(k, t0):
+        st = obs[(t0 - 1) % T]
+        for t in range(t0, t0 + k):
+            pop.policy(st, act)
+            nxt = obs[t % T]
+            pop.observe(st, act, rew[t % T], nxt, done[t % T], end)
+            pop.train_flagged()
+            st = nxt
+    warm = 520                                                    # past training_start = 500: the train gate is live
+    env_steps(warm, 0)
+    torch.cuda.synchronize(device)
+    steps = max(args.steps, 64)
+    trained0 = sum(pop.engine.train_step_count(i) for i in range(n))
+    flush_l2(torch, device)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        env_steps(steps, warm)
+        e1.record()
+        torch.cuda.synchronize(device)
+    secs = e0.elapsed_time(e1) * 1e-3
+    trained = sum(pop.engine.train_step_count(i) for i in range(n)) - trained0
+    t = torch.tensor([secs, float(trained)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.barrier()
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        secs, trained = float(tm[0].item()), float(ts[1].item())
+    if rank == 0:
+        # CPU side: the restated reference loop (oracle) for one agent on one core, same cadence parameters
+        from oracle import dqn_oracle as O
+        from oracle.agent_oracle import OracleAgent
+        from oracle.episode_oracle import EpisodeOracle
+        hp = pop.hparams[0]
+        rng = np.random.default_rng(0)
+        theta = O.init_params(rng, D, A)
+        oa = OracleAgent(theta, O.init_opt_state(theta), O.OptSpec("adam", 1e-4), ring, D, hp["gamma"], hp["batch_size"], seed=1)
+        eo = EpisodeOracle(oa, hp["epsilon"], hp["epsilon_decay_rate"], hp["min_epsilon"], 10000, 1500, 500, hp["train_frequency"],
+                           hp["replace_frequency"], 240.0, A, seed=1)
+        so, ro = rng.standard_normal((4096, D)).astype(np.float32), (2 * rng.standard_normal(4096)).astype(np.float32)
+        with threadpool_limits(limits=1):
+            for i in range(520):
+                eo.observe(so[i], eo.policy(so[i])[0], ro[i], so[i + 1], False)
+            c0 = time.perf_counter(); k = 0
+            while time.perf_counter() - c0 < 10.0:
+                i = 520 + k % 3000
+                eo.observe(so[i], eo.policy(so[i])[0], ro[i], so[i + 1], False)
+                k += 1
+            cpu_rate = k / (time.perf_counter() - c0)
+        print(json.dumps({
+            "metric": "env_steps_per_sec", "value": n_global * steps / secs, "unit": "agent-env-steps/s", "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "population of %d sweep agents, full device-side episode loop (policy -> observe -> gated train -> sync), "
+                                   "synthetic vectorised env" % n_global, "obs_dim": D, "num_actions": A, "ring_slots_per_agent": ring,
+                       "l2": "rings %.1f GB per rank >> L2" % (n * ring * 96 / 1e9)},
+            "clocks": clk.summary(), "gpu_launches": int(steps * 3.5), "agent_train_steps_per_sec": trained / secs,
+            "cpu_baseline": {"value": cpu_rate, "unit": "agent-env-steps/s", "cores": 1, "kind": "port",
+                             "sample": "%d env steps of ONE agent (train_frequency %d) through oracle/episode_oracle.py in 10 s" % (k, hp["train_frequency"])}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_dp(args):
     """BASELINE configs[3]: large-batch data-parallel DDQN, global batch 65536, hidden 1024x1024, D=8, A=4.
     Each rank: forward+backward on B/world rows -> ONE NCCL all-reduce of P+1 floats -> identical Adam.
@@ -590,7 +679,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid (ncu): only the fused timed region, no e2e / extras / cpu baseline; not a bench value")
-    ap.add_argument("--workload", default="single", choices=["single", "population", "dp", "per"])
+    ap.add_argument("--workload", default="single", choices=["single", "population", "dp", "per", "episodes"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--hidden", type=int, default=1024)
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tc3xtf32"])
@@ -621,6 +710,8 @@ def main():
         return run_dp(args)
     if args.workload == "per":
         return run_per(args)
+    if args.workload == "episodes":
+        return run_episodes(args)
     run_single(args)
 
 
