@@ -183,6 +183,26 @@ def test_store_and_train_in_one_launch_equals_store_then_train():
     compare_state(engs[1], ora, "store+train fused", rtol=2e-5)
 
 
+def test_long_runs_are_bitwise_reproducible():
+    """4000 steps, once as 8 launches of 500 and once as 40 launches of 100, on two handles: bit-identical parameters,
+    moments and losses.  (The cluster kernel exchanges gradients and weights through distributed shared memory with
+    relaxed cluster barriers; a missed ordering would show up here as run-to-run divergence.)"""
+    a, _, _ = make_pair(seed=11, lr=1e-3, N=5000, n_fill=5000)
+    b, _, _ = make_pair(seed=11, lr=1e-3, N=5000, n_fill=5000)
+    for _ in range(8):
+        a.train_steps(500)
+    for _ in range(40):
+        b.train_steps(100)
+    assert np.array_equal(a.get_params_flat(), b.get_params_flat())
+    (ca, ma, va), (cb, mb, vb) = a.get_opt_state(), b.get_opt_state()
+    assert ca == cb == 4000
+    for m in O.MODULES:
+        for k in ("w", "b"):
+            assert np.array_equal(ma[m][k], mb[m][k]) and np.array_equal(va[m][k], vb[m][k])
+    assert np.array_equal(a.losses(4000), b.losses(4000))
+    assert np.all(np.isfinite(a.get_params_flat()))
+
+
 def test_greedy_actions_bit_exact():
     eng, ora, rng = make_pair(seed=9)
     states = rng.standard_normal((2000, 9)).astype(np.float32)
