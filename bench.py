@@ -314,8 +314,16 @@ def run_single(args):
     flops = B * FLOP_PER_SAMPLE / (secs / args.steps) / 1e9
     cluster = args.step_kernel in ("auto", "cluster")
     n_sm = 4 if cluster else 1
+    kname = "dqn_train_cluster_kernel<4>" if cluster else "dqn_train_fused_kernel<4>"
+    traffic = None
+    try:      # DRAM bytes of one launch from the committed ncu --set full capture, scaled to this run's steps per launch
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)[kname]
+        traffic = tr["dram_bytes_per_launch"] / tr["steps_per_launch"] * steps_per_launch
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "dqn_train_cluster_kernel<4>" if cluster else "dqn_train_fused_kernel<4>", "peak_source": peak_src,
+                "traffic": traffic, "kernel": kname, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": launch_s * 1e3,
                 "note": "latency-bound by construction: one agent's steps are a serial chain (step t+1 needs theta_t) on %s; "
                         "theta/theta^-/grads stay in shared memory, so the only HBM traffic is 64 gathered records per step "
