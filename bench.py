@@ -187,7 +187,7 @@ def workload_config():
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
-def build_agent(dqn_b200, device, seed):
+def build_agent(dqn_b200, device, seed, session=False):
     rng = np.random.default_rng(seed)
     model = dqn_b200.Model(A)
     params = model.init(rng, np.zeros((1, D), np.float32))
@@ -197,7 +197,7 @@ def build_agent(dqn_b200, device, seed):
                            epsilon_decay_rate=0.99, min_epsilon=0.15, max_episodes=10000, max_steps=1500,
                            training_start=250, batch_size=B, train_frequency=TRAIN_FREQUENCY, back_up_frequency=50,
                            replace_frequency=20, reward_to_reach=230.0, num_actions=A,
-                           saving_directory="/tmp/dqn_b200_bench", device=device, seed=seed)
+                           saving_directory="/tmp/dqn_b200_bench", device=device, seed=seed, session=session)
     data = synthetic(rng, N_RING)
     for o in range(0, N_RING, 250_000):
         agent._replay_buffer.add_many(*[x[o:o + 250_000] for x in data])
@@ -237,7 +237,7 @@ def run_single(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
-    agent, data = build_agent(dqn_b200, local, seed=rank)
+    agent, data = build_agent(dqn_b200, local, seed=rank, session=not args.no_session)
     eng = agent._engine
 
     def barrier():
@@ -283,12 +283,14 @@ def run_single(args):
         return last
 
     e2e_loop(8)
+    eng.synchronize()                       # (session mode: retire the resident kernel before other work uses the stream)
     flush_l2(torch, device)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t0 = time.perf_counter()
     e2e_loop(e2e_steps, off=8 * TRAIN_FREQUENCY)
+    eng.synchronize()                       # inside the timed region: the session's state is back in HBM
     e1.record()
     torch.cuda.synchronize(device)
     e2e_wall = time.perf_counter() - t0
@@ -360,7 +362,8 @@ def run_single(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": TRAIN_FREQUENCY * REC_BYTES_ALGO,
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "api": "ReplayBuffer.add x4 (host numpy) + Agent._step() + loss readback per step"},
+                "api": "ReplayBuffer.add x4 (host numpy) + Agent._step() + loss readback per step"
+                       + ("" if args.no_session else "; Agent(session=True): commands served by the resident train-step kernel")},
         "gpu_launches": launches, "replay_samples_per_sec": value * B,
         "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
     }
@@ -693,6 +696,8 @@ def main():
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tc3xtf32"])
     ap.add_argument("--agents", type=int, default=1024)
     ap.add_argument("--steps-per-launch", type=int, default=16)
+    ap.add_argument("--no-session", action="store_true",
+                    help="single workload: e2e through one launch per Agent._step() instead of the resident session kernel")
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
                     help="dp workload: gradient all-reduce by the library's own peer-memory kernel (p2p) or by NCCL")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "cta", "cluster"],
@@ -710,7 +715,7 @@ def main():
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
                "--workload", args.workload, "--agents", str(args.agents), "--steps-per-launch", str(args.steps_per_launch),
                "--batch", str(args.batch), "--hidden", str(args.hidden), "--gemm", args.gemm, "--step-kernel", args.step_kernel,
-               "--collective", args.collective]
+               "--collective", args.collective] + (["--no-session"] if args.no_session else [])
         sys.exit(subprocess.call(cmd))
     if args.workload == "population":
         return run_population(args)

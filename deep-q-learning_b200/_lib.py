@@ -91,6 +91,7 @@ PROTOTYPES = {
     "dqn_set_hparams": (C.c_int, [_H, _i32, C.POINTER(DqnHparams)]),
     "dqn_get_hparams": (C.c_int, [_H, _i32, C.POINTER(DqnHparams)]),
     "dqn_set_step_kernel": (C.c_int, [_H, _i32]),
+    "dqn_set_session": (C.c_int, [_H, _i32]),
     "dqn_store": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P]),
     "dqn_store_device": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P]),
     "dqn_buffer_state": (C.c_int, [_H, _i32, C.POINTER(_i64), C.POINTER(_i64)]),

@@ -9,6 +9,10 @@ the device in the reference's tree layout.  The four jitted closures the referen
 agent (``_compute_action``, ``_compute_q_targets``, ``_train_step`` and ``preprocessing``,
 ``q_agent.py:110-112,154``) are fused: ``_step()`` is one kernel launch.
 
+``session=True`` keeps ONE launch of the train-step kernel resident: ``_policy``'s greedy branch, ``add`` + ``_step`` and
+``_update_target_model`` are then served from commands in mapped host memory with no kernel launch on the env loop's
+path (``dqn_set_session`` in ``include/dqn_b200.h``); anything else (checkpoints, parameter reads) ends the session first.
+
 ``network`` is a ``specs.Model`` and ``optimizer`` a ``specs.Optimizer`` (see ``specs.py``); ``env``
 is any object with the old-gym ``reset() -> obs[1,D]`` / ``step(a) -> (obs, reward, done, info)``
 API of ``LunarLander/env.py`` and is only needed by the episode loop.
@@ -31,7 +35,7 @@ class Agent:
                  gamma, epsilon, epsilon_decay_rate, min_epsilon, max_episodes, max_steps,
                  training_start, batch_size, train_frequency, back_up_frequency, replace_frequency,
                  reward_to_reach, num_actions, saving_directory, monitoring=False, verbose=1,
-                 *, device=0, seed=0):
+                 *, device=0, seed=0, session=False):
         self._network = network
         self._optimizer = optimizer
         self._env = env
@@ -40,7 +44,7 @@ class Agent:
             raise ValueError("network.num_actions != num_actions")
         # batch_size 0 is what ParamAgent's constructor passes before inject(); the device needs >= 1
         self._engine = DqnEngine(obs_dim, num_actions, buffer_size, max(int(batch_size), 1), gamma,
-                                 optimizer, n_agents=1, seed=seed, device=device)
+                                 optimizer, n_agents=1, seed=seed, device=device, session=session)
         self._lib, self._h = self._engine.lib, self._engine.h
         self._params = params
         self._opt_state = opt_state

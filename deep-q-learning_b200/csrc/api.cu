@@ -2,6 +2,7 @@
 // No compute happens on the host; every entry point either moves bytes or launches a kernel.
 #include <math.h>
 #include <stdio.h>
+#include <time.h>
 #include <string.h>
 
 #include <string>
@@ -128,6 +129,13 @@ struct dqn_handle {
   cudaEvent_t slot_ev[kSlots];  // completion of the H2D copy that last used each pinned store slot
   int slot_next;
   std::vector<AgentCtl> hctl;   // host mirror of the per-agent control blocks
+  // session mode (dqn_set_session): a resident cluster kernel serves STEP / ACT / SYNC commands from mapped host memory
+  SessionCtl* sess;             // mapped pinned host memory (nullptr until enabled)
+  SessionCtl* sess_dev;         // device alias
+  bool session_enabled, session_active, session_outstanding;
+  unsigned long long session_seq;       // sequence number of the last command published
+  float session_last_loss;
+  double session_last_cmd;      // host clock (s) of the last command: the kernel leaves after ~30 ms of silence
   EpisodeCtl* ep;               // device: per-agent episode-loop state (episode.cu)
   struct HostEpisode { long long step_count; int training_start, train_frequency; bool configured, pending_train; };
   std::vector<HostEpisode> hep; // host mirror of what decides the train gate (it depends on counters only, never on data)
@@ -135,15 +143,22 @@ struct dqn_handle {
 
 namespace {
 
-int check_agent(const dqn_handle* h, int agent) {
+int session_stop(dqn_handle* h);     // defined with the other session functions below
+int check_agent_raw(const dqn_handle* h, int agent) {
   if (!h) return fail(DQN_E_INVALID, "handle is NULL");
   if (agent < 0 || agent >= h->cfg.n_agents) return fail(DQN_E_INVALID, "agent index out of range");
   return DQN_OK;
 }
-int check_range(const dqn_handle* h, int b, int e) {
+// Every entry point that is not served by a running session first ends it (the resident kernel owns the agent's
+// parameters in shared memory and occupies the stream): the state is written back and the stream drained.
+int check_agent(dqn_handle* h, int agent) {
+  if (int rc = check_agent_raw(h, agent)) return rc;
+  return h->session_active ? session_stop(h) : DQN_OK;
+}
+int check_range(dqn_handle* h, int b, int e) {
   if (!h) return fail(DQN_E_INVALID, "handle is NULL");
   if (b < 0 || e > h->cfg.n_agents || b >= e) return fail(DQN_E_INVALID, "agent range out of bounds or empty");
-  return DQN_OK;
+  return h->session_active ? session_stop(h) : DQN_OK;
 }
 uint32_t* ring_of(dqn_handle* h, int agent) { return h->rings + (size_t)agent * (size_t)h->dims.N * h->dims.recw; }
 long long size_of(const dqn_handle* h, int agent) {
@@ -233,6 +248,9 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->mailbox_dev, (void*)h->mailbox, 0);
   if (e != cudaSuccess) { cudaFreeHost(h->pinned); if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaHostAlloc(mapped) failed"); }
   memset((void*)h->mailbox, 0, sizeof(unsigned long long) * cfg->n_agents);
+  h->sess = nullptr; h->sess_dev = nullptr;
+  h->session_enabled = h->session_active = h->session_outstanding = false;
+  h->session_seq = 0; h->session_last_loss = 0.f; h->session_last_cmd = 0.0;
   h->slot_next = 0;
   for (int i = 0; i < kSlots; ++i) cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming);
   // zero parameters / moments / rings / losses (ReplayBuffer.__init__ zero-fills, replay_buffer.py:26-30)
@@ -271,7 +289,9 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
 DQN_API int dqn_destroy(dqn_handle* h) {
   if (!h) return DQN_OK;
   cudaSetDevice(h->cfg.device);
+  if (h->session_active) session_stop(h);
   cudaStreamSynchronize(h->stream);
+  if (h->sess) cudaFreeHost((void*)h->sess);
   for (int i = 0; i < kSlots; ++i) cudaEventDestroy(h->slot_ev[i]);
   if (h->mailbox) cudaFreeHost((void*)h->mailbox);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -289,6 +309,7 @@ DQN_API int dqn_param_count(const dqn_handle* h, int32_t* p_out) {
 DQN_API int dqn_synchronize(dqn_handle* h) {
   if (!h) return fail(DQN_E_INVALID, "handle is NULL");
   CU(cudaSetDevice(h->cfg.device));
+  if (h->session_active) if (int rc = session_stop(h)) return rc;
   CU(cudaStreamSynchronize(h->stream));
   return DQN_OK;
 }
@@ -411,6 +432,7 @@ DQN_API int dqn_get_hparams(dqn_handle* h, int32_t agent, dqn_hparams* hp) {
 
 DQN_API int dqn_set_step_kernel(dqn_handle* h, int32_t step_kernel) {
   if (!h) return fail(DQN_E_INVALID, "handle is NULL");
+  if (h->session_active) if (int rc = session_stop(h)) return rc;
   if (step_kernel < DQN_STEP_AUTO || step_kernel > DQN_STEP_CLUSTER) return fail(DQN_E_INVALID, "dqn_set_step_kernel: unknown kernel id");
   h->step_kernel = step_kernel;
   return DQN_OK;
@@ -653,12 +675,148 @@ int wait_mailbox(dqn_handle* h, int agent, float* loss_out) {
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// session mode: one resident launch of the cluster kernel serves the agent's per-env-step calls
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+double host_now() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void cpu_relax() {
+#if defined(__x86_64__)
+  __builtin_ia32_pause();
+#endif
+}
+
+int session_launch(dqn_handle* h) {
+  TrainArgs ta;
+  memset(&ta, 0, sizeof ta);
+  ta.params = h->params; ta.ctl = h->ctl; ta.rings = h->rings; ta.loss_ring = h->loss_ring; ta.loss_mailbox = h->mailbox_dev;
+  ta.dims = h->dims; ta.seed = h->cfg.seed; ta.agent_begin = 0; ta.agent_id_base = h->cfg.agent_id_base; ta.n_sel = 1; ta.K = 0;
+  ta.sess = h->sess_dev; ta.sess_first_seq = h->session_seq + 1;
+  CU(launch_train_cluster(h->stream, ta, nullptr));
+  h->session_active = true;
+  h->session_last_cmd = host_now();
+  return DQN_OK;
+}
+
+// wait for the answer to the command in flight (if any); a command that a timed-out kernel never saw is re-sent to a
+// fresh launch
+int session_collect(dqn_handle* h, uint32_t* payload_out) {
+  if (!h->session_outstanding) return DQN_OK;
+  const uint32_t want = (uint32_t)h->session_seq;
+  for (unsigned long spin = 1;; ++spin) {
+    const unsigned long long v = h->sess->response;
+    if ((uint32_t)(v >> 32) == want) {
+      if (payload_out) *payload_out = (uint32_t)v;
+      h->session_outstanding = false;
+      return DQN_OK;
+    }
+    if ((spin & 0x3fff) == 0) {
+      const cudaError_t e = cudaStreamQuery(h->stream);
+      if (e == cudaSuccess) {                       // the kernel has left (idle time-out) ...
+        if ((uint32_t)(h->sess->response >> 32) == want) continue;      // ... after answering
+        if (int rc = session_launch(h)) return rc;                       // ... without seeing the command: serve it again
+      } else if (e != cudaErrorNotReady) {
+        h->session_active = false; h->session_outstanding = false;
+        return fail(DQN_E_CUDA, std::string("session kernel failed: ") + cudaGetErrorString(e));
+      }
+    }
+    cpu_relax();
+  }
+}
+
+int session_submit(dqn_handle* h, int op, int n) {
+  if (int rc = session_collect(h, nullptr)) return rc;       // at most one command in flight
+  const double now = host_now();
+  if (h->session_active && now - h->session_last_cmd > 0.010) {
+    // the kernel leaves by itself after ~30 ms of silence; past 10 ms do not race it: retire it and start a fresh one
+    if (int rc = session_stop(h)) return rc;
+  }
+  if (!h->session_active) if (int rc = session_launch(h)) return rc;
+  h->session_seq += 1;
+  __sync_synchronize();                                      // slot contents before the doorbell
+  h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)op << 8) | (unsigned long long)n;
+  h->session_outstanding = true;
+  h->session_last_cmd = now;
+  return DQN_OK;
+}
+}  // namespace
+
+extern "C++" {
+namespace {
+int session_stop(dqn_handle* h) {
+  if (!h->session_active) return DQN_OK;
+  CU(cudaSetDevice(h->cfg.device));
+  uint32_t payload = 0;
+  const bool was_step = h->session_outstanding && ((h->sess->doorbell >> 8) & 0xff) == kOpStep;
+  if (int rc = session_collect(h, &payload)) return rc;
+  if (was_step) memcpy(&h->session_last_loss, &payload, 4);
+  h->session_seq += 1;
+  __sync_synchronize();
+  h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)kOpExit << 8);
+  h->session_active = false;                                 // (a kernel that already timed out never reads the EXIT; harmless)
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+DQN_API int dqn_set_session(dqn_handle* h, int32_t enable) {
+  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
+  CU(cudaSetDevice(h->cfg.device));
+  if (!enable) {
+    if (int rc = session_stop(h)) return rc;
+    h->session_enabled = false;
+    return DQN_OK;
+  }
+  if (h->cfg.n_agents != 1) return fail(DQN_E_INVALID, "dqn_set_session: session mode serves a single-agent handle");
+  if (!h->sess) {
+    CU(cudaHostAlloc((void**)&h->sess, sizeof(SessionCtl), cudaHostAllocMapped));
+    memset((void*)h->sess, 0, sizeof(SessionCtl));
+    CU(cudaHostGetDevicePointer((void**)&h->sess_dev, (void*)h->sess, 0));
+  }
+  h->session_enabled = true;
+  return DQN_OK;
+}
+
 DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a, const float* r,
                                  const float* s2, const uint8_t* done, int32_t K, float* loss_out) {
-  if (int rc = check_agent(h, agent)) return rc;
+  if (int rc = check_agent_raw(h, agent)) return rc;
   if (K < 1) return fail(DQN_E_INVALID, "dqn_store_train_step: K must be >= 1");
   if (n < 0 || (n > 0 && (!s || !a || !r || !s2 || !done))) return fail(DQN_E_INVALID, "dqn_store_train_step: negative n or NULL array");
   CU(cudaSetDevice(h->cfg.device));
+  if (h->session_enabled && K == 1 && n <= kInlineMax) {
+    // served by the resident kernel: records into the mapped slot, ring the doorbell; no launch, no copy
+    if (size_of(h, agent) + n == 0) return fail(DQN_E_INVALID, "dqn_train_step: replay ring of an agent is empty");
+    if (int rc = session_collect(h, nullptr)) return rc;     // the slot is free once the previous command is answered
+    const int D = h->dims.D, recw = h->dims.recw;
+    uint32_t* slot = h->sess->rec;
+    for (int i = 0; i < (int)n; ++i) {
+      uint32_t* rec = slot + (size_t)i * recw;
+      memcpy(rec, s + (size_t)i * D, (size_t)D * 4);
+      memcpy(rec + D, s2 + (size_t)i * D, (size_t)D * 4);
+      memcpy(rec + 2 * D, a + i, 8);
+      memcpy(rec + 2 * D + 2, r + i, 4);
+      rec[2 * D + 3] = done[i] ? 1u : 0u;
+      for (int w = 2 * D + 4; w < recw; ++w) rec[w] = 0u;
+    }
+    if (int rc = session_submit(h, kOpStep, (int)n)) return rc;
+    AgentCtl& c = h->hctl[agent];
+    c.ring_counter += n;
+    c.train_steps += 1;
+    if (c.adam_count < 0x7fffffff) c.adam_count += 1;
+    if (loss_out) {
+      uint32_t bits = 0;
+      if (int rc = session_collect(h, &bits)) return rc;
+      memcpy(&h->session_last_loss, &bits, 4);
+      *loss_out = h->session_last_loss;
+    }
+    return DQN_OK;
+  }
+  if (h->session_active) if (int rc = session_stop(h)) return rc;
   if (n > 0 && n <= kInlineMax && uses_cluster(h, 1)) {
     // the transitions ride in the kernel-parameter buffer: no H2D copy, no store launch
     InlineStore ist;
@@ -713,6 +871,25 @@ DQN_API int dqn_train_step_device_idx(dqn_handle* h, int32_t agent_begin, int32_
 }
 
 DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_out, int64_t* train_steps_out) {
+  if (int rc = check_agent_raw(h, agent)) return rc;
+  if (h->session_active && n <= 1) {
+    if (train_steps_out) *train_steps_out = h->hctl[agent].train_steps;
+    if (n == 0) return DQN_OK;
+    if (!loss_out || h->hctl[agent].train_steps < 1) return fail(DQN_E_INVALID, "dqn_get_losses: n must be <= min(train steps so far, 4096)");
+    if (h->session_outstanding) {
+      const bool was_step = ((h->sess->doorbell >> 8) & 0xff) == kOpStep;
+      uint32_t bits = 0;
+      if (int rc = session_collect(h, &bits)) return rc;
+      if (was_step) memcpy(&h->session_last_loss, &bits, 4);
+    }
+    if ((uint32_t)(h->mailbox[agent] >> 32) == (uint32_t)h->hctl[agent].train_steps) {   // also covers steps of earlier launches
+      const uint32_t bits = (uint32_t)h->mailbox[agent];
+      memcpy(loss_out, &bits, 4);
+    } else {
+      *loss_out = h->session_last_loss;
+    }
+    return DQN_OK;
+  }
   if (int rc = check_agent(h, agent)) return rc;
   const long long ts = h->hctl[agent].train_steps;
   if (train_steps_out) *train_steps_out = ts;
@@ -733,6 +910,7 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
 }
 
 DQN_API int dqn_sync_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end) {
+  if (h && h->session_active && agent_begin == 0 && agent_end == 1) return session_submit(h, kOpSync, 0);
   if (int rc = check_range(h, agent_begin, agent_end)) return rc;
   CU(cudaSetDevice(h->cfg.device));
   CU(launch_sync_target(h->stream, h->params, h->dims, agent_begin, agent_end - agent_begin));
@@ -860,6 +1038,18 @@ DQN_API int dqn_episode_get_state(dqn_handle* h, int32_t agent, dqn_episode_stat
 }
 
 DQN_API int dqn_act(dqn_handle* h, int32_t agent, const float* state, int32_t* action_out) {
+  if (int rc = check_agent_raw(h, agent)) return rc;
+  if (h->session_enabled) {
+    if (!state || !action_out) return fail(DQN_E_INVALID, "dqn_act: NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    if (int rc = session_collect(h, nullptr)) return rc;
+    memcpy((void*)h->sess->state, state, (size_t)h->dims.D * 4);
+    if (int rc = session_submit(h, kOpAct, 0)) return rc;
+    uint32_t act = 0;
+    if (int rc = session_collect(h, &act)) return rc;
+    *action_out = (int32_t)act;
+    return DQN_OK;
+  }
   if (int rc = check_agent(h, agent)) return rc;
   return dqn_act_batch(h, agent, agent + 1, state, action_out);
 }

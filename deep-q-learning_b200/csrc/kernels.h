@@ -20,6 +20,19 @@ struct TapsDev {
   int enabled;
 };
 
+// Session mode of the cluster train-step kernel: a block of MAPPED PINNED host memory through which a resident kernel
+// takes commands (no launch, no copy per command).  The host writes state / rec and then the doorbell; the kernel
+// answers in `response`.  At most one command is in flight.
+enum { kOpStep = 1, kOpAct = 2, kOpSync = 3, kOpExit = 4 };
+struct SessionCtl {
+  volatile unsigned long long doorbell;   // host -> device: (seq << 16) | (op << 8) | n
+  volatile unsigned long long response;   // device -> host: (seq << 32) | payload (loss bits / action)
+  volatile unsigned long long closed;     // device -> host: written once when the kernel leaves (next seq it would have served)
+  unsigned long long pad[5];
+  float state[16];                        // ACT: the state
+  uint32_t rec[16 * 40];                  // STEP: n records in the ring's AoS layout, stride dims.recw words
+};
+
 struct TrainArgs {
   float* params;              // [n_agents][4][PK], packed layout (common.cuh)
   AgentCtl* ctl;              // [n_agents]
@@ -29,6 +42,8 @@ struct TrainArgs {
                                       //   of the launch's last step, one 8-byte store -- the host can poll it
   const long long* idx;       // device i64 [n_sel][K][B] or nullptr (Philox)
   const EpisodeCtl* gate;     // nullptr, or per-agent episode state: only agents with gate[agent].train_flag step
+  SessionCtl* sess;           // nullptr, or (cluster kernel, one agent) the session block: serve commands until EXIT / idle
+  unsigned long long sess_first_seq;   // sequence number of the first command this launch serves
   Dims dims;
   unsigned long long seed;
   int agent_begin;

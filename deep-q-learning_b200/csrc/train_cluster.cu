@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include "act_device.cuh"
 #include "common.cuh"
 #include "kernels.h"
 #include "tile_ops.cuh"
@@ -43,7 +44,7 @@ constexpr int NPC = 4;            // slice parameters per thread: one 16-byte ch
 
 struct CLay {
   int pW2, pWh, PS, SL;
-  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oScr, oMeta, oDummy, oRed, oStage, total;
+  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oScr, oMeta, oDummy, oRed, oCmd, oStage, total;
 };
 
 __host__ __device__ inline CLay make_clayout(int D, int recw) {
@@ -68,6 +69,7 @@ __host__ __device__ inline CLay make_clayout(int D, int recw) {
   L.oMeta = o; o += R * 4;
   L.oDummy = o; o += 4;
   L.oRed = o; o += 64;
+  L.oCmd = o; o += 8;
   L.oStage = o; o += R * recw;
   L.total = o;
   return L;
@@ -95,6 +97,22 @@ __device__ __forceinline__ void cluster_barrier_after_local_stores() {
 #endif
 }
 
+// ---- session ("serve") mode: the kernel stays resident and takes commands from mapped host memory (kernels.h) ----
+__device__ __forceinline__ unsigned long long ld_sys_u64(const volatile unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_u64(volatile unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr long long kIdleCycles = 60000000;   // ~30 ms at 1.965 GHz without a command: write back and exit on its own
+
 template <int A>
 __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArgs args, const InlineStore ist) {
   extern __shared__ __align__(16) float sm[];
@@ -121,6 +139,8 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   float* const Scr = sm + L.oScr;     // [4 parts][8 c][48 forward rows]
   float* const Meta = sm + L.oMeta;   // [16][4]
   float* const Red = sm + L.oRed;     // [0] this CTA's loss share, [8..11] Adam bias corrections, [16..31] head-bias partials
+  volatile unsigned long long* const CmdWord = reinterpret_cast<volatile unsigned long long*>(sm + L.oCmd);   // session: (seq << 16 | op << 8 | n), written by rank 0
+  volatile int* const Cmd = reinterpret_cast<volatile int*>(sm + L.oCmd + 2);                                // session: op, n for the whole CTA
   float* const Stage = sm + L.oStage;
 
   float* const gW = args.params + (size_t)agent * 4 * PK;
@@ -165,8 +185,10 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     __threadfence();
     __syncthreads();
   }
-  const long long rc = rc0 + ist.n;
-  const long long size = rc < args.dims.N ? rc : args.dims.N;
+  long long rc = rc0 + ist.n;
+  long long size = rc < args.dims.N ? rc : args.dims.N;
+  SessionCtl* const sess = args.sess;
+  const bool serve = sess != nullptr;
   const int ntiles = (B + BT - 1) / BT;
   const float fB = (float)B;
   const int cpr = recw >> 2;
@@ -216,12 +238,87 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   double pb1 = ctl->pb1, pb2 = ctl->pb2;    // b1**count, b2**count carried across launches (thread 0 uses them)
 
   PHASE_CLOCK(1);
-  prefetch(0, 0);
+  if (!serve) prefetch(0, 0);
   // (no cluster barrier here: the first remote access comes after the first step's cluster barrier, which every CTA
   //  reaches only after its own shared memory is initialised)
   PHASE_CLOCK(2);
 
-  for (int kstep = 0; kstep < args.K; ++kstep) {
+  // ---- session mode -------------------------------------------------------------------------------------------------
+  // Rank 0 polls the doorbell in mapped host memory and forwards each command word to the four CTAs' shared memory, so
+  // the whole cluster takes the same decision (including the idle time-out).  Commands: STEP = n ReplayBuffer.add +
+  // one Agent._step (records read from the host slot), ACT = greedy action for one state (rank 0), SYNC = theta^- :=
+  // theta, EXIT.  The host has at most one command in flight.
+  unsigned long long next_seq = args.sess_first_seq;
+  bool wt_dirty = false;
+  volatile unsigned long long* CmdWordR[CS];
+#pragma unroll
+  for (int c = 0; c < CS; ++c) CmdWordR[c] = cluster.map_shared_rank(const_cast<unsigned long long*>(CmdWord), c);
+  if (serve) {
+    if (t == 0) *CmdWord = 0ull;
+    cluster.sync();                      // every CTA's command word exists before rank 0 may store into it
+  }
+
+  int kstep = 0;
+  for (;; ++kstep) {
+    if (!serve && kstep >= args.K) break;
+    if (serve) {
+      int op, n;
+      for (;;) {                         // commands that are not a train step are handled right here
+        if (t == 0) {
+          unsigned long long w;
+          if (rank == 0) {
+            const long long c0 = clock64();
+            for (;;) {
+              w = ld_sys_u64(&sess->doorbell);
+              if ((w >> 16) == next_seq) break;
+              if (clock64() - c0 > kIdleCycles) { w = (next_seq << 16) | ((unsigned long long)kOpExit << 8); break; }
+            }
+#pragma unroll
+            for (int c = 0; c < CS; ++c) *CmdWordR[c] = w;
+          } else {
+            // rank 0 answers ACT on its own and may already have forwarded a later command: ACTs can be skipped here
+            // (every other command holds rank 0 at a cluster barrier until this CTA has taken it)
+            do { w = *CmdWord; } while ((w >> 16) < next_seq);
+          }
+          Cmd[0] = (int)((w >> 8) & 0xff);
+          Cmd[1] = (int)(w & 0xff);
+          Cmd[2] = (int)((w >> 16) - next_seq);
+        }
+        __syncthreads();
+        op = Cmd[0]; n = Cmd[1];
+        next_seq += (unsigned long long)Cmd[2];
+        __syncthreads();
+        if (op == kOpAct) {              // compute_action (q_learning_functions.py:67-73) from the resident weights
+          if (rank == 0 && warp == 0) {
+            if (lane < D) Stage[lane] = __uint_as_float(ld_sys_u32(reinterpret_cast<const volatile uint32_t*>(sess->state) + lane));
+            __syncwarp();
+            const int best = warp_greedy_action(W, D, A, Stage, nullptr);
+            if (lane == 0) st_sys_u64(&sess->response, (next_seq << 32) | (unsigned long long)(uint32_t)best);
+          }
+          __syncthreads();
+          ++next_seq;
+        } else if (op == kOpSync) {      // Agent._update_target_model (q_agent.py:143-144) on every replica
+          for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) { const float4 w4 = ld4(W + 4 * p4); st4(Wt + 4 * p4, w4.x, w4.y, w4.z, w4.w); }
+          wt_dirty = true;
+          cluster_barrier_after_local_stores();     // every CTA has taken the command before rank 0 can forward the next one
+          if (rank == 0 && t == 0) st_sys_u64(&sess->response, next_seq << 32);
+          ++next_seq;
+        } else {
+          break;
+        }
+      }
+      if (op != kOpStep) break;          // EXIT (or the idle time-out)
+      // ReplayBuffer.add x n: every CTA copies the same records from the host slot into the ring (benign identical race)
+      for (int w = t; w < n * recw; w += NT) {
+        const int i = w / recw, c = w - i * recw;
+        ring[(size_t)((rc + i) % args.dims.N) * recw + c] = ld_sys_u32(sess->rec + w);
+      }
+      __threadfence();
+      __syncthreads();
+      rc += n;
+      size = rc < args.dims.N ? rc : args.dims.N;
+      prefetch(kstep, 0);
+    }
     if (t == 0) {
       if (count0 + kstep < 0x7fffffff) { pb1 *= (double)b1; pb2 *= (double)b2; }
       Red[8 + 2 * (kstep & 1)] = 1.0f - (float)pb1;
@@ -246,7 +343,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       }
       __syncthreads();
       if (tile + 1 < ntiles) prefetch(kstep, tile + 1);
-      else if (kstep + 1 < args.K) prefetch(kstep + 1, 0);
+      else if (!serve && kstep + 1 < args.K) prefetch(kstep + 1, 0);
 
       // ---- forward, all 48 forward rows at once (threads 0..191: 12 row tiles x 16 column tiles) ----
       const int ct = t & 15, rt = t >> 4;
@@ -479,12 +576,14 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     if (rank == 0 && t == 0) {
       const float loss = (((Redr[0][0] + Redr[1][0]) + Redr[2][0]) + Redr[3][0]) / fB;
       args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
-      if (kstep == args.K - 1)
-        args.loss_mailbox[agent] = ((unsigned long long)(uint32_t)(step0 + args.K) << 32) | __float_as_uint(loss);
+      if (serve || kstep == args.K - 1)
+        args.loss_mailbox[agent] = ((unsigned long long)(uint32_t)(step0 + kstep + 1) << 32) | __float_as_uint(loss);
+      if (serve) st_sys_u64(&sess->response, (next_seq << 32) | __float_as_uint(loss));
       if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
     }
     cluster_barrier_after_local_stores();    // every slice of theta_{t+1} is in its owner's replica; nobody reads the partial gradients any more
-    if (kstep + 1 < args.K) {
+    if (serve) ++next_seq;
+    if (serve || kstep + 1 < args.K) {
       // all-gather (pull): the three slices the peers own, 16-byte DSMEM loads.  Peers rewrite their slices only after
       // the next step's first cluster barrier, which this CTA reaches after these loads.
       const int pp = 4 * t;
@@ -499,19 +598,22 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     }
   }  // steps
   PHASE_CLOCK(6);
+  if (serve) cluster_barrier_after_local_stores();   // peers may still be pulling this CTA's weight slice of the last step
 
   // ---- write back this CTA's slice (the last cluster barrier above was the last DSMEM access: CTAs may exit freely) ----
   if (owner) {
+    if (wt_dirty) *reinterpret_cast<float4*>(gWt + pown) = ld4(Wt + pown);
     *reinterpret_cast<float4*>(gW + pown) = ld4(W + pown);
     *reinterpret_cast<float4*>(gM + pown) = make_float4(mreg[0], mreg[1], mreg[2], mreg[3]);
     *reinterpret_cast<float4*>(gV + pown) = make_float4(vreg[0], vreg[1], vreg[2], vreg[3]);
   }
   if (rank == 0 && t == 0) {
-    ctl->train_steps = step0 + args.K;
-    if (ist.n > 0) ctl->ring_counter = rc;
-    const long long c = (long long)count0 + args.K;
+    ctl->train_steps = step0 + kstep;
+    if (ist.n > 0 || serve) ctl->ring_counter = rc;
+    const long long c = (long long)count0 + kstep;
     ctl->adam_count = c > 0x7fffffffLL ? 0x7fffffff : (int)c;
     ctl->pb1 = pb1; ctl->pb2 = pb2;
+    if (serve) { __threadfence_system(); st_sys_u64(&sess->closed, next_seq); }
   }
   PHASE_CLOCK(7);
 }

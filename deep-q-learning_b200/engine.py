@@ -19,7 +19,7 @@ def _f32(a):
 
 class DqnEngine:
     def __init__(self, obs_dim, num_actions, buffer_size, batch_size, gamma, optimizer, n_agents=1,
-                 seed=0, device=0, hidden=(32, 64), agent_id_base=0, step_kernel=None):
+                 seed=0, device=0, hidden=(32, 64), agent_id_base=0, step_kernel=None, session=False):
         import torch   # allocator + stream only
 
         self.lib = _lib.load()
@@ -58,6 +58,8 @@ class DqnEngine:
         _lib.check(self.lib.dqn_create(C.byref(cfg), C.byref(h)))
         self.h = h
         self._cfg = cfg
+        if session:       # resident kernel serving add+step / act / sync commands from mapped host memory (single agent)
+            _lib.check(self.lib.dqn_set_session(self.h, 1))
         self._loss1 = np.empty(1, np.float32)
         self._loss1_ptr = _lib.ptr(self._loss1)
 
@@ -73,6 +75,9 @@ class DqnEngine:
             self.close()
         except Exception:
             pass
+
+    def set_session(self, enable):
+        _lib.check(self.lib.dqn_set_session(self.h, 1 if enable else 0))
 
     def synchronize(self):
         _lib.check(self.lib.dqn_synchronize(self.h))

@@ -44,7 +44,7 @@ class ParamAgent(Agent):
                  max_episodes, max_steps, training_start, back_up_frequency, reward_to_reach, num_actions,
                  saving_directory, monitoring=False, gamma=0., epsilon=0., epsilon_decay_rate=0.,
                  min_epsilon=0., replace_frequency=0, batch_size=0, train_frequency=0,
-                 *, gamma_mode="frozen", device=0, seed=0):
+                 *, gamma_mode="frozen", device=0, seed=0, session=False):
         if gamma_mode not in ("frozen", "live"):
             raise ValueError("gamma_mode must be 'frozen' (reference behaviour) or 'live'")
         self._gamma_mode = gamma_mode
@@ -52,7 +52,7 @@ class ParamAgent(Agent):
                          gamma, epsilon, epsilon_decay_rate, min_epsilon, max_episodes, max_steps,
                          training_start, batch_size, train_frequency, back_up_frequency, replace_frequency,
                          reward_to_reach, num_actions, saving_directory, monitoring, verbose=0,
-                         device=device, seed=seed)
+                         device=device, seed=seed, session=session)
 
     @property
     def max_episodes(self):

@@ -173,6 +173,13 @@ DQN_API int dqn_train_step(dqn_handle* h, int32_t agent_begin, int32_t agent_end
 #define DQN_MAX_INLINE_STORE 16
 DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a, const float* r,
                                  const float* s2, const uint8_t* done, int32_t K, float* loss_out);
+/* Session mode (single-agent handles): ONE resident launch of the cluster kernel keeps theta / theta^- / Adam state in
+ * shared memory and serves the agent's per-env-step calls from commands in mapped host memory -- no launch and no copy
+ * per call: dqn_store_train_step (n <= 16, K = 1), dqn_act, dqn_sync_target(h, 0, 1), dqn_get_losses(n <= 1).  This is
+ * the reference's env loop (q_agent.py:174-189: _policy -> add -> _step) without a kernel launch on its path.  The
+ * kernel is started on demand, leaves by itself after ~30 ms without a command (state written back), and any other
+ * entry point ends the session first.  While it is resident the handle's stream is occupied. */
+DQN_API int dqn_set_session(dqn_handle* h, int32_t enable);
 /* Same, explicit indices already on the device (i64[n_sel*K*B]) -- no host copy, enqueue only. */
 DQN_API int dqn_train_step_device_idx(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K,
                               const int64_t* idx_dev);

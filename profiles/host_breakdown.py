@@ -1,7 +1,7 @@
 import time, numpy as np, sys, os
 sys.path.insert(0, os.getcwd())
 import bench, dqn_b200, torch
-agent, data = bench.build_agent(dqn_b200, 0, 0)
+agent, data = bench.build_agent(dqn_b200, 0, 0, session='--no-session' not in sys.argv)
 eng = agent._engine; rb = agent._replay_buffer
 s,a,r,s2,d = [x[:40000] for x in data]
 a_py=[int(x) for x in a]; r_py=[float(x) for x in r]; d_py=[bool(x) for x in d]
