@@ -2,6 +2,7 @@
 // No compute happens on the host; every entry point either moves bytes or launches a kernel.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <time.h>
 #include <string.h>
 
@@ -133,6 +134,7 @@ struct dqn_handle {
   SessionCtl* sess;             // mapped pinned host memory (nullptr until enabled)
   SessionCtl* sess_dev;         // device alias
   bool session_enabled, session_active, session_outstanding;
+  bool session_no_lease;        // diagnostics (dqn_set_session(h, 2)): never retire the kernel early, rely on the re-send path
   unsigned long long session_seq;       // sequence number of the last command published
   float session_last_loss;
   double session_last_cmd;      // host clock (s) of the last command: the kernel leaves after ~30 ms of silence
@@ -249,7 +251,7 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   if (e != cudaSuccess) { cudaFreeHost(h->pinned); if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaHostAlloc(mapped) failed"); }
   memset((void*)h->mailbox, 0, sizeof(unsigned long long) * cfg->n_agents);
   h->sess = nullptr; h->sess_dev = nullptr;
-  h->session_enabled = h->session_active = h->session_outstanding = false;
+  h->session_enabled = h->session_active = h->session_outstanding = h->session_no_lease = false;
   h->session_seq = 0; h->session_last_loss = 0.f; h->session_last_cmd = 0.0;
   h->slot_next = 0;
   for (int i = 0; i < kSlots; ++i) cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming);
@@ -690,12 +692,12 @@ void cpu_relax() {
 #endif
 }
 
-int session_launch(dqn_handle* h) {
+int session_launch(dqn_handle* h, unsigned long long first_seq) {
   TrainArgs ta;
   memset(&ta, 0, sizeof ta);
   ta.params = h->params; ta.ctl = h->ctl; ta.rings = h->rings; ta.loss_ring = h->loss_ring; ta.loss_mailbox = h->mailbox_dev;
   ta.dims = h->dims; ta.seed = h->cfg.seed; ta.agent_begin = 0; ta.agent_id_base = h->cfg.agent_id_base; ta.n_sel = 1; ta.K = 0;
-  ta.sess = h->sess_dev; ta.sess_first_seq = h->session_seq + 1;
+  ta.sess = h->sess_dev; ta.sess_first_seq = first_seq;
   CU(launch_train_cluster(h->stream, ta, nullptr));
   h->session_active = true;
   h->session_last_cmd = host_now();
@@ -718,7 +720,7 @@ int session_collect(dqn_handle* h, uint32_t* payload_out) {
       const cudaError_t e = cudaStreamQuery(h->stream);
       if (e == cudaSuccess) {                       // the kernel has left (idle time-out) ...
         if ((uint32_t)(h->sess->response >> 32) == want) continue;      // ... after answering
-        if (int rc = session_launch(h)) return rc;                       // ... without seeing the command: serve it again
+        if (int rc = session_launch(h, h->session_seq)) return rc;      // ... without seeing the command: a fresh launch serves it
       } else if (e != cudaErrorNotReady) {
         h->session_active = false; h->session_outstanding = false;
         return fail(DQN_E_CUDA, std::string("session kernel failed: ") + cudaGetErrorString(e));
@@ -728,20 +730,23 @@ int session_collect(dqn_handle* h, uint32_t* payload_out) {
   }
 }
 
-int session_submit(dqn_handle* h, int op, int n) {
+// Make the session ready for the next command: the previous one answered, a live kernel.  The caller then writes the
+// payload stamped with session_seq + 1 and publishes.
+int session_prepare(dqn_handle* h) {
   if (int rc = session_collect(h, nullptr)) return rc;       // at most one command in flight
-  const double now = host_now();
-  if (h->session_active && now - h->session_last_cmd > 0.010) {
+  if (h->session_active && !h->session_no_lease && host_now() - h->session_last_cmd > 0.010) {
     // the kernel leaves by itself after ~30 ms of silence; past 10 ms do not race it: retire it and start a fresh one
     if (int rc = session_stop(h)) return rc;
   }
-  if (!h->session_active) if (int rc = session_launch(h)) return rc;
+  if (!h->session_active) if (int rc = session_launch(h, h->session_seq + 1)) return rc;
+  return DQN_OK;
+}
+void session_publish(dqn_handle* h, int op, int n) {
   h->session_seq += 1;
-  __sync_synchronize();                                      // slot contents before the doorbell
+  __sync_synchronize();                                      // payload before the doorbell
   h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)op << 8) | (unsigned long long)n;
   h->session_outstanding = true;
-  h->session_last_cmd = now;
-  return DQN_OK;
+  h->session_last_cmd = host_now();
 }
 }  // namespace
 
@@ -779,6 +784,7 @@ DQN_API int dqn_set_session(dqn_handle* h, int32_t enable) {
     CU(cudaHostGetDevicePointer((void**)&h->sess_dev, (void*)h->sess, 0));
   }
   h->session_enabled = true;
+  h->session_no_lease = enable == 2;
   return DQN_OK;
 }
 
@@ -791,19 +797,21 @@ DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const 
   if (h->session_enabled && K == 1 && n <= kInlineMax) {
     // served by the resident kernel: records into the mapped slot, ring the doorbell; no launch, no copy
     if (size_of(h, agent) + n == 0) return fail(DQN_E_INVALID, "dqn_train_step: replay ring of an agent is empty");
-    if (int rc = session_collect(h, nullptr)) return rc;     // the slot is free once the previous command is answered
+    if (int rc = session_prepare(h)) return rc;              // previous command answered (the slot is free), kernel alive
     const int D = h->dims.D, recw = h->dims.recw;
-    uint32_t* slot = h->sess->rec;
+    const unsigned long long stamp = ((h->session_seq + 1) & 0xffffffffull) << 32;     // the command's sequence number
+    volatile unsigned long long* slot = h->sess->stamped;
     for (int i = 0; i < (int)n; ++i) {
-      uint32_t* rec = slot + (size_t)i * recw;
+      uint32_t rec[kInlineWords];
+      memset(rec, 0, sizeof rec);
       memcpy(rec, s + (size_t)i * D, (size_t)D * 4);
       memcpy(rec + D, s2 + (size_t)i * D, (size_t)D * 4);
       memcpy(rec + 2 * D, a + i, 8);
       memcpy(rec + 2 * D + 2, r + i, 4);
       rec[2 * D + 3] = done[i] ? 1u : 0u;
-      for (int w = 2 * D + 4; w < recw; ++w) rec[w] = 0u;
+      for (int w = 0; w < recw; ++w) slot[(size_t)i * recw + w] = stamp | rec[w];
     }
-    if (int rc = session_submit(h, kOpStep, (int)n)) return rc;
+    session_publish(h, kOpStep, (int)n);
     AgentCtl& c = h->hctl[agent];
     c.ring_counter += n;
     c.train_steps += 1;
@@ -910,7 +918,11 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
 }
 
 DQN_API int dqn_sync_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end) {
-  if (h && h->session_active && agent_begin == 0 && agent_end == 1) return session_submit(h, kOpSync, 0);
+  if (h && h->session_active && agent_begin == 0 && agent_end == 1) {
+    if (int rc = session_prepare(h)) return rc;
+    session_publish(h, kOpSync, 0);
+    return DQN_OK;
+  }
   if (int rc = check_range(h, agent_begin, agent_end)) return rc;
   CU(cudaSetDevice(h->cfg.device));
   CU(launch_sync_target(h->stream, h->params, h->dims, agent_begin, agent_end - agent_begin));
@@ -1042,9 +1054,14 @@ DQN_API int dqn_act(dqn_handle* h, int32_t agent, const float* state, int32_t* a
   if (h->session_enabled) {
     if (!state || !action_out) return fail(DQN_E_INVALID, "dqn_act: NULL argument");
     CU(cudaSetDevice(h->cfg.device));
-    if (int rc = session_collect(h, nullptr)) return rc;
-    memcpy((void*)h->sess->state, state, (size_t)h->dims.D * 4);
-    if (int rc = session_submit(h, kOpAct, 0)) return rc;
+    if (int rc = session_prepare(h)) return rc;
+    const unsigned long long stamp = ((h->session_seq + 1) & 0xffffffffull) << 32;
+    for (int k = 0; k < h->dims.D; ++k) {
+      uint32_t bits;
+      memcpy(&bits, state + k, 4);
+      h->sess->stamped[k] = stamp | bits;
+    }
+    session_publish(h, kOpAct, 0);
     uint32_t act = 0;
     if (int rc = session_collect(h, &act)) return rc;
     *action_out = (int32_t)act;

@@ -29,8 +29,9 @@ struct SessionCtl {
   volatile unsigned long long response;   // device -> host: (seq << 32) | payload (loss bits / action)
   volatile unsigned long long closed;     // device -> host: written once when the kernel leaves (next seq it would have served)
   unsigned long long pad[5];
-  float state[16];                        // ACT: the state
-  uint32_t rec[16 * 40];                  // STEP: n records in the ring's AoS layout, stride dims.recw words
+  // payload, one 8-byte unit per 32-bit word: (low 32 bits of seq) << 32 | word.  STEP: n records in the ring's AoS
+  // layout, stride dims.recw words; ACT: the D floats of the state.  A unit is valid when its stamp is the command's.
+  volatile unsigned long long stamped[16 * 40];
 };
 
 struct TrainArgs {

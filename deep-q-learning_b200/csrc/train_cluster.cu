@@ -264,22 +264,54 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     if (serve) {
       int op, n;
       for (;;) {                         // commands that are not a train step are handled right here
-        if (t == 0) {
-          unsigned long long w;
-          if (rank == 0) {
+        if (rank == 0) {
+          // Warp 0 polls.  Every poll also reads the first 128 stamped payload units (seq << 32 | word), so that when the
+          // doorbell shows the command its payload -- up to 128 words: 5 records at D <= 10, or the state of an ACT --
+          // has arrived in the same PCIe round trip; a unit whose stamp is not the command's is re-read.
+          if (warp == 0) {
+            unsigned long long w = 0ull, u[4];
             const long long c0 = clock64();
             for (;;) {
-              w = ld_sys_u64(&sess->doorbell);
-              if ((w >> 16) == next_seq) break;
-              if (clock64() - c0 > kIdleCycles) { w = (next_seq << 16) | ((unsigned long long)kOpExit << 8); break; }
-            }
+              if (lane == 0) {
+                w = ld_sys_u64(&sess->doorbell);
+                if ((w >> 16) != next_seq && clock64() - c0 > kIdleCycles) w = (next_seq << 16) | ((unsigned long long)kOpExit << 8);
+              }
 #pragma unroll
-            for (int c = 0; c < CS; ++c) *CmdWordR[c] = w;
-          } else {
-            // rank 0 answers ACT on its own and may already have forwarded a later command: ACTs can be skipped here
-            // (every other command holds rank 0 at a cluster barrier until this CTA has taken it)
-            do { w = *CmdWord; } while ((w >> 16) < next_seq);
+              for (int q = 0; q < 4; ++q) u[q] = ld_sys_u64(&sess->stamped[lane + 32 * q]);
+              w = __shfl_sync(0xffffffffu, w, 0);
+              if ((w >> 16) == next_seq) break;
+            }
+            const int wop = (int)((w >> 8) & 0xff), wn = (int)(w & 0xff);
+            const int need = wop == kOpStep ? wn * recw : (wop == kOpAct ? D : 0);
+            for (int base = 0; base < need; base += 128) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int idx = base + lane + 32 * q;
+                if (idx < need) {
+                  unsigned long long x = base == 0 ? u[q] : ld_sys_u64(&sess->stamped[idx]);
+                  while ((uint32_t)(x >> 32) != (uint32_t)next_seq) x = ld_sys_u64(&sess->stamped[idx]);
+                  if (wop == kOpStep) {            // ReplayBuffer.add x n (replay_buffer.py:58-65)
+                    const int i = idx / recw, c = idx - i * recw;
+                    ring[(size_t)((rc + i) % args.dims.N) * recw + c] = (uint32_t)x;
+                  } else {
+                    Stage[idx] = __uint_as_float((uint32_t)x);
+                  }
+                }
+              }
+            }
+            __threadfence();                       // the records are in the ring before any CTA is told about the step
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < CS; ++c) *CmdWordR[c] = w;
+              Cmd[0] = wop; Cmd[1] = wn; Cmd[2] = 0;
+            }
           }
+        } else if (t == 0) {
+          // rank 0 answers ACT on its own and may already have forwarded a later command: ACTs can be skipped here
+          // (every other command holds rank 0 at a cluster barrier until this CTA has taken it)
+          unsigned long long w;
+          do { w = *CmdWord; } while ((w >> 16) < next_seq);
           Cmd[0] = (int)((w >> 8) & 0xff);
           Cmd[1] = (int)(w & 0xff);
           Cmd[2] = (int)((w >> 16) - next_seq);
@@ -289,9 +321,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         next_seq += (unsigned long long)Cmd[2];
         __syncthreads();
         if (op == kOpAct) {              // compute_action (q_learning_functions.py:67-73) from the resident weights
-          if (rank == 0 && warp == 0) {
-            if (lane < D) Stage[lane] = __uint_as_float(ld_sys_u32(reinterpret_cast<const volatile uint32_t*>(sess->state) + lane));
-            __syncwarp();
+          if (rank == 0 && warp == 0) {          // the state is already in Stage (stamped payload)
             const int best = warp_greedy_action(W, D, A, Stage, nullptr);
             if (lane == 0) st_sys_u64(&sess->response, (next_seq << 32) | (unsigned long long)(uint32_t)best);
           }
@@ -308,14 +338,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         }
       }
       if (op != kOpStep) break;          // EXIT (or the idle time-out)
-      // ReplayBuffer.add x n: every CTA copies the same records from the host slot into the ring (benign identical race)
-      for (int w = t; w < n * recw; w += NT) {
-        const int i = w / recw, c = w - i * recw;
-        ring[(size_t)((rc + i) % args.dims.N) * recw + c] = ld_sys_u32(sess->rec + w);
-      }
-      __threadfence();
-      __syncthreads();
-      rc += n;
+      rc += n;                           // rank 0 has put the n records into the ring (above)
       size = rc < args.dims.N ? rc : args.dims.N;
       prefetch(kstep, 0);
     }

@@ -77,7 +77,7 @@ class DqnEngine:
             pass
 
     def set_session(self, enable):
-        _lib.check(self.lib.dqn_set_session(self.h, 1 if enable else 0))
+        _lib.check(self.lib.dqn_set_session(self.h, int(enable)))
 
     def synchronize(self):
         _lib.check(self.lib.dqn_synchronize(self.h))

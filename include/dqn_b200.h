@@ -179,7 +179,8 @@ DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const 
  * the reference's env loop (q_agent.py:174-189: _policy -> add -> _step) without a kernel launch on its path.  The
  * kernel is started on demand, leaves by itself after ~30 ms without a command (state written back), and any other
  * entry point ends the session first.  While it is resident the handle's stream is occupied. */
-DQN_API int dqn_set_session(dqn_handle* h, int32_t enable);
+DQN_API int dqn_set_session(dqn_handle* h, int32_t enable);   /* 0 off, 1 on, 2 on without the host-side lease (diagnostics:
+                                                                   a command sent to a timed-out kernel is re-sent to a fresh one) */
 /* Same, explicit indices already on the device (i64[n_sel*K*B]) -- no host copy, enqueue only. */
 DQN_API int dqn_train_step_device_idx(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t K,
                               const int64_t* idx_dev);

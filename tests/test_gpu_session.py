@@ -97,6 +97,25 @@ def test_session_survives_idle_timeouts_and_unserved_calls():
         dqn_b200.DqnEngine(9, 4, 100, 8, 0.9, dqn_b200.adam(1e-3), n_agents=2, session=True)   # single-agent handles only
 
 
+def test_command_sent_to_a_timed_out_kernel_is_resent():
+    """Without the host-side lease (dqn_set_session(h, 2)) a command can reach a kernel that has already left on its idle
+    time-out: the host notices the drained stream and serves the same command from a fresh launch."""
+    ref, ses = pair(seed=21)
+    ses.set_session(2)
+    rng = np.random.default_rng(2)
+    l0, l1 = np.zeros(1, np.float32), np.zeros(1, np.float32)
+    for it in range(6):
+        data = synthetic_transitions(rng, 3, 9, 4, done_p=0.2)
+        store_step(ref, data, l0)
+        store_step(ses, data, l1)
+        assert l0[0] == l1[0]
+        st = rng.standard_normal(9).astype(np.float32)
+        time.sleep(0.07)                                              # the resident kernel leaves (~30 ms idle)
+        assert ref.act(st) == ses.act(st)                             # ... and this command finds it gone
+        time.sleep(0.07)
+    same_state(ref, ses)
+
+
 def test_agent_dropin_with_session():
     """Agent(session=True): _policy / add / _step / _update_target_model through the resident kernel == the plain Agent."""
     import asyncio
