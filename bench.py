@@ -471,6 +471,54 @@ def run_population(args):
         dist.destroy_process_group()
 
 
+def run_replay(args):
+    """Replay path alone, HBM-bound: 16M-slot ring (1.5 GB >> L2), 1M transitions per launch.  store = ReplayBuffer.add x 1M
+    (SoA device arrays -> AoS ring), gather = sample_batch with Philox indices (ring -> the reference's five SoA arrays)."""
+    import ctypes as C
+    import torch
+    import dqn_b200
+    device = torch.device("cuda:0")
+    torch.cuda.set_device(device)
+    ring, nb = 16 * 2**20, 2**20
+    eng = dqn_b200.DqnEngine(D, A, ring, B, GAMMA, dqn_b200.adamw(LR), seed=0, device=0)
+    lib, chk = eng.lib, dqn_b200.pkg._lib.check
+    g = torch.Generator(device=device); g.manual_seed(0)
+    src = [torch.randn(nb, D, generator=g, device=device), torch.randint(0, A, (nb,), generator=g, device=device, dtype=torch.int64),
+           torch.randn(nb, generator=g, device=device), torch.randn(nb, D, generator=g, device=device),
+           (torch.rand(nb, generator=g, device=device) < 0.01).to(torch.uint8)]
+    out = [torch.empty_like(t) for t in src]
+    sp, op = [C.c_void_p(t.data_ptr()) for t in src], [C.c_void_p(t.data_ptr()) for t in out]
+    for _ in range(ring // nb):                                   # fill the ring once (also the warm-up of the store kernel)
+        chk(lib.dqn_store_device(eng.h, 0, nb, *sp))
+    for i in range(max(args.warmup, 3)):
+        chk(lib.dqn_sample_batch_device(eng.h, 0, None, i, nb, *op))
+    steps = max(min(args.steps, 200), 10)
+    flush_l2(torch, device)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    with ClockSampler(0) as clk:
+        e[0].record()
+        for i in range(steps):
+            chk(lib.dqn_sample_batch_device(eng.h, 0, None, 100 + i, nb, *op))
+        e[1].record()
+        for i in range(steps):
+            chk(lib.dqn_store_device(eng.h, 0, nb, *sp))
+        e[2].record()
+        torch.cuda.synchronize(device)
+    tg, ts = e[0].elapsed_time(e[1]) * 1e-3 / steps, e[1].elapsed_time(e[2]) * 1e-3 / steps
+    peak, peak_src = measured_peaks()
+    gbs_g, gbs_s = nb * 2 * REC_BYTES_ALGO / tg / 1e9, nb * 2 * REC_BYTES_ALGO / ts / 1e9
+    print(json.dumps({
+        "metric": "replay_samples_per_sec", "value": nb / tg, "unit": "samples/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": tg * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "replay path alone: 16M-slot ring (1.5 GB), 1M Philox-indexed samples per launch (sample_batch), 1M transitions per store",
+                   "obs_dim": D, "l2": "ring 1.5 GB >> 126 MB L2; 512 MB flush before the timed region"},
+        "clocks": clk.summary(), "gpu_launches": 2 * steps, "replay_stores_per_sec": nb / ts,
+        "roofline": {"bound": "hbm", "achieved": gbs_g, "peak": peak, "unit": "GB/s", "frac": gbs_g / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "replay_gather_kernel", "algorithmic_bytes_per_launch": nb * 2 * REC_BYTES_ALGO,
+                     "note": "77 B read + 77 B written per sample (reference dtypes); records are 96-byte AoS, so a random sample moves 3 sectors "
+                             "= 96 B of DRAM for 77 B; store kernel: %.0f GB/s algorithmic (%.3f of peak)" % (gbs_s, gbs_s / peak)}}))
+
+
 def run_episodes(args):
     """The reference's whole per-env-step loop (q_agent.py:174-203) for a population, on the device: epsilon-greedy policy ->
     (synthetic vectorised env) -> observe (store + episode bookkeeping + train gate) -> gated train step + hard sync.
@@ -690,7 +738,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid (ncu): only the fused timed region, no e2e / extras / cpu baseline; not a bench value")
-    ap.add_argument("--workload", default="single", choices=["single", "population", "dp", "per", "episodes"])
+    ap.add_argument("--workload", default="single", choices=["single", "population", "dp", "per", "episodes", "replay"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--hidden", type=int, default=1024)
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tc3xtf32"])
@@ -725,6 +773,8 @@ def main():
         return run_per(args)
     if args.workload == "episodes":
         return run_episodes(args)
+    if args.workload == "replay":
+        return run_replay(args)
     run_single(args)
 
 
