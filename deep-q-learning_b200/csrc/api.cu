@@ -1,60 +1,22 @@
 // api.cu -- the C ABI of include/dqn_b200.h: handle management, host<->device staging, launches.
 // No compute happens on the host; every entry point either moves bytes or launches a kernel.
-#include <math.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <time.h>
-#include <string.h>
-
-#include <string>
-#include <vector>
-
-#include "../../include/dqn_b200.h"
-#include "common.cuh"
-#include "kernels.h"
+// (Session mode lives in api_session.cu, the device-side episode loop in api_episode.cu.)
+#include "handle.h"
 
 using namespace dqn;
 
 namespace {
-
 thread_local std::string g_err;
-
-int fail(int code, const std::string& msg) {
+}  // namespace
+namespace dqn {
+int host_fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
-}  // namespace
-namespace dqn {
 void set_last_error(const char* msg) { g_err = msg; }
-}
+}  // namespace dqn
+
 namespace {
-
-#define CU(expr)                                                                                   \
-  do {                                                                                             \
-    cudaError_t _e = (expr);                                                                       \
-    if (_e != cudaSuccess) {                                                                       \
-      char _b[512];                                                                                \
-      snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-      return fail(DQN_E_CUDA, _b);                                                                 \
-    }                                                                                              \
-  } while (0)
-
-constexpr size_t kStageBytes = 8u << 20;
-constexpr size_t kPinnedBytes = 128u << 10;   // [0,64K): ring of store slots; [64K,128K): bounce for synchronous calls
-constexpr size_t kSlotBytes = 2u << 10;
-constexpr int kSlots = 32;
-constexpr size_t kBounceOff = 64u << 10;
-constexpr size_t kBounceBytes = 64u << 10;
-
-size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-struct Carve {
-  size_t params, ctl, ep, rings, loss, stage, taps, total;
-};
-
-struct TapsOff {
-  size_t idx, q, nq, nqt, maxa, tgt, loss, grads, bytes;
-};
 
 TapsOff taps_layout(const Dims& d) {
   TapsOff t;
@@ -108,66 +70,9 @@ int validate(const dqn_config* cfg, Dims* d) {
 
 }  // namespace
 
-struct dqn_handle {
-  dqn_config cfg;
-  int step_kernel, sm_count;
-  Dims dims;
-  cudaStream_t stream;
-  uint8_t* arena;
-  bool own_arena;
-  Carve cv;
-  TapsOff to;
-  float* params;
-  AgentCtl* ctl;
-  uint32_t* rings;
-  float* loss_ring;
-  uint8_t* stage;
-  uint8_t* taps;
-  uint8_t* pinned;
-  uint8_t* bounce;              // pinned + kBounceOff
-  volatile unsigned long long* mailbox;   // mapped pinned host memory, [n_agents]: (train_steps << 32) | loss bits of each
-  unsigned long long* mailbox_dev;        //   agent's last launch (one 8-byte store by the kernel); device alias
-  cudaEvent_t slot_ev[kSlots];  // completion of the H2D copy that last used each pinned store slot
-  int slot_next;
-  std::vector<AgentCtl> hctl;   // host mirror of the per-agent control blocks
-  // session mode (dqn_set_session): a resident cluster kernel serves STEP / ACT / SYNC commands from mapped host memory
-  SessionCtl* sess;             // mapped pinned host memory (nullptr until enabled)
-  SessionCtl* sess_dev;         // device alias
-  bool session_enabled, session_active, session_outstanding;
-  bool session_no_lease;        // diagnostics (dqn_set_session(h, 2)): never retire the kernel early, rely on the re-send path
-  unsigned long long session_seq;       // sequence number of the last command published
-  float session_last_loss;
-  double session_last_cmd;      // host clock (s) of the last command: the kernel leaves after ~30 ms of silence
-  EpisodeCtl* ep;               // device: per-agent episode-loop state (episode.cu)
-  struct HostEpisode { long long step_count; int training_start, train_frequency; bool configured, pending_train; };
-  std::vector<HostEpisode> hep; // host mirror of what decides the train gate (it depends on counters only, never on data)
-};
-
 namespace {
 
-int session_stop(dqn_handle* h);     // defined with the other session functions below
-int check_agent_raw(const dqn_handle* h, int agent) {
-  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
-  if (agent < 0 || agent >= h->cfg.n_agents) return fail(DQN_E_INVALID, "agent index out of range");
-  return DQN_OK;
-}
-// Every entry point that is not served by a running session first ends it (the resident kernel owns the agent's
-// parameters in shared memory and occupies the stream): the state is written back and the stream drained.
-int check_agent(dqn_handle* h, int agent) {
-  if (int rc = check_agent_raw(h, agent)) return rc;
-  return h->session_active ? session_stop(h) : DQN_OK;
-}
-int check_range(dqn_handle* h, int b, int e) {
-  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
-  if (b < 0 || e > h->cfg.n_agents || b >= e) return fail(DQN_E_INVALID, "agent range out of bounds or empty");
-  return h->session_active ? session_stop(h) : DQN_OK;
-}
 uint32_t* ring_of(dqn_handle* h, int agent) { return h->rings + (size_t)agent * (size_t)h->dims.N * h->dims.recw; }
-long long size_of(const dqn_handle* h, int agent) {
-  const long long c = h->hctl[agent].ring_counter;
-  return c < h->dims.N ? c : h->dims.N;
-}
-
 struct SoA {   // carve of the staging buffer into the five transition arrays for n transitions
   float* s; long long* a; float* r; float* s2; uint8_t* done;
 };
@@ -588,8 +493,11 @@ bool uses_cluster(const dqn_handle* h, int n_sel) {
   return h->step_kernel == DQN_STEP_CLUSTER || (h->step_kernel == DQN_STEP_AUTO && 4 * n_sel <= h->sm_count);
 }
 
-int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, dqn_debug_taps* taps, const InlineStore* ist = nullptr,
-                 const EpisodeCtl* gate = nullptr) {
+}  // namespace
+extern "C++" {
+namespace dqn {
+int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, dqn_debug_taps* taps, const InlineStore* ist,
+                 const EpisodeCtl* gate) {
   const int n_sel = e - b;
   for (int ag = b; ag < e; ++ag) {
     if (size_of(h, ag) == 0 && !(ist && ist->n > 0)) return fail(DQN_E_INVALID, "dqn_train_step: replay ring of an agent is empty");
@@ -641,7 +549,8 @@ int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, d
   }
   return DQN_OK;
 }
-}  // namespace
+}  // namespace dqn
+}  // extern "C++"
 
 namespace {
 // Loss of the agent's most recent launch without a stream synchronisation: the kernel's last store is
@@ -676,117 +585,6 @@ int wait_mailbox(dqn_handle* h, int agent, float* loss_out) {
   }
 }
 }  // namespace
-
-// ---------------------------------------------------------------------------------------------------------------
-// session mode: one resident launch of the cluster kernel serves the agent's per-env-step calls
-// ---------------------------------------------------------------------------------------------------------------
-namespace {
-double host_now() {
-  timespec ts;
-  clock_gettime(CLOCK_MONOTONIC, &ts);
-  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
-}
-void cpu_relax() {
-#if defined(__x86_64__)
-  __builtin_ia32_pause();
-#endif
-}
-
-int session_launch(dqn_handle* h, unsigned long long first_seq) {
-  TrainArgs ta;
-  memset(&ta, 0, sizeof ta);
-  ta.params = h->params; ta.ctl = h->ctl; ta.rings = h->rings; ta.loss_ring = h->loss_ring; ta.loss_mailbox = h->mailbox_dev;
-  ta.dims = h->dims; ta.seed = h->cfg.seed; ta.agent_begin = 0; ta.agent_id_base = h->cfg.agent_id_base; ta.n_sel = 1; ta.K = 0;
-  ta.sess = h->sess_dev; ta.sess_first_seq = first_seq;
-  CU(launch_train_cluster(h->stream, ta, nullptr));
-  h->session_active = true;
-  h->session_last_cmd = host_now();
-  return DQN_OK;
-}
-
-// wait for the answer to the command in flight (if any); a command that a timed-out kernel never saw is re-sent to a
-// fresh launch
-int session_collect(dqn_handle* h, uint32_t* payload_out) {
-  if (!h->session_outstanding) return DQN_OK;
-  const uint32_t want = (uint32_t)h->session_seq;
-  for (unsigned long spin = 1;; ++spin) {
-    const unsigned long long v = h->sess->response;
-    if ((uint32_t)(v >> 32) == want) {
-      if (payload_out) *payload_out = (uint32_t)v;
-      h->session_outstanding = false;
-      return DQN_OK;
-    }
-    if ((spin & 0x3fff) == 0) {
-      const cudaError_t e = cudaStreamQuery(h->stream);
-      if (e == cudaSuccess) {                       // the kernel has left (idle time-out) ...
-        if ((uint32_t)(h->sess->response >> 32) == want) continue;      // ... after answering
-        if (int rc = session_launch(h, h->session_seq)) return rc;      // ... without seeing the command: a fresh launch serves it
-      } else if (e != cudaErrorNotReady) {
-        h->session_active = false; h->session_outstanding = false;
-        return fail(DQN_E_CUDA, std::string("session kernel failed: ") + cudaGetErrorString(e));
-      }
-    }
-    cpu_relax();
-  }
-}
-
-// Make the session ready for the next command: the previous one answered, a live kernel.  The caller then writes the
-// payload stamped with session_seq + 1 and publishes.
-int session_prepare(dqn_handle* h) {
-  if (int rc = session_collect(h, nullptr)) return rc;       // at most one command in flight
-  if (h->session_active && !h->session_no_lease && host_now() - h->session_last_cmd > 0.010) {
-    // the kernel leaves by itself after ~30 ms of silence; past 10 ms do not race it: retire it and start a fresh one
-    if (int rc = session_stop(h)) return rc;
-  }
-  if (!h->session_active) if (int rc = session_launch(h, h->session_seq + 1)) return rc;
-  return DQN_OK;
-}
-void session_publish(dqn_handle* h, int op, int n) {
-  h->session_seq += 1;
-  __sync_synchronize();                                      // payload before the doorbell
-  h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)op << 8) | (unsigned long long)n;
-  h->session_outstanding = true;
-  h->session_last_cmd = host_now();
-}
-}  // namespace
-
-extern "C++" {
-namespace {
-int session_stop(dqn_handle* h) {
-  if (!h->session_active) return DQN_OK;
-  CU(cudaSetDevice(h->cfg.device));
-  uint32_t payload = 0;
-  const bool was_step = h->session_outstanding && ((h->sess->doorbell >> 8) & 0xff) == kOpStep;
-  if (int rc = session_collect(h, &payload)) return rc;
-  if (was_step) memcpy(&h->session_last_loss, &payload, 4);
-  h->session_seq += 1;
-  __sync_synchronize();
-  h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)kOpExit << 8);
-  h->session_active = false;                                 // (a kernel that already timed out never reads the EXIT; harmless)
-  CU(cudaStreamSynchronize(h->stream));
-  return DQN_OK;
-}
-}  // namespace
-}  // extern "C++"
-
-DQN_API int dqn_set_session(dqn_handle* h, int32_t enable) {
-  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
-  CU(cudaSetDevice(h->cfg.device));
-  if (!enable) {
-    if (int rc = session_stop(h)) return rc;
-    h->session_enabled = false;
-    return DQN_OK;
-  }
-  if (h->cfg.n_agents != 1) return fail(DQN_E_INVALID, "dqn_set_session: session mode serves a single-agent handle");
-  if (!h->sess) {
-    CU(cudaHostAlloc((void**)&h->sess, sizeof(SessionCtl), cudaHostAllocMapped));
-    memset((void*)h->sess, 0, sizeof(SessionCtl));
-    CU(cudaHostGetDevicePointer((void**)&h->sess_dev, (void*)h->sess, 0));
-  }
-  h->session_enabled = true;
-  h->session_no_lease = enable == 2;
-  return DQN_OK;
-}
 
 DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const float* s, const int64_t* a, const float* r,
                                  const float* s2, const uint8_t* done, int32_t K, float* loss_out) {
@@ -953,99 +751,6 @@ DQN_API int dqn_act_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end,
     CU(cudaMemcpyAsync(actions_out, dact, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
-  return DQN_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// episode-loop control on the device (episode.cu): Agent._policy / one iteration of Agent._run_episode, batched
-// ---------------------------------------------------------------------------------------------------------------
-DQN_API int dqn_episode_configure(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const dqn_episode_config* cfgs, int32_t reset_counters) {
-  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
-  if (!cfgs) return fail(DQN_E_INVALID, "dqn_episode_configure: cfgs is NULL");
-  const int n = agent_end - agent_begin;
-  if ((size_t)n * sizeof(EpisodeCtl) > kStageBytes) return fail(DQN_E_INVALID, "dqn_episode_configure: too many agents for one call");
-  CU(cudaSetDevice(h->cfg.device));
-  std::vector<EpisodeCtl> cur(n);
-  CU(cudaMemcpyAsync(cur.data(), h->ep + agent_begin, (size_t)n * sizeof(EpisodeCtl), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  for (int i = 0; i < n; ++i) {
-    const dqn_episode_config& c = cfgs[i];
-    if (c.train_frequency < 1 || c.replace_frequency < 1 || c.max_steps < 1 || c.max_episodes < 1 || c.training_start < 0)
-      return fail(DQN_E_INVALID, "dqn_episode_configure: train_frequency, replace_frequency, max_steps, max_episodes must be >= 1 and training_start >= 0");
-    EpisodeCtl& e = cur[i];
-    e.epsilon = c.epsilon; e.eps_decay = c.epsilon_decay_rate; e.min_eps = c.min_epsilon; e.reward_to_reach = c.reward_to_reach;
-    e.max_episodes = c.max_episodes; e.max_steps = c.max_steps; e.training_start = c.training_start;
-    e.train_frequency = c.train_frequency; e.replace_frequency = c.replace_frequency;
-    dqn_handle::HostEpisode& m = h->hep[agent_begin + i];
-    if (reset_counters || !m.configured) {        // a fresh Agent.training() call: its locals restart (q_agent.py:210-211, :172-173)
-      e.step_count = 0; e.episode = 0; e.step_in_episode = 0; e.epi_reward = 0.0; e.finished = 0; e.train_flag = 0; e.sync_flag = 0;
-      m.step_count = 0; m.pending_train = false;
-      if (!m.configured) { e.window_len = 0; e.window_pos = 0; e.avg_reward = 0.0; e.last_epi_reward = 0.0; e.policy_calls = 0; }
-    }
-    m.training_start = c.training_start; m.train_frequency = c.train_frequency; m.configured = true;
-  }
-  CU(cudaMemcpyAsync(h->ep + agent_begin, cur.data(), (size_t)n * sizeof(EpisodeCtl), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return DQN_OK;
-}
-
-namespace {
-int check_configured(const dqn_handle* h, int b, int e, const char* who) {
-  for (int ag = b; ag < e; ++ag)
-    if (!h->hep[ag].configured) return fail(DQN_E_INVALID, std::string(who) + ": call dqn_episode_configure for these agents first");
-  return DQN_OK;
-}
-}  // namespace
-
-DQN_API int dqn_policy_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* states_dev, int32_t* actions_dev) {
-  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
-  if (int rc = check_configured(h, agent_begin, agent_end, "dqn_policy_batch")) return rc;
-  if (!states_dev || !actions_dev) return fail(DQN_E_INVALID, "dqn_policy_batch: NULL argument");
-  CU(cudaSetDevice(h->cfg.device));
-  CU(launch_policy(h->stream, h->params, h->dims, h->ep, agent_begin, agent_end - agent_begin, h->cfg.agent_id_base, h->cfg.seed,
-                   states_dev, actions_dev));
-  return DQN_OK;
-}
-
-DQN_API int dqn_observe_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* s_dev, const int32_t* a_dev,
-                              const float* r_dev, const float* s2_dev, const uint8_t* done_dev, uint8_t* episode_end_dev) {
-  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
-  if (int rc = check_configured(h, agent_begin, agent_end, "dqn_observe_batch")) return rc;
-  if (!s_dev || !a_dev || !r_dev || !s2_dev || !done_dev || !episode_end_dev) return fail(DQN_E_INVALID, "dqn_observe_batch: NULL argument");
-  CU(cudaSetDevice(h->cfg.device));
-  CU(launch_observe(h->stream, h->rings, h->ctl, h->ep, h->dims, agent_begin, agent_end - agent_begin, s_dev, a_dev, r_dev, s2_dev,
-                    done_dev, episode_end_dev));
-  for (int ag = agent_begin; ag < agent_end; ++ag) {     // the gate is a function of counters only: mirror it without a read-back
-    dqn_handle::HostEpisode& m = h->hep[ag];
-    h->hctl[ag].ring_counter += 1;
-    m.step_count += 1;
-    m.pending_train = size_of(h, ag) >= m.training_start && m.step_count % m.train_frequency == 0;
-  }
-  return DQN_OK;
-}
-
-DQN_API int dqn_train_flagged(dqn_handle* h, int32_t agent_begin, int32_t agent_end) {
-  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
-  if (int rc = check_configured(h, agent_begin, agent_end, "dqn_train_flagged")) return rc;
-  CU(cudaSetDevice(h->cfg.device));
-  bool any = false;
-  for (int ag = agent_begin; ag < agent_end; ++ag) any = any || h->hep[ag].pending_train;
-  if (any) if (int rc = train_common(h, agent_begin, agent_end, 1, nullptr, nullptr, nullptr, h->ep)) return rc;
-  for (int ag = agent_begin; ag < agent_end; ++ag) h->hep[ag].pending_train = false;
-  CU(launch_episode_post(h->stream, h->params, h->dims, h->ep, agent_begin, agent_end - agent_begin));
-  return DQN_OK;
-}
-
-DQN_API int dqn_episode_get_state(dqn_handle* h, int32_t agent, dqn_episode_state* out) {
-  if (int rc = check_agent(h, agent)) return rc;
-  if (!out) return fail(DQN_E_INVALID, "dqn_episode_get_state: out is NULL");
-  CU(cudaSetDevice(h->cfg.device));
-  EpisodeCtl e;
-  CU(cudaMemcpyAsync(&e, h->ep + agent, sizeof e, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  out->epsilon = e.epsilon; out->average_reward = e.avg_reward; out->last_episode_reward = e.last_epi_reward;
-  out->episode_reward = e.epi_reward; out->step_count = e.step_count; out->policy_calls = e.policy_calls;
-  out->episode = e.episode; out->step_in_episode = e.step_in_episode; out->window_len = e.window_len; out->finished = e.finished;
   return DQN_OK;
 }
 

@@ -1,0 +1,120 @@
+// api_session.cu -- host side of session mode (dqn_set_session): one resident launch of the cluster train-step kernel
+// (train_cluster.cu, "serve" loop) is fed commands through a block of mapped pinned host memory (SessionCtl, kernels.h).
+#include "handle.h"
+
+using namespace dqn;
+
+// ---------------------------------------------------------------------------------------------------------------
+// session mode: one resident launch of the cluster kernel serves the agent's per-env-step calls
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+double host_now() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void cpu_relax() {
+#if defined(__x86_64__)
+  __builtin_ia32_pause();
+#endif
+}
+
+int session_launch(dqn_handle* h, unsigned long long first_seq) {
+  TrainArgs ta;
+  memset(&ta, 0, sizeof ta);
+  ta.params = h->params; ta.ctl = h->ctl; ta.rings = h->rings; ta.loss_ring = h->loss_ring; ta.loss_mailbox = h->mailbox_dev;
+  ta.dims = h->dims; ta.seed = h->cfg.seed; ta.agent_begin = 0; ta.agent_id_base = h->cfg.agent_id_base; ta.n_sel = 1; ta.K = 0;
+  ta.sess = h->sess_dev; ta.sess_first_seq = first_seq;
+  CU(launch_train_cluster(h->stream, ta, nullptr));
+  h->session_active = true;
+  h->session_last_cmd = host_now();
+  return DQN_OK;
+}
+
+}  // namespace
+
+namespace dqn {
+// wait for the answer to the command in flight (if any); a command that a timed-out kernel never saw is re-sent to a
+// fresh launch
+int session_collect(dqn_handle* h, uint32_t* payload_out) {
+  if (!h->session_outstanding) return DQN_OK;
+  const uint32_t want = (uint32_t)h->session_seq;
+  for (unsigned long spin = 1;; ++spin) {
+    const unsigned long long v = h->sess->response;
+    if ((uint32_t)(v >> 32) == want) {
+      if (payload_out) *payload_out = (uint32_t)v;
+      h->session_outstanding = false;
+      return DQN_OK;
+    }
+    if ((spin & 0x3fff) == 0) {
+      const cudaError_t e = cudaStreamQuery(h->stream);
+      if (e == cudaSuccess) {                       // the kernel has left (idle time-out) ...
+        if ((uint32_t)(h->sess->response >> 32) == want) continue;      // ... after answering
+        if (int rc = session_launch(h, h->session_seq)) return rc;      // ... without seeing the command: a fresh launch serves it
+      } else if (e != cudaErrorNotReady) {
+        h->session_active = false; h->session_outstanding = false;
+        return fail(DQN_E_CUDA, std::string("session kernel failed: ") + cudaGetErrorString(e));
+      }
+    }
+    cpu_relax();
+  }
+}
+
+// Make the session ready for the next command: the previous one answered, a live kernel.  The caller then writes the
+// payload stamped with session_seq + 1 and publishes.
+int session_prepare(dqn_handle* h) {
+  if (int rc = session_collect(h, nullptr)) return rc;       // at most one command in flight
+  if (h->session_active && !h->session_no_lease && host_now() - h->session_last_cmd > 0.010) {
+    // the kernel leaves by itself after ~30 ms of silence; past 10 ms do not race it: retire it and start a fresh one
+    if (int rc = session_stop(h)) return rc;
+  }
+  if (!h->session_active) if (int rc = session_launch(h, h->session_seq + 1)) return rc;
+  return DQN_OK;
+}
+void session_publish(dqn_handle* h, int op, int n) {
+  h->session_seq += 1;
+  __sync_synchronize();                                      // payload before the doorbell
+  h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)op << 8) | (unsigned long long)n;
+  h->session_outstanding = true;
+  h->session_last_cmd = host_now();
+}
+
+int session_stop(dqn_handle* h) {
+  if (!h->session_active) return DQN_OK;
+  CU(cudaSetDevice(h->cfg.device));
+  uint32_t payload = 0;
+  const bool was_step = h->session_outstanding && ((h->sess->doorbell >> 8) & 0xff) == kOpStep;
+  if (int rc = session_collect(h, &payload)) return rc;
+  if (was_step) memcpy(&h->session_last_loss, &payload, 4);
+  h->session_seq += 1;
+  __sync_synchronize();
+  h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)kOpExit << 8);
+  h->session_active = false;                                 // (a kernel that already timed out never reads the EXIT; harmless)
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+}  // namespace dqn
+
+extern "C" {
+
+DQN_API int dqn_set_session(dqn_handle* h, int32_t enable) {
+  if (!h) return fail(DQN_E_INVALID, "handle is NULL");
+  CU(cudaSetDevice(h->cfg.device));
+  if (!enable) {
+    if (int rc = session_stop(h)) return rc;
+    h->session_enabled = false;
+    return DQN_OK;
+  }
+  if (h->cfg.n_agents != 1) return fail(DQN_E_INVALID, "dqn_set_session: session mode serves a single-agent handle");
+  if (!h->sess) {
+    CU(cudaHostAlloc((void**)&h->sess, sizeof(SessionCtl), cudaHostAllocMapped));
+    memset((void*)h->sess, 0, sizeof(SessionCtl));
+    CU(cudaHostGetDevicePointer((void**)&h->sess_dev, (void*)h->sess, 0));
+  }
+  h->session_enabled = true;
+  h->session_no_lease = enable == 2;
+  return DQN_OK;
+}
+
+
+}  // extern "C"
