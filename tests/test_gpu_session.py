@@ -16,6 +16,7 @@ _lib = dqn_b200.pkg._lib
 
 
 def pair(D=9, A=4, N=300, B=32, seed=5):
+    """(launch-per-call engine, session engine) with identical state."""
     theta = O.init_params(np.random.default_rng(seed), D, A, bias_std=0.05)
     out = []
     for session in (False, True):
@@ -95,6 +96,22 @@ def test_session_survives_idle_timeouts_and_unserved_calls():
     store_step(ses, synthetic_transitions(np.random.default_rng(1), 0, 9, 4), None)   # n = 0 is allowed
     with pytest.raises(dqn_b200.DqnError):
         dqn_b200.DqnEngine(9, 4, 100, 8, 0.9, dqn_b200.adam(1e-3), n_agents=2, session=True)   # single-agent handles only
+
+
+def test_session_large_payloads():
+    """D = 16 (160-byte records) and up to 16 adds per step: 640 payload units, i.e. several read rounds beyond the 128
+    units that ride along with the doorbell poll; A = 7, B = 130 (three tiles) for good measure."""
+    ref, ses = pair(D=16, A=7, N=200, B=130, seed=17)
+    rng = np.random.default_rng(3)
+    l0, l1 = np.zeros(1, np.float32), np.zeros(1, np.float32)
+    for it, n in enumerate([16, 16, 1, 9, 16, 5, 16, 13, 16, 2]):
+        data = synthetic_transitions(rng, n, 16, 7, done_p=0.3)
+        store_step(ref, data, l0)
+        store_step(ses, data, l1)
+        assert l0[0] == l1[0], f"iteration {it}"
+        st = rng.standard_normal(16).astype(np.float32)
+        assert ref.act(st) == ses.act(st)
+    same_state(ref, ses)
 
 
 def test_command_sent_to_a_timed_out_kernel_is_resent():

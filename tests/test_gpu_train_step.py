@@ -93,6 +93,22 @@ def test_shapes_batches_optimisers(D, A, B, kind, gamma):
         compare_step(eng, ora, what=f"D{D} A{A} B{B} step{step}")
 
 
+def test_edge_sizes():
+    """Largest batch the ABI accepts (16 tiles of 64 rows), a one-slot ring, a ring smaller than the batch."""
+    eng, ora, rng = make_pair(D=8, A=4, B=1024, N=3000, n_fill=3000, lr=1e-3, seed=31)
+    compare_step(eng, ora, what="B=1024")
+    compare_step(eng, ora, what="B=1024 step 2")
+    eng, ora, rng = make_pair(D=9, A=4, B=16, N=1, n_fill=1, seed=32)            # every sample is the same transition
+    compare_step(eng, ora, what="N=1")
+    eng, ora, rng = make_pair(D=9, A=4, B=64, N=10, n_fill=25, seed=33)           # wrapped 2.5 times, size 10 < B
+    compare_step(eng, ora, what="N=10 < B")
+    with pytest.raises(dqn_b200.DqnError):
+        dqn_b200.DqnEngine(9, 4, 100, 1025, 0.99, dqn_b200.adam(1e-3))             # B > DQN_MAX_BATCH
+    empty = dqn_b200.DqnEngine(9, 4, 100, 8, 0.99, dqn_b200.adam(1e-3))
+    with pytest.raises(dqn_b200.DqnError):
+        empty.train_steps(1)                                                       # randint(0, 0) raises in the reference too
+
+
 def test_explicit_indices_and_duplicates():
     eng, ora, rng = make_pair(B=64)
     idx = rng.integers(0, 1500, 64)
