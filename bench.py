@@ -346,6 +346,25 @@ def run_single(args):
         s1.record()
         torch.cuda.synchronize(device)
         extras["k1_steps_per_sec"] = k1 / (s0.elapsed_time(s1) * 1e-3)
+        # the reference's whole inner loop (q_agent.py:174-189) with a greedy policy call per env transition:
+        # train_frequency x (_policy -> add) + _step + loss read
+        nloop = 2000
+        agent._epsilon = 0.0
+        states1 = s[:TRAIN_FREQUENCY * (nloop + 8)].reshape(-1, 1, D)
+        def env_loop(n, off):
+            for i in range(n):
+                for j in range(TRAIN_FREQUENCY):
+                    k = off + i * TRAIN_FREQUENCY + j
+                    act = agent._policy(states1[k])
+                    rb.add(s[k], act, r_py[k], s2[k], d_py[k])
+                agent._step()
+                eng.last_loss()
+        env_loop(8, 0)
+        c0 = time.perf_counter()
+        env_loop(nloop, 8 * TRAIN_FREQUENCY)
+        eng.synchronize()
+        extras["env_loop_steps_per_sec"] = nloop / (time.perf_counter() - c0)
+        extras["env_loop_note"] = "%d x (greedy Agent._policy + ReplayBuffer.add) + Agent._step + loss per step, wall clock" % TRAIN_FREQUENCY
         extras["replay_gather"] = bench_gather(torch, dqn_b200, eng, device, peak)
     except Exception as ex:       # extras never invalidate the main line
         extras["error"] = repr(ex)
