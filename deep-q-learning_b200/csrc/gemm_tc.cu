@@ -126,14 +126,33 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
 template <bool MNMAJOR>
 __device__ __forceinline__ void ld_tile(const float* __restrict__ G, int ld, int mn0, int k0, int p, float4 (&v)[8]) {
   if (!MNMAJOR) {
-    const float* src = G + (size_t)(mn0 + p) * ld + k0;
+    // coalesced: one instruction = 4 rows x 128 B (8 lanes per row); row_transpose() turns this into "thread = row"
+    const int w = p >> 5, lane = p & 31;
+    const float* src = G + (size_t)(mn0 + 32 * w + (lane >> 3)) * ld + k0 + 4 * (lane & 7);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(src + 4 * q);
+    for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(src + (size_t)(4 * i) * ld);
   } else {
     const int mq = p & 31, kb = p >> 5;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(G + (size_t)(k0 + kb + 4 * i) * ld + mn0 + 4 * mq);
   }
+}
+
+// K-major tiles are loaded coalesced (lane = (row % 4, 16-byte chunk)), but both consumers want "thread p owns row p":
+// tcgen05.st.32x32b writes one TMEM lane per thread, and the UMMA K-major layout is written conflict-free that way.
+// A row-per-thread global load touches 32 different 128-byte lines per instruction (32 L1 wavefronts instead of 4) and
+// made the kernel l1tex-bound (ncu: 70-88 % l1tex).  The transpose goes through a 4 KB per-warp staging area in shared
+// memory, 16-byte chunks XOR-swizzled by the row so that both the write and the read are conflict-free.
+__device__ __forceinline__ void row_transpose(float4 (&v)[8], uint8_t* stage_warp, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int R = 4 * i + (lane >> 3), c = lane & 7;
+    *reinterpret_cast<float4*>(stage_warp + R * 128 + ((c ^ (R & 7)) << 4)) = v[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(stage_warp + lane * 128 + ((q ^ (lane & 7)) << 4));
+  __syncwarp();
 }
 
 template <bool MNMAJOR>
@@ -247,8 +266,11 @@ gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* 
     // Two register sets alternate: the global loads of stage kt+2 are issued as soon as stage kt has been staged,
     // so load latency (~1 us under load) overlaps the split / store work and the slot waits of the other set.
     float4 va0[8], vb0[8], va1[8], vb1[8];
-    auto stage_out = [&](int kt, const float4 (&va)[8], const float4 (&vb)[8]) {
+    uint8_t* const xpose = reinterpret_cast<uint8_t*>(tmem_slot) + 64 + warp * 4096;   // per-warp transpose staging
+    auto stage_out = [&](int kt, float4 (&va)[8], float4 (&vb)[8]) {
       const int s = kt % kStages;
+      if constexpr (!A_MN) row_transpose(va, xpose, lane);
+      if constexpr (!B_MN) row_transpose(vb, xpose, lane);
       if (kt >= kStages) mbar_wait(smem_u32(&empty[s]), ((kt / kStages) - 1) & 1);   // slot drained by the MMAs
       uint8_t* st = tiles + s * kStageBytes;
       if constexpr (A_TMEM) st_a_tmem(va, tmem_d + 256u + (uint32_t)(s * 64), tmem_d + 256u + (uint32_t)(s * 64 + 32), tid);
@@ -361,7 +383,7 @@ template <bool A_MN, bool B_MN, int EPI>
 cudaError_t launch_tc(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                       const float* aux, int ldaux, int splitk) {
   constexpr int kATile = A_MN ? kTileMN : 0, kBTile = B_MN ? kTileMN : kTileK;
-  constexpr int smem = (A_MN ? 3 : 4) * (2 * kATile + 2 * kBTile) + 128;
+  constexpr int smem = (A_MN ? 3 : 4) * (2 * kATile + 2 * kBTile) + 256 + 4 * 4096;   // stages | barriers | transpose staging
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
