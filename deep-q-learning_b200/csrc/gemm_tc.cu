@@ -35,7 +35,7 @@ constexpr int kTileK = TM * TK * 4;            // bytes of a K-major operand til
 constexpr int kLboMN = 512;                    // stride between atoms along MN
 constexpr int kSboMN = 4 * kLboMN;             // stride between atoms along K (2048 B)
 constexpr int kTileMN = (TK / 4) * kSboMN;     // 16384 B
-constexpr int kNumThreads = 288;
+constexpr int kNumThreads = 384;             // 3 warpgroups: producers | epilogue | MMA issuer (+3 idle warps)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -263,9 +263,11 @@ gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* 
 
   if (warp < 4) {
     // ===================== producers =====================
-    // Two register sets alternate: the global loads of stage kt+2 are issued as soon as stage kt has been staged,
-    // so load latency (~1 us under load) overlaps the split / store work and the slot waits of the other set.
-    float4 va0[8], vb0[8], va1[8], vb1[8];
+    // Three register sets rotate: the global loads of stage kt+3 are issued as soon as stage kt has been staged, so
+    // ~3 stages (96 KB per SM) of loads are in flight and their latency (~1 us under load) overlaps the split / store
+    // work.  The registers come from the other warpgroups (setmaxnreg): the MMA warpgroup needs almost none.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    float4 va0[8], vb0[8], va1[8], vb1[8], va2[8], vb2[8];
     uint8_t* const xpose = reinterpret_cast<uint8_t*>(tmem_slot) + 64 + warp * 4096;   // per-warp transpose staging
     auto stage_out = [&](int kt, float4 (&va)[8], float4 (&vb)[8]) {
       const int s = kt % kStages;
@@ -283,17 +285,34 @@ gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* 
     ld_tile<A_MN>(A, lda, m0, kbeg, tid, va0);
     ld_tile<B_MN>(B, ldb, n0, kbeg, tid, vb0);
     if (nk > 1) { ld_tile<A_MN>(A, lda, m0, kbeg + TK, tid, va1); ld_tile<B_MN>(B, ldb, n0, kbeg + TK, tid, vb1); }
-    for (int kt = 0; kt < nk; kt += 2) {
-      stage_out(kt, va0, vb0);
-      if (kt + 2 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 2) * TK, tid, va0); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 2) * TK, tid, vb0); }
-      if (kt + 1 < nk) {
-        stage_out(kt + 1, va1, vb1);
-        if (kt + 3 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 3) * TK, tid, va1); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 3) * TK, tid, vb1); }
+    if constexpr (A_TMEM) {            // 4 shared-memory slots: three stages of loads in flight
+      if (nk > 2) { ld_tile<A_MN>(A, lda, m0, kbeg + 2 * TK, tid, va2); ld_tile<B_MN>(B, ldb, n0, kbeg + 2 * TK, tid, vb2); }
+      for (int kt = 0; kt < nk; kt += 3) {
+        stage_out(kt, va0, vb0);
+        if (kt + 3 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 3) * TK, tid, va0); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 3) * TK, tid, vb0); }
+        if (kt + 1 < nk) {
+          stage_out(kt + 1, va1, vb1);
+          if (kt + 4 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 4) * TK, tid, va1); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 4) * TK, tid, vb1); }
+        }
+        if (kt + 2 < nk) {
+          stage_out(kt + 2, va2, vb2);
+          if (kt + 5 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 5) * TK, tid, va2); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 5) * TK, tid, vb2); }
+        }
+      }
+    } else {                           // both operands in shared memory (3 slots): two stages in flight measure faster
+      for (int kt = 0; kt < nk; kt += 2) {
+        stage_out(kt, va0, vb0);
+        if (kt + 2 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 2) * TK, tid, va0); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 2) * TK, tid, vb0); }
+        if (kt + 1 < nk) {
+          stage_out(kt + 1, va1, vb1);
+          if (kt + 3 < nk) { ld_tile<A_MN>(A, lda, m0, kbeg + (kt + 3) * TK, tid, va1); ld_tile<B_MN>(B, ldb, n0, kbeg + (kt + 3) * TK, tid, vb1); }
+        }
       }
     }
-  } else if (warp == 8) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+  } else if (warp >= 8) {
+    // ===================== MMA issuer (one thread of warp 8; warps 9-11 only donate their registers) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 8 && lane == 0) {
       constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
       for (int kt = 0; kt < nk; ++kt) {
         const int s = kt % kStages;
