@@ -188,11 +188,20 @@ lb_head_kernel(const float* __restrict__ H2, const float* __restrict__ theta, co
   float acc[1 + kMaxA];
 #pragma unroll
   for (int c = 0; c <= kMaxA; ++c) acc[c] = 0.f;
-  for (int k = lane; k < H2n; k += 32) {
-    const float hv = h[k];
-    acc[0] = fmaf(hv, __ldg(Wv + k), acc[0]);
+  // lane l takes k = l, l + 32, ...: the activation row is read in 128-byte warp loads and the head weights (20 KB,
+  // L1-resident) with a 16-byte lane stride.  Eight activation loads are issued ahead of their FMAs: the kernel is an
+  // HBM reader (3 B x H2 x 4 bytes once) and needs the bytes in flight.
+  for (int k0 = lane; k0 < H2n; k0 += 256) {               // H2n is a multiple of 256
+    float hv[8];
 #pragma unroll
-    for (int j = 0; j < kMaxA; ++j) if (j < A) acc[1 + j] = fmaf(hv, __ldg(Wa + (size_t)k * A + j), acc[1 + j]);
+    for (int u = 0; u < 8; ++u) hv[u] = h[k0 + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + 32 * u;
+      acc[0] = fmaf(hv[u], __ldg(Wv + k), acc[0]);
+#pragma unroll
+      for (int j = 0; j < kMaxA; ++j) if (j < A) acc[1 + j] = fmaf(hv[u], __ldg(Wa + (size_t)k * A + j), acc[1 + j]);
+    }
   }
 #pragma unroll
   for (int c = 0; c <= kMaxA; ++c)
