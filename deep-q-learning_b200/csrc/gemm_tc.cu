@@ -5,12 +5,14 @@
 //
 // which restores ~2^-21 relative accuracy per product -- the fp32 parity bar -- at 1/3 of the TF32 rate.
 // One CTA computes a 128 x 128 tile with one tcgen05.mma (M=128, N=128, K=8) per 8 reduction elements:
-//   warps 0-3  producers: global fp32 -> registers -> {hi, lo} split -> shared memory in the UMMA
-//              canonical no-swizzle layout (K-major or MN-major core matrices), 3-stage mbarrier ring;
-//              the split IS the reason operands are staged by threads instead of TMA
+//   warps 0-3  producers: global fp32 (coalesced) -> registers -> {hi, lo} split -> shared memory in the UMMA
+//              canonical layout (K-major no-swizzle / MN-major SWIZZLE_128B_BASE32B) or TMEM, 3- or 4-slot mbarrier
+//              ring; the split IS the reason operands are staged by threads instead of TMA.  Up to three stages of
+//              loads are in flight in registers (setmaxnreg: 240 regs for this warpgroup)
 //   warps 4-7  epilogue: tcgen05.ld of the 128x128 fp32 accumulator (one TMEM lane per output row),
 //              fused bias+relu / relu'-mask / split-K partial store
 //   warp 8     TMEM allocation + single-thread MMA issue, tcgen05.commit onto the stage / accumulator barriers
+//   warps 9-11 idle: they only complete the third warpgroup so that it can give its registers away (setmaxnreg 40)
 // K-major A operands never touch shared memory: each producer thread owns one row of the A tile and writes its
 // hi / lo values straight into TMEM (tcgen05.st, lane = row), and the MMA takes A from TMEM (.ts form).  A 128x128x8
 // tf32 MMA with both operands in shared memory reads 8 KB per 64 cycles = the whole 128 B/clk shared-memory
