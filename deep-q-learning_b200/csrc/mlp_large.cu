@@ -29,25 +29,31 @@ __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.
 __global__ void __launch_bounds__(256)
 lb_layer1_kernel(const float* __restrict__ s, const float* __restrict__ s2, const float* __restrict__ theta,
                  const float* __restrict__ theta_t, float* __restrict__ H1, int B, int D, int H1n) {
-  const int j4 = blockIdx.x * blockDim.x + threadIdx.x;      // float4 column index
-  if (j4 * 4 >= H1n) return;
+  // A pure HBM writer (3 B x H1 x 4 bytes).  The block's 1024-column slice of [W1; b1] sits in shared memory, so a
+  // thread needs ~30 registers and eight blocks stay resident per SM: enough independent 16-byte stores in flight.
+  extern __shared__ __align__(16) float w1s[];                 // [D + 1][1024]
+  const int col0 = blockIdx.x * 1024;
   const int pass = blockIdx.z;                                 // 0: theta on s, 1: theta on s', 2: theta^- on s'
   const float* W1 = pass == 2 ? theta_t : theta;
-  const float* b1 = W1 + (size_t)D * H1n;
   const float* x = pass == 0 ? s : s2;
-  float4 w[kMaxD];
-#pragma unroll
-  for (int d = 0; d < kMaxD; ++d) if (d < D) w[d] = *reinterpret_cast<const float4*>(W1 + (size_t)d * H1n + 4 * j4);
-  const float4 bias = *reinterpret_cast<const float4*>(b1 + 4 * j4);
+  const int ncol = min(1024, H1n - col0);
+  for (int i = threadIdx.x; i < (D + 1) * (ncol >> 2); i += blockDim.x) {
+    const int d = i / (ncol >> 2), c4 = i - d * (ncol >> 2);
+    reinterpret_cast<float4*>(w1s)[d * 256 + c4] = *reinterpret_cast<const float4*>(W1 + (size_t)d * H1n + col0 + 4 * c4);   // row D = b1
+  }
+  __syncthreads();
+  const int j4 = threadIdx.x;
+  if (4 * j4 >= ncol) return;
+  const float4 bias = reinterpret_cast<const float4*>(w1s)[D * 256 + j4];
   for (int r = blockIdx.y; r < B; r += gridDim.y) {
     float4 acc = bias;
-#pragma unroll
-    for (int d = 0; d < kMaxD; ++d) if (d < D) {
+    for (int d = 0; d < D; ++d) {
       const float xv = __ldg(x + (size_t)r * D + d);
-      acc.x = fmaf(xv, w[d].x, acc.x); acc.y = fmaf(xv, w[d].y, acc.y); acc.z = fmaf(xv, w[d].z, acc.z); acc.w = fmaf(xv, w[d].w, acc.w);
+      const float4 w = reinterpret_cast<const float4*>(w1s)[d * 256 + j4];
+      acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y); acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
     }
     acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-    *reinterpret_cast<float4*>(H1 + ((size_t)pass * B + r) * H1n + 4 * j4) = acc;
+    *reinterpret_cast<float4*>(H1 + ((size_t)pass * B + r) * H1n + col0 + 4 * j4) = acc;
   }
 }
 
@@ -173,48 +179,70 @@ reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, 
 // ------------------------------------------------------------------------------------------------
 // head: Q = V + Adv - mean(Adv)  (dddqn.py:29-31).  One warp per row, rows [0,3B).
 // ------------------------------------------------------------------------------------------------
+constexpr int kHeadRows = 4;     // rows per warp: every head-weight load is reused for four activation rows
+
 __global__ void __launch_bounds__(256)
 lb_head_kernel(const float* __restrict__ H2, const float* __restrict__ theta, const float* __restrict__ theta_t,
                float* __restrict__ Q, int B, int H2n, int A, int offWv) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= 3 * B) return;
-  const float* th = row >= 2 * B ? theta_t : theta;
+  const int row0 = kHeadRows * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));   // 2B and 3B are multiples of 4
+  if (row0 >= 3 * B) return;
+  const float* th = row0 >= 2 * B ? theta_t : theta;
   const float* Wv = th + offWv;
   const float* bv = Wv + H2n;
   const float* Wa = bv + 1;
   const float* ba = Wa + (size_t)H2n * A;
-  const float* h = H2 + (size_t)row * H2n;
-  float acc[1 + kMaxA];
+  const float* h = H2 + (size_t)row0 * H2n;
+  float acc[kHeadRows][1 + kMaxA];
 #pragma unroll
-  for (int c = 0; c <= kMaxA; ++c) acc[c] = 0.f;
-  // lane l takes k = l, l + 32, ...: the activation row is read in 128-byte warp loads and the head weights (20 KB,
-  // L1-resident) with a 16-byte lane stride.  Eight activation loads are issued ahead of their FMAs: the kernel is an
-  // HBM reader (3 B x H2 x 4 bytes once) and needs the bytes in flight.
-  for (int k0 = lane; k0 < H2n; k0 += 256) {               // H2n is a multiple of 256
-    float hv[8];
+  for (int r = 0; r < kHeadRows; ++r)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) hv[u] = h[k0 + 32 * u];
+    for (int c = 0; c <= kMaxA; ++c) acc[r][c] = 0.f;
+  // lane l takes k = l, l + 32, ...: activation rows are read in 128-byte warp loads (16 of them in flight per lane);
+  // the head weights (20 KB, L1-resident) are loaded once per k and used for the four rows -- with one row per warp the
+  // five weight loads per activation load made the kernel L1-bound at 1.5 TB/s of what is a pure HBM read
+  // (3 B x H2 x 4 bytes once).
+  for (int k0 = lane; k0 < H2n; k0 += 128) {               // H2n is a multiple of 256
+    float hv[kHeadRows][4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int r = 0; r < kHeadRows; ++r)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) hv[r][u] = h[(size_t)r * H2n + k0 + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
       const int k = k0 + 32 * u;
-      acc[0] = fmaf(hv[u], __ldg(Wv + k), acc[0]);
+      const float wv = __ldg(Wv + k);
 #pragma unroll
-      for (int j = 0; j < kMaxA; ++j) if (j < A) acc[1 + j] = fmaf(hv[u], __ldg(Wa + (size_t)k * A + j), acc[1 + j]);
+      for (int r = 0; r < kHeadRows; ++r) acc[r][0] = fmaf(hv[r][u], wv, acc[r][0]);
+#pragma unroll
+      for (int j = 0; j < kMaxA; ++j) if (j < A) {
+        const float wa = __ldg(Wa + (size_t)k * A + j);
+#pragma unroll
+        for (int r = 0; r < kHeadRows; ++r) acc[r][1 + j] = fmaf(hv[r][u], wa, acc[r][1 + j]);
+      }
     }
   }
 #pragma unroll
-  for (int c = 0; c <= kMaxA; ++c)
+  for (int r = 0; r < kHeadRows; ++r)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-  if (lane == 0) {
-    const float val = acc[0] + bv[0];
+    for (int c = 0; c <= kMaxA; ++c)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], o);
+  if (lane < kHeadRows) {
+    float a[1 + kMaxA];
+#pragma unroll
+    for (int c = 0; c <= kMaxA; ++c) {                       // row `lane` of the four (static indexing only)
+      a[c] = acc[0][c];
+#pragma unroll
+      for (int r = 1; r < kHeadRows; ++r) if (lane == r) a[c] = acc[r][c];
+    }
+    const float val = a[0] + bv[0];
     float msum = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxA; ++j) if (j < A) { acc[1 + j] += ba[j]; msum += acc[1 + j]; }
+    for (int j = 0; j < kMaxA; ++j) if (j < A) { a[1 + j] += ba[j]; msum += a[1 + j]; }
     const float mean = msum / (float)A;
 #pragma unroll
-    for (int j = 0; j < kMaxA; ++j) if (j < A) Q[(size_t)row * A + j] = val + acc[1 + j] - mean;
+    for (int j = 0; j < kMaxA; ++j) if (j < A) Q[(size_t)(row0 + lane) * A + j] = val + a[1 + j] - mean;
   }
 }
 
@@ -413,14 +441,20 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
   const int offbv = offWv + H2n, offba = offbv + 1 + H2n * A;
   // ---- forward ----
   {
-    dim3 grid((H1n / 4 + 255) / 256, B < 1024 ? B : 1024, 3);
-    lb_layer1_kernel<<<grid, 256, 0, st>>>(ws.s, ws.s2, ws.theta, ws.theta_t, ws.H1, B, D, H1n);
+    dim3 grid((H1n + 1023) / 1024, B < 512 ? B : 512, 3);
+    const int smem = (D + 1) * 1024 * 4;                       // <= 68 KB
+    static bool configured = false;
+    if (!configured) {
+      LBCHK(cudaFuncSetAttribute(lb_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kMaxD + 1) * 1024 * 4));
+      configured = true;
+    }
+    lb_layer1_kernel<<<grid, 256, smem, st>>>(ws.s, ws.s2, ws.theta, ws.theta_t, ws.H1, B, D, H1n);
     LBCHK(cudaGetLastError());
   }
   LBCHK(lb_gemm(st, gemm_mode, kGemmNN_BiasRelu, 2 * B, H2n, H1n, ws.H1, H1n, ws.theta + offW2, H2n, ws.H2, H2n, ws.theta + offb2, 0, 1, ws));
   LBCHK(lb_gemm(st, gemm_mode, kGemmNN_BiasRelu, B, H2n, H1n, ws.H1 + (size_t)2 * B * H1n, H1n, ws.theta_t + offW2, H2n,
                 ws.H2 + (size_t)2 * B * H2n, H2n, ws.theta_t + offb2, 0, 1, ws));
-  lb_head_kernel<<<(3 * B + 7) / 8, 256, 0, st>>>(ws.H2, ws.theta, ws.theta_t, ws.Q, B, H2n, A, offWv);
+  lb_head_kernel<<<(3 * B / kHeadRows + 7) / 8, 256, 0, st>>>(ws.H2, ws.theta, ws.theta_t, ws.Q, B, H2n, A, offWv);
   LBCHK(cudaGetLastError());
   const int nblk = (B + 255) / 256;
   lb_targets_kernel<<<nblk, 256, 0, st>>>(ws.Q, ws.a, ws.r, ws.done, ws.dhd, ws.partial, B, A, gamma, inv_global_batch, taps);
