@@ -337,6 +337,7 @@ def run_single(args):
     extras = {}
     try:
         k1 = 2000
+        eng.set_session(0)                                         # K = 1 launches: one kernel launch per Agent._step()
         agent._steps(1)
         torch.cuda.synchronize(device)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -346,6 +347,7 @@ def run_single(args):
         s1.record()
         torch.cuda.synchronize(device)
         extras["k1_steps_per_sec"] = k1 / (s0.elapsed_time(s1) * 1e-3)
+        eng.set_session(0 if args.no_session else 1)
         # the reference's whole inner loop (q_agent.py:174-189) with a greedy policy call per env transition:
         # train_frequency x (_policy -> add) + _step + loss read
         nloop = 2000

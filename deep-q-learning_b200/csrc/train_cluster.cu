@@ -113,7 +113,9 @@ __device__ __forceinline__ void st_sys_u64(volatile unsigned long long* p, unsig
 }
 constexpr long long kIdleCycles = 60000000;   // ~30 ms at 1.965 GHz without a command: write back and exit on its own
 
-template <int A>
+// SERVE = false: K steps then write back (dqn_train_step*).  SERVE = true: session mode, commands until EXIT / idle.
+// Two instantiations so that the K-step form carries none of the command loop (it costs ~3 % of a fused step).
+template <int A, bool SERVE>
 __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArgs args, const InlineStore ist) {
   extern __shared__ __align__(16) float sm[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   long long rc = rc0 + ist.n;
   long long size = rc < args.dims.N ? rc : args.dims.N;
   SessionCtl* const sess = args.sess;
-  const bool serve = sess != nullptr;
+  constexpr bool serve = SERVE;
   const int ntiles = (B + BT - 1) / BT;
   const float fB = (float)B;
   const int cpr = recw >> 2;
@@ -642,17 +644,19 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
 }
 
 typedef void (*ClusterKernel)(const TrainArgs, const InlineStore);
-ClusterKernel pick_cluster_kernel(int A) {
+template <bool SERVE>
+ClusterKernel pick_cluster_kernel_t(int A) {
   switch (A) {
-    case 2: return dqn_train_cluster_kernel<2>;
-    case 3: return dqn_train_cluster_kernel<3>;
-    case 4: return dqn_train_cluster_kernel<4>;
-    case 5: return dqn_train_cluster_kernel<5>;
-    case 6: return dqn_train_cluster_kernel<6>;
-    case 7: return dqn_train_cluster_kernel<7>;
+    case 2: return dqn_train_cluster_kernel<2, SERVE>;
+    case 3: return dqn_train_cluster_kernel<3, SERVE>;
+    case 4: return dqn_train_cluster_kernel<4, SERVE>;
+    case 5: return dqn_train_cluster_kernel<5, SERVE>;
+    case 6: return dqn_train_cluster_kernel<6, SERVE>;
+    case 7: return dqn_train_cluster_kernel<7, SERVE>;
     default: return nullptr;
   }
 }
+ClusterKernel pick_cluster_kernel(int A, bool serve) { return serve ? pick_cluster_kernel_t<true>(A) : pick_cluster_kernel_t<false>(A); }
 
 }  // namespace
 
@@ -665,14 +669,18 @@ extern "C" __attribute__((visibility("default"))) int dqn_debug_phase_clocks(lon
 size_t train_cluster_smem_bytes(const Dims& d) { return (size_t)make_clayout(d.D, d.recw).total * sizeof(float); }
 
 cudaError_t train_cluster_prepare(const Dims& d) {
-  ClusterKernel k = pick_cluster_kernel(d.A);
-  if (!k) return cudaErrorInvalidValue;
-  return cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_cluster_smem_bytes(d));
+  for (int serve = 0; serve < 2; ++serve) {
+    ClusterKernel k = pick_cluster_kernel(d.A, serve != 0);
+    if (!k) return cudaErrorInvalidValue;
+    const cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_cluster_smem_bytes(d));
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_train_cluster(cudaStream_t st, const TrainArgs& args, const InlineStore* ist) {
   static const InlineStore none = {};
-  ClusterKernel k = pick_cluster_kernel(args.dims.A);
+  ClusterKernel k = pick_cluster_kernel(args.dims.A, args.sess != nullptr);
   if (!k) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(args.n_sel * CS));
