@@ -84,7 +84,8 @@ __device__ long long g_phase_clock[16];
 
 // Cluster barrier for this kernel's DSMEM protocol.  Everything the CTAs exchange is READ remotely (ld.shared::cluster)
 // from data its owner wrote with ordinary shared-memory stores: partial gradients, new weight slices, loss shares.
-// No CTA ever stores into another CTA's shared memory.  The stock cluster.sync() is arrive.release + wait.acquire and
+// No CTA ever stores training data into another CTA's shared memory (the one remote store in this file is the session
+// command word, a self-contained 8-byte value the receiver polls).  The stock cluster.sync() is arrive.release + wait.acquire and
 // costs a MEMBAR.ALL.GPU per call (~700 cycles, 12 % of a step in ncu).  Here the CTA barrier first drains the CTA's
 // own shared-memory stores (they are then in the SM's shared memory, which is what a remote load reads), and the
 // cluster arrive itself is relaxed.  -DDQN_CLUSTER_STRICT restores the release/acquire form.
