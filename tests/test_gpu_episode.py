@@ -125,3 +125,55 @@ def test_finished_flag_and_unconfigured_agents():
     assert s0["average_reward"] == 3.0 and s0["finished"] == 1                # average 3.0 > reward_to_reach 2.5
     assert s1["episode"] == 3 and s1["finished"] == 1 and s1["average_reward"] == 2.0   # ran out of episodes (flag is sticky)
     assert s0["epsilon"] == 0.25 and eng.buffer_state(0) == (6, 6)
+
+
+@pytest.mark.parametrize("case", ["basic", "early_stop", "loop_bound", "window"])
+def test_device_loop_follows_the_reference_training_traces(case):
+    """The device loop against traces of the reference's own ``Agent.training()`` (tests/golden/episode_ref_*.npz, produced
+    by oracle/make_golden_episode.py from the unmodified ``q_agent.py``): same reward / done stream -> it trains at the
+    same env steps, ends episodes at the same steps, decays epsilon to the same doubles, keeps the same reward window,
+    stores the same ring and raises `finished` where ``training()`` returned."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, f"episode_ref_{case}.npz"), allow_pickle=False)
+    cfg = {k[4:]: g[k].item() for k in g.files if k.startswith("cfg_")}
+    N, B = int(cfg["buffer_size"]), int(cfg["batch_size"])
+    eng = dqn_b200.DqnEngine(9, 4, N, B, cfg["gamma"], dqn_b200.adam(1e-3), seed=5)
+    theta = O.init_params(np.random.default_rng(0), 9, 4, bias_std=0.05)
+    eng.set_params(theta, 0, 0)
+    eng.set_params(theta, 0, 1)
+    eng.configure_episodes([dict(epsilon=cfg["epsilon"], epsilon_decay_rate=cfg["epsilon_decay_rate"], min_epsilon=cfg["min_epsilon"],
+                                 reward_to_reach=cfg["reward_to_reach"], max_episodes=int(cfg["max_episodes"]), max_steps=int(cfg["max_steps"]),
+                                 training_start=int(cfg["training_start"]), train_frequency=int(cfg["train_frequency"]),
+                                 replace_frequency=int(cfg["replace_frequency"]))])
+    dev = "cuda:0"
+    obs = torch.from_numpy(np.ascontiguousarray(g["observations"])).to(dev)
+    rew = torch.from_numpy(g["rewards"].astype(np.float32)).to(dev)          # multiples of 1/4: exact in float32
+    don = torch.from_numpy(g["dones"].astype(np.uint8)).to(dev)
+    trained_at, episode_len, eps_after, last_end, trained = [], [], [], 0, 0
+    for t in range(int(g["env_steps"])):
+        assert eng.episode_state(0)["finished"] == 0, "the reference was still running here"
+        a = eng.policy(obs[t:t + 1])
+        ended = eng.observe(obs[t:t + 1], a, rew[t:t + 1], obs[t + 1:t + 2], don[t:t + 1])
+        eng.train_flagged()
+        n = eng.train_step_count(0)
+        if n != trained:
+            trained_at.append(t + 1)
+            trained = n
+        if int(ended.cpu()[0]):
+            episode_len.append(t + 1 - last_end)
+            last_end = t + 1
+            eps_after.append(eng.episode_state(0)["epsilon"])
+    st = eng.episode_state(0)
+    assert trained_at == g["trained_at"].tolist()
+    assert episode_len == g["episode_len"].tolist()
+    assert np.array_equal(np.array(eps_after), g["eps_after"])                # bit-exact doubles
+    assert st["episode"] == int(g["episodes"]) and st["step_count"] == int(g["env_steps"]) and st["finished"] == 1
+    assert st["window_len"] == len(g["reward_history"]) and st["last_episode_reward"] == g["reward_history"][-1]
+    assert abs(st["average_reward"] - float(g["average_reward"])) <= 4e-16 * max(1.0, abs(float(g["average_reward"])))
+    s, a_, r, s2, d = eng.buffer_export(0)
+    assert eng.buffer_state(0)[0] == int(g["buffer_size_final"])
+    assert np.array_equal(r, g["ring_rewards"].astype(np.float32)) and np.array_equal(d, g["ring_dones"])
+    cnt, _, _ = eng.get_opt_state(0)
+    assert int(cnt) == len(g["trained_at"])
