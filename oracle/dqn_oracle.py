@@ -1,6 +1,7 @@
 """NumPy fp32 restatement of the reference's dueling double-DQN train step (oracle; test infra only).
 
-PARITY UNPINNED for this half -- see ``oracle/__init__.py``.  Every function cites the reference
+Pinned by ``tests/golden/train_ref_*.npz`` (the reference's own ``q_learning_functions.py`` / ``dddqn.py`` executed over
+``oracle/ref_shims``) -- see ``oracle/__init__.py``.  Every function cites the reference
 lines it restates (paths relative to ``/root/reference``).  Third-party arithmetic that is not in
 the reference tree (no version pinned by the reference; era: jax 0.3.x, dm-haiku 0.0.x,
 optax 0.1.x) is restated from the libraries' published semantics:

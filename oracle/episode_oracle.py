@@ -7,6 +7,9 @@ Follows ``General/QLearning/q_agent.py``: ``_policy`` ``:137-141``, one iteratio
 replace_frequency == 0``, epsilon decay ``:120-121``, the 50-entry reward window ``:123-126``) and the stop test
 of ``training`` ``:211, :219``.
 
+Pinned by ``tests/golden/episode_ref_*.npz``: traces of the reference's own ``Agent.training()`` run over
+``oracle/ref_shims`` with a scripted environment (``oracle/make_golden_episode.py``).
+
 Two things cannot follow the reference literally and are stated here instead:
 * the reference draws ``random.uniform(0, 1)`` and ``numpy.random.randint(0, A)`` from unseeded host RNGs
   (SURVEY 3.3).  The draws of policy call ``c`` of agent ``g`` are Philox4x32-10 outputs with counter
