@@ -156,7 +156,7 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   if (e != cudaSuccess) { cudaFreeHost(h->pinned); if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaHostAlloc(mapped) failed"); }
   memset((void*)h->mailbox, 0, sizeof(unsigned long long) * cfg->n_agents);
   h->sess = nullptr; h->sess_dev = nullptr;
-  h->session_enabled = h->session_active = h->session_outstanding = h->session_no_lease = false;
+  h->session_enabled = h->session_active = h->session_outstanding = h->session_no_lease = h->session_launch_blocked = false;
   h->session_seq = 0; h->session_last_loss = 0.f; h->session_last_cmd = 0.0;
   h->slot_next = 0;
   for (int i = 0; i < kSlots; ++i) cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming);
@@ -592,10 +592,14 @@ DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const 
   if (K < 1) return fail(DQN_E_INVALID, "dqn_store_train_step: K must be >= 1");
   if (n < 0 || (n > 0 && (!s || !a || !r || !s2 || !done))) return fail(DQN_E_INVALID, "dqn_store_train_step: negative n or NULL array");
   CU(cudaSetDevice(h->cfg.device));
+  int srv = DQN_OK;
   if (h->session_enabled && K == 1 && n <= kInlineMax) {
-    // served by the resident kernel: records into the mapped slot, ring the doorbell; no launch, no copy
     if (size_of(h, agent) + n == 0) return fail(DQN_E_INVALID, "dqn_train_step: replay ring of an agent is empty");
-    if (int rc = session_prepare(h)) return rc;              // previous command answered (the slot is free), kernel alive
+    srv = session_prepare(h);                                // previous command answered (the slot is free), kernel alive
+    if (srv < 0) return srv;
+  }
+  if (h->session_enabled && K == 1 && n <= kInlineMax && srv == DQN_OK) {
+    // served by the resident kernel: records into the mapped slot, ring the doorbell; no launch, no copy
     const int D = h->dims.D, recw = h->dims.recw;
     const unsigned long long stamp = ((h->session_seq + 1) & 0xffffffffull) << 32;     // the command's sequence number
     volatile unsigned long long* slot = h->sess->stamped;
@@ -717,9 +721,12 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
 
 DQN_API int dqn_sync_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end) {
   if (h && h->session_active && agent_begin == 0 && agent_end == 1) {
-    if (int rc = session_prepare(h)) return rc;
-    session_publish(h, kOpSync, 0);
-    return DQN_OK;
+    const int srv = session_prepare(h);
+    if (srv < 0) return srv;
+    if (srv == DQN_OK) {
+      session_publish(h, kOpSync, 0);
+      return DQN_OK;
+    }
   }
   if (int rc = check_range(h, agent_begin, agent_end)) return rc;
   CU(cudaSetDevice(h->cfg.device));
@@ -756,10 +763,14 @@ DQN_API int dqn_act_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end,
 
 DQN_API int dqn_act(dqn_handle* h, int32_t agent, const float* state, int32_t* action_out) {
   if (int rc = check_agent_raw(h, agent)) return rc;
+  int srv = DQN_OK;
   if (h->session_enabled) {
     if (!state || !action_out) return fail(DQN_E_INVALID, "dqn_act: NULL argument");
     CU(cudaSetDevice(h->cfg.device));
-    if (int rc = session_prepare(h)) return rc;
+    srv = session_prepare(h);
+    if (srv < 0) return srv;
+  }
+  if (h->session_enabled && srv == DQN_OK) {
     const unsigned long long stamp = ((h->session_seq + 1) & 0xffffffffull) << 32;
     for (int k = 0; k < h->dims.D; ++k) {
       uint32_t bits;

@@ -25,9 +25,13 @@ int session_launch(dqn_handle* h, unsigned long long first_seq) {
   ta.params = h->params; ta.ctl = h->ctl; ta.rings = h->rings; ta.loss_ring = h->loss_ring; ta.loss_mailbox = h->mailbox_dev;
   ta.dims = h->dims; ta.seed = h->cfg.seed; ta.agent_begin = 0; ta.agent_id_base = h->cfg.agent_id_base; ta.n_sel = 1; ta.K = 0;
   ta.sess = h->sess_dev; ta.sess_first_seq = first_seq;
+  const double t0 = host_now();
   CU(launch_train_cluster(h->stream, ta, nullptr));
   h->session_active = true;
   h->session_last_cmd = host_now();
+  // A launch call that returns only after the kernel's whole idle time-out means launches are synchronous here (a
+  // profiler serialising kernels): the resident kernel can never be sent a command.
+  h->session_launch_blocked = h->session_last_cmd - t0 > 0.020;
   return DQN_OK;
 }
 
@@ -68,7 +72,15 @@ int session_prepare(dqn_handle* h) {
     // the kernel leaves by itself after ~30 ms of silence; past 10 ms do not race it: retire it and start a fresh one
     if (int rc = session_stop(h)) return rc;
   }
-  if (!h->session_active) if (int rc = session_launch(h, h->session_seq + 1)) return rc;
+  if (!h->session_active) {
+    if (int rc = session_launch(h, h->session_seq + 1)) return rc;
+    if (h->session_launch_blocked) {           // fall back to one launch per call for the rest of this handle's life
+      h->session_active = false;
+      h->session_enabled = false;
+      CU(cudaStreamSynchronize(h->stream));
+      return kSessionUnavailable;
+    }
+  }
   return DQN_OK;
 }
 void session_publish(dqn_handle* h, int op, int n) {

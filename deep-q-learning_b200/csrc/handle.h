@@ -77,6 +77,7 @@ struct dqn_handle {
   dqn::SessionCtl* sess;             // mapped pinned host memory (nullptr until enabled)
   dqn::SessionCtl* sess_dev;         // device alias
   bool session_enabled, session_active, session_outstanding;
+  bool session_launch_blocked;  // the last session launch call returned only after the kernel had left (profiler)
   bool session_no_lease;        // diagnostics (dqn_set_session(h, 2)): never retire the kernel early, rely on the re-send path
   unsigned long long session_seq;       // sequence number of the last command published
   float session_last_loss;
@@ -90,6 +91,7 @@ namespace dqn {
 
 // session mode (api_session.cu)
 int session_stop(dqn_handle* h);                                  // answer in flight collected, EXIT, stream drained
+constexpr int kSessionUnavailable = 1;                            // session_prepare: launches are synchronous here, session mode switched off
 int session_prepare(dqn_handle* h);                               // previous command answered, a live kernel
 void session_publish(dqn_handle* h, int op, int n);               // payload already written with stamp session_seq + 1
 int session_collect(dqn_handle* h, uint32_t* payload_out);        // wait for the answer of the command in flight
