@@ -51,3 +51,56 @@ def test_kernel_reproduces_the_reference_sources(case):
     clear = (srt[:, -1] - srt[:, -2]) > 1e-4
     got = np.array([eng.act(s) for s in g["probe_states"]])
     assert clear.sum() > 50 and np.array_equal(got[clear], g["probe_actions"][clear])
+
+
+def _tree(flat_, D=9, A=4):
+    tree, o = {}, 0
+    for name, (fi, fo) in zip(O.MODULES, [(D, 32), (32, 64), (64, 1), (64, A)]):
+        tree[name] = {"w": flat_[o:o + fi * fo].reshape(fi, fo).copy(), "b": flat_[o + fi * fo:o + fi * fo + fo].copy()}
+        o += fi * fo + fo
+    return tree
+
+
+def _flat(tree):
+    return np.concatenate([np.ravel(tree[m][k]) for m in O.MODULES for k in ("w", "b")])
+
+
+@pytest.mark.parametrize("session", [False, True])
+def test_dropin_agent_entry_points_match_the_reference_agent(session):
+    """The drop-in ``Agent`` / ``ParamAgent`` (same constructor kwargs, ``add``, ``_step``, ``_update_target_model``,
+    ``inject``) against the reference's own objects doing the same calls (tests/golden/agent_step_ref.npz)."""
+    import asyncio
+    g = np.load(os.path.join(GOLDEN, "agent_step_ref.npz"), allow_pickle=False)
+    N, theta = int(g["N"]), _tree(g["theta_init"])
+    tr = (g["state"], int(g["action"]), float(g["reward"]), g["observation"], bool(g["done"]))
+    opt = dqn_b200.adamw(0.0002)
+    agent = dqn_b200.Agent(network=dqn_b200.Model(4), params=theta, optimizer=opt, opt_state=opt.init(theta), env=None, buffer_size=N,
+                           obs_shape=(N, 9), ac_shape=(N,), gamma=0.99, epsilon=1.0, epsilon_decay_rate=0.99, min_epsilon=0.15,
+                           max_episodes=10000, max_steps=1500, training_start=250, batch_size=64, train_frequency=4,
+                           back_up_frequency=50, replace_frequency=20, reward_to_reach=230.0, num_actions=4,
+                           saving_directory="/tmp/dqn_b200_golden_agent", monitoring=False, session=session)
+    for _ in range(100):
+        agent._replay_buffer.add(*tr)
+    for t in range(3):
+        agent._step()
+        assert_close(_flat(agent._params), g[f"agent_theta{t}"], what=f"Agent._step #{t + 1}")
+        if t == 1:
+            asyncio.run(agent._update_target_model())
+    assert int(agent._opt_state[0].count) == int(g["agent_count"]) and agent._replay_buffer.size == int(g["agent_buffer_size"])
+
+    opt = dqn_b200.adam(0.0001)
+    pagent = dqn_b200.ParamAgent(network=dqn_b200.Model(4), params=theta, optimizer=opt, opt_state=opt.init(theta), env=None,
+                                 buffer_size=N, obs_shape=(N, 9), ac_shape=(N,), max_episodes=10000, max_steps=1500,
+                                 training_start=500, back_up_frequency=50, reward_to_reach=240.0, num_actions=4,
+                                 saving_directory="/tmp/dqn_b200_golden_pagent", session=session)      # gamma_mode="frozen" is the default
+    pagent.inject(0.9028, 0.979, 0.9873, 0.1469, 25, 52, 7)
+    assert pagent._batch_size == int(g["pagent_batch_size"]) and pagent._gamma == float(g["pagent_gamma_attr"])
+    for _ in range(60):
+        pagent._replay_buffer.add(*tr)
+    dbg = pagent._step_debug()                                   # first step with taps: the q-targets the kernel used
+    a = int(g["action"])
+    assert_close(dbg["targets"][0], g["pagent_q_targets"][0], what="ParamAgent q-targets (gamma frozen at 0, SURVEY F12)")
+    assert_close(_flat(pagent._params), g["pagent_theta0"], what="ParamAgent._step #1")
+    for t in (1, 2):
+        pagent._step()
+        assert_close(_flat(pagent._params), g[f"pagent_theta{t}"], what=f"ParamAgent._step #{t + 1}")
