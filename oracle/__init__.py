@@ -20,7 +20,8 @@ Parity status
   README) and freezes what the reference's closures compute -- ``preprocessing`` -> ``compute_q_targets`` ->
   ``train_step``, several steps with hard syncs, ``compute_action`` -- into ``tests/golden/train_ref_*.npz``.
   ``tests/test_oracle_train_golden.py`` holds the oracle to those vectors; ``tests/test_gpu_train_golden.py`` holds the
-  kernels to them directly.  What remains restated (and is named as such) is the arithmetic of the absent libraries'
+  kernels to them directly; ``oracle/make_golden_agent_step.py`` records the reference's own ``Agent._step()`` and
+  ``ParamAgent.inject()`` + ``_step()`` entry points the same way (``tests/golden/agent_step_ref.npz``).  What remains restated (and is named as such) is the arithmetic of the absent libraries'
   primitives, not the reference's code.  It is additionally cross-validated by an independent torch-autograd derivation
   (``tests/test_oracle_autograd.py``) and anchored on ``Test/lunar_lander/{params,opt_state}.pickle`` (tree names,
   layouts, theta_0).
