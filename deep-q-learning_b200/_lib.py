@@ -55,6 +55,11 @@ class DqnEpisodeState(C.Structure):
                 ("episode", C.c_int32), ("step_in_episode", C.c_int32), ("window_len", C.c_int32), ("finished", C.c_int32)]
 
 
+class DqnCounters(C.Structure):
+    _fields_ = [("ring_counter", C.c_int64), ("train_steps", C.c_int64), ("adam_count", C.c_int32), ("reserved", C.c_int32),
+                ("pb1", C.c_double), ("pb2", C.c_double)]
+
+
 class DqnDebugTaps(C.Structure):
     _fields_ = [("indices", C.c_void_p), ("q", C.c_void_p), ("next_q", C.c_void_p), ("next_q_tm", C.c_void_p),
                 ("max_actions", C.c_void_p), ("targets", C.c_void_p), ("loss", C.c_void_p), ("grads", C.c_void_p)]
@@ -92,6 +97,8 @@ PROTOTYPES = {
     "dqn_get_hparams": (C.c_int, [_H, _i32, C.POINTER(DqnHparams)]),
     "dqn_set_step_kernel": (C.c_int, [_H, _i32]),
     "dqn_set_session": (C.c_int, [_H, _i32]),
+    "dqn_get_counters": (C.c_int, [_H, _i32, C.POINTER(DqnCounters)]),
+    "dqn_set_counters": (C.c_int, [_H, _i32, C.POINTER(DqnCounters)]),
     "dqn_store": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P]),
     "dqn_store_device": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P]),
     "dqn_buffer_state": (C.c_int, [_H, _i32, C.POINTER(_i64), C.POINTER(_i64)]),

@@ -170,6 +170,27 @@ class Agent:
         self._replay_buffer.flush()
         return self._engine.train_step_debug(indices=indices, agent=0)
 
+    # -- resume (beyond the reference: its checkpoint holds params / opt_state only, General/Base/utils.py:21-29) -------
+    def save_resume_state(self, path):
+        """Everything the reference's checkpoint omits as well: target network, replay ring, counters, epsilon, rewards."""
+        self._replay_buffer.flush()
+        st = self._engine.export_state(0)
+        st.update(agent_epsilon=np.float64(self._epsilon), agent_reward_history=np.asarray(self._reward_history, np.float64),
+                  agent_rb_counter=np.int64(self._replay_buffer._counter), agent_rb_sample_calls=np.int64(self._replay_buffer._sample_calls))
+        np.savez_compressed(path, **st)
+
+    def load_resume_state(self, path):
+        st = dict(np.load(path, allow_pickle=False))
+        self._replay_buffer.flush()
+        self._engine.import_state(st, 0)
+        self._epsilon = float(st["agent_epsilon"])
+        self._reward_history = [float(x) for x in st["agent_reward_history"]]
+        rb = self._replay_buffer
+        rb._counter = int(st["agent_rb_counter"])
+        rb._num_samples = min(rb._counter, rb._buffer_size)
+        rb._sample_calls = int(st["agent_rb_sample_calls"])
+        self.__dict__["_Agent__batch_size"] = int(st["hparam_batch_size"])
+
     def _run_episode(self, step_count, episode):
         epi_reward = 0.
         state = self._env.reset()

@@ -337,6 +337,35 @@ DQN_API int dqn_get_hparams(dqn_handle* h, int32_t agent, dqn_hparams* hp) {
   return DQN_OK;
 }
 
+// Resume support: the counters the reference never saves -- ReplayBuffer._counter, the number of
+// _step() calls (= Philox stream position) and the carried Adam decay powers -- so that a restored agent continues
+// bit for bit.  Parameters / moments / ring contents go through dqn_set_params, dqn_set_opt_state, dqn_store.
+DQN_API int dqn_get_counters(dqn_handle* h, int32_t agent, dqn_counters* out) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (!out) return fail(DQN_E_INVALID, "dqn_get_counters: out is NULL");
+  CU(cudaSetDevice(h->cfg.device));
+  AgentCtl c;
+  CU(cudaMemcpyAsync(&c, &h->ctl[agent], sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  out->ring_counter = c.ring_counter; out->train_steps = c.train_steps; out->adam_count = c.adam_count;
+  out->reserved = 0; out->pb1 = c.pb1; out->pb2 = c.pb2;
+  return DQN_OK;
+}
+
+DQN_API int dqn_set_counters(dqn_handle* h, int32_t agent, const dqn_counters* in) {
+  if (int rc = check_agent(h, agent)) return rc;
+  if (!in || in->ring_counter < 0 || in->train_steps < 0 || in->adam_count < 0)
+    return fail(DQN_E_INVALID, "dqn_set_counters: NULL or negative counter");
+  CU(cudaSetDevice(h->cfg.device));
+  AgentCtl& c = h->hctl[agent];
+  c.ring_counter = in->ring_counter; c.train_steps = in->train_steps; c.adam_count = in->adam_count;
+  c.pb1 = in->pb1; c.pb2 = in->pb2;
+  CU(cudaMemcpyAsync(&h->ctl[agent].adam_count, &c.adam_count, sizeof(AgentCtl) - offsetof(AgentCtl, adam_count),
+                     cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+
 DQN_API int dqn_set_step_kernel(dqn_handle* h, int32_t step_kernel) {
   if (!h) return fail(DQN_E_INVALID, "handle is NULL");
   if (h->session_active) if (int rc = session_stop(h)) return rc;

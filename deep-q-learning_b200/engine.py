@@ -120,6 +120,41 @@ class DqnEngine:
         _lib.check(self.lib.dqn_get_hparams(self.h, agent, C.byref(hp)))
         return {k: getattr(hp, k) for k, _ in _lib.DqnHparams._fields_}
 
+    # -- whole-agent state for resume (what the reference's checkpoint omits: target net, ring, counters) --------------
+    def get_counters(self, agent=0):
+        c = _lib.DqnCounters()
+        _lib.check(self.lib.dqn_get_counters(self.h, agent, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in _lib.DqnCounters._fields_ if k != "reserved"}
+
+    def set_counters(self, counters, agent=0):
+        c = _lib.DqnCounters(int(counters["ring_counter"]), int(counters["train_steps"]), int(counters["adam_count"]), 0,
+                             float(counters["pb1"]), float(counters["pb2"]))
+        _lib.check(self.lib.dqn_set_counters(self.h, agent, C.byref(c)))
+
+    def export_state(self, agent=0):
+        """Everything needed to continue this agent bit for bit (numpy arrays / scalars, ``np.savez``-able)."""
+        cnt, mu, nu = np.int32(0), np.empty(self.P, np.float32), np.empty(self.P, np.float32)
+        c = C.c_int32(0)
+        _lib.check(self.lib.dqn_get_opt_state(self.h, agent, C.byref(c), _lib.ptr(mu), _lib.ptr(nu), self.P))
+        s, a, r, s2, d = self.buffer_export(agent)
+        out = dict(params=self.get_params_flat(agent, _lib.DQN_PARAMS_ONLINE), target_params=self.get_params_flat(agent, _lib.DQN_PARAMS_TARGET),
+                   mu=mu, nu=nu, states=s, actions=a, rewards=r, observations=s2, dones=d)
+        out.update({"counter_" + k: np.asarray(v) for k, v in self.get_counters(agent).items()})
+        out.update({"hparam_" + k: np.asarray(v) for k, v in self.get_hparams(agent).items()})
+        return out
+
+    def import_state(self, state, agent=0):
+        hp = {k[7:]: state[k].item() for k in state if k.startswith("hparam_")}
+        self.set_hparams(agent, **hp)
+        self.set_params_flat(state["params"], agent, _lib.DQN_PARAMS_ONLINE)
+        self.set_params_flat(state["target_params"], agent, _lib.DQN_PARAMS_TARGET)
+        counters = {k[8:]: state[k].item() for k in state if k.startswith("counter_")}
+        mu, nu = _f32(state["mu"]), _f32(state["nu"])
+        _lib.check(self.lib.dqn_set_opt_state(self.h, agent, int(counters["adam_count"]), _lib.ptr(mu), _lib.ptr(nu), mu.size))
+        self.set_counters(dict(counters, ring_counter=0), agent)                    # slots are restored in slot order from 0 ...
+        self.store(state["states"], state["actions"], state["rewards"], state["observations"], state["dones"], agent=agent)
+        self.set_counters(counters, agent)                                           # ... then the real counters (and decay powers)
+
     # -- replay ring ----------------------------------------------------------------------------------
     def store(self, s, a, r, s2, done, agent=0):
         s, s2, r = _f32(s), _f32(s2), _f32(r)

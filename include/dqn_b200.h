@@ -131,6 +131,17 @@ DQN_API int dqn_get_opt_state(dqn_handle* h, int32_t agent, int32_t* count, floa
 DQN_API int dqn_set_hparams(dqn_handle* h, int32_t agent, const dqn_hparams* hp);
 DQN_API int dqn_get_hparams(dqn_handle* h, int32_t agent, dqn_hparams* hp);
 DQN_API int dqn_set_step_kernel(dqn_handle* h, int32_t step_kernel);   /* DQN_STEP_* */
+/* Resume support: what the reference's checkpoint (General/Base/utils.py:21-29) omits.  ring_counter = ReplayBuffer._counter
+ * (replay_buffer.py:64), train_steps = number of Agent._step() calls so far (the position of the Philox index stream),
+ * adam_count / pb1 / pb2 = optax count and the carried b1**count, b2**count.  A handle restored with dqn_set_params (both
+ * networks), dqn_set_opt_state, dqn_store (ring contents in slot order) and dqn_set_counters continues bit for bit. */
+typedef struct dqn_counters {
+  int64_t ring_counter, train_steps;
+  int32_t adam_count, reserved;
+  double pb1, pb2;
+} dqn_counters;
+DQN_API int dqn_get_counters(dqn_handle* h, int32_t agent, dqn_counters* out);
+DQN_API int dqn_set_counters(dqn_handle* h, int32_t agent, const dqn_counters* in);
 
 /* ReplayBuffer.add (replay_buffer.py:58-65), vectorised: equivalent to n scalar add() calls in order
  * into agent's ring (slot (counter+i) % N).  Host pointers: s/s2 f32[n*D], a i64[n], r f32[n],

@@ -295,3 +295,45 @@ def test_param_agent_inject_and_gamma_modes():
         p = ag._params
         for m in O.MODULES:
             assert_close(p[m]["w"], ora.params[m]["w"], what=f"{mode} {m}")
+
+
+def test_resume_state_continues_bitwise(tmp_path, golden):
+    """save_resume_state / load_resume_state: a fresh agent restored from the file continues exactly like
+    the one that kept running -- parameters, both networks, moments, ring (wrapped), Philox position, decay powers."""
+    theta0 = golden_tree(golden["ref_checkpoint"], "params")
+
+    def make():
+        opt = dqn_b200.adamw(1e-3)
+        return dqn_b200.Agent(network=dqn_b200.Model(4), params=theta0, optimizer=opt, opt_state=opt.init(theta0), env=None,
+                              buffer_size=150, obs_shape=(150, 9), ac_shape=(150,), gamma=0.97, epsilon=0.7, epsilon_decay_rate=0.99,
+                              min_epsilon=0.1, max_episodes=10, max_steps=100, training_start=10, batch_size=48, train_frequency=2,
+                              back_up_frequency=50, replace_frequency=3, reward_to_reach=1e9, num_actions=4,
+                              saving_directory=str(tmp_path), seed=19)
+    rng = np.random.default_rng(6)
+    s, a, r, s2, d = synthetic_transitions(rng, 400, 9, 4, done_p=0.2)
+
+    def drive(agent, lo, hi):
+        for i in range(lo, hi):
+            agent._replay_buffer.add(s[i], int(a[i]), float(r[i]), s2[i], bool(d[i]))
+            if i >= 10 and i % 2 == 0:
+                agent._step()
+            if i % 60 == 59:
+                agent._sync_target()
+
+    a1 = make()
+    drive(a1, 0, 230)                                         # the 150-slot ring has wrapped
+    a1._epsilon, a1._reward_history = 0.4321, [1.5, -2.0, 7.25]
+    path = str(tmp_path / "resume.npz")
+    a1.save_resume_state(path)
+    a2 = make()
+    a2.load_resume_state(path)
+    assert a2._epsilon == 0.4321 and a2._reward_history == [1.5, -2.0, 7.25] and a2._replay_buffer.size == 150
+    drive(a1, 230, 400)
+    drive(a2, 230, 400)
+    e1, e2 = a1._engine, a2._engine
+    assert np.array_equal(e1.get_params_flat(0, 0), e2.get_params_flat(0, 0))
+    assert np.array_equal(e1.get_params_flat(0, 1), e2.get_params_flat(0, 1))
+    assert e1.get_counters() == e2.get_counters()
+    for x, y in zip(e1.buffer_export(), e2.buffer_export()):
+        assert np.array_equal(x, y)
+    assert np.array_equal(e1.losses(50), e2.losses(50))
