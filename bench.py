@@ -697,7 +697,10 @@ def run_dp(args):
                        "collective": {"p2p": "own kernel over NVLink peer memory (csrc/comm_p2p.cu), %d floats", "nccl": "NCCL all-reduce of %d floats",
                                       "none": "none (1 GPU), %d floats"}[tr.collective] % (tr.P + 1),
                        "l2": "activations %.1f GB per rank >> L2" % (3 * 2 * (Bg // world) * H[0] * 4 / 1e9)},
-            "clocks": clk.summary(), "gpu_launches": None, "replay_samples_per_sec": Bg * args.steps / secs_max, "loss": loss,
+            # 18 kernels per step on every rank (index draw, gather, layer 1, 4 GEMMs, head, targets, 2 bias finishes, dh2, 3 partial
+            # reductions, head grads, dW1, Adam) + the peer-memory all-reduce when world > 1
+            "clocks": clk.summary(), "gpu_launches": args.steps * (18 + (1 if tr.collective == "p2p" else 0)),
+            "replay_samples_per_sec": Bg * args.steps / secs_max, "loss": loss,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
                          "note": "peak = measured sustained dense bf16 (MEASURED_PEAKS.json); fp32-exact modes run at 1/%s of it at best (%s)"
                                  % ("n/a" if mode_factor is None else int(mode_factor), "FFMA pipe, 74 TF/GPU" if mode_factor is None else "tf32 = 1/2 bf16, x3 split"),
