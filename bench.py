@@ -347,6 +347,16 @@ def run_single(args):
         s1.record()
         torch.cuda.synchronize(device)
         extras["k1_steps_per_sec"] = k1 / (s0.elapsed_time(s1) * 1e-3)
+        for kk in (16, 256):                                       # K fused steps per launch
+            agent._steps(kk)
+            torch.cuda.synchronize(device)
+            n_l = max(4096 // kk, 8)
+            s0.record()
+            for _ in range(n_l):
+                agent._steps(kk)
+            s1.record()
+            torch.cuda.synchronize(device)
+            extras["k%d_steps_per_sec" % kk] = n_l * kk / (s0.elapsed_time(s1) * 1e-3)
         eng.set_session(0 if args.no_session else 1)
         # the reference's whole inner loop (q_agent.py:174-189) with a greedy policy call per env transition:
         # train_frequency x (_policy -> add) + _step + loss read
