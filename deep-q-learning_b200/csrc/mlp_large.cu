@@ -176,6 +176,42 @@ reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, 
   out[i] = s;
 }
 
+// Same for few columns and many partials (the column-sum passes: n ~ 9k, nz = B / 128): 32 columns x 8 z-groups per
+// block, z-group g sums z = g, g + 8, ..., the 8 group sums are added in group order.  Fixed order -> deterministic.
+__global__ void __launch_bounds__(256)
+reduce_partials_wide_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int nz, long long zstride) {
+  __shared__ float red[8][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + c;
+  float s = 0.f;
+  if (i < n) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // four independent chains: loads in flight
+    int z = g;
+    for (; z + 24 < nz; z += 32) {
+      s0 += part[(size_t)z * zstride + i];
+      s1 += part[(size_t)(z + 8) * zstride + i];
+      s2 += part[(size_t)(z + 16) * zstride + i];
+      s3 += part[(size_t)(z + 24) * zstride + i];
+    }
+    for (; z < nz; z += 8) s0 += part[(size_t)z * zstride + i];
+    s = (s0 + s1) + (s2 + s3);
+  }
+  red[g][c] = s;
+  __syncthreads();
+  if (g == 0 && i < n) {
+    float t = red[0][c];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) t += red[q][c];
+    out[i] = t;
+  }
+}
+
+cudaError_t launch_reduce_partials(cudaStream_t st, const float* part, float* out, long long n, int nz, long long zstride) {
+  if (nz >= 64) reduce_partials_wide_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(part, out, n, nz, zstride);
+  else reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, out, n, nz, zstride);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // head: Q = V + Adv - mean(Adv)  (dddqn.py:29-31).  One warp per row, rows [0,3B).
 // ------------------------------------------------------------------------------------------------
@@ -469,7 +505,7 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     lb_dh2_kernel<<<grid, 256, 0, st>>>(ws.H2, ws.dhd, ws.theta, ws.dH2, ws.colpart, B, H2n, A, offWv);
     LBCHK(cudaGetLastError());
     const long long n = (long long)(2 + kMaxA) * H2n;
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.colpart, ws.colred, n, nchunk, n);
+    LBCHK(launch_reduce_partials(st, ws.colpart, ws.colred, n, nchunk, n));
     lb_head_grads_kernel<<<(H2n + 255) / 256, 256, 0, st>>>(ws.colred, ws.grads, H2n, A, offb2, offWv);
     LBCHK(cudaGetLastError());
   }
@@ -478,7 +514,7 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     while (splitk < 16 && (H1n / BM) * (H2n / BN) * splitk < 296 && (B / (splitk * 2)) % BK == 0 && B / (splitk * 2) >= 256) splitk *= 2;
     LBCHK(lb_gemm(st, gemm_mode, kGemmTN_SplitK, H1n, H2n, B, ws.H1, H1n, ws.dH2, H2n, ws.gemmpart, H2n, nullptr, 0, splitk, ws));
     const long long n = (long long)H1n * H2n;
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.gemmpart, ws.grads + offW2, n, splitk, n);
+    LBCHK(launch_reduce_partials(st, ws.gemmpart, ws.grads + offW2, n, splitk, n));
     LBCHK(cudaGetLastError());
   }
   LBCHK(lb_gemm(st, gemm_mode, kGemmNT_ReluMask, B, H1n, H2n, ws.dH2, H2n, ws.theta + offW2, H2n, ws.dH1, H1n, ws.H1, H1n, 1, ws));
@@ -487,8 +523,7 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     lb_dw1_kernel<<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
     LBCHK(cudaGetLastError());
     const long long n = (long long)(D + 1) * H1n;                 // [d][k] == flat [W1 | b1]
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.colpart, ws.grads, n, nchunk, n);
-    LBCHK(cudaGetLastError());
+    LBCHK(launch_reduce_partials(st, ws.colpart, ws.grads, n, nchunk, n));
   }
   return cudaSuccess;
 }
