@@ -1,0 +1,79 @@
+/* hoststage.c -- CPython helper for ReplayBuffer.add (General/Base/replay_buffer.py:58-65 in the reference).
+ *
+ * The reference's add() is five numpy __setitem__ calls per transition (~1 us); the drop-in stages transitions in host
+ * arrays and hands them to the library at the next train step, so add() is pure host bookkeeping on the e2e path.  This
+ * module does the five stores in C through the buffer protocol (~0.3 us).  It is an optional accelerator of HOST staging
+ * only: without it replay.py uses the numpy stores; no device work lives here.
+ *
+ *   stage = hoststage.new(addr_states, addr_actions, addr_rewards, addr_observations, addr_dones, D, capacity)
+ *   hoststage.put(stage, i, state, action, reward, observation, done)     # row i of the five staging arrays
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <stdint.h>
+#include <string.h>
+
+typedef struct {
+  float* s;
+  int64_t* a;
+  float* r;
+  float* o;
+  uint8_t* d;
+  Py_ssize_t D, cap;
+} Stage;
+
+static void stage_free(PyObject* cap) { PyMem_Free(PyCapsule_GetPointer(cap, "dqn_b200.hoststage")); }
+
+static PyObject* hs_new(PyObject* self, PyObject* args) {
+  unsigned long long as, aa, ar, ao, ad;
+  Py_ssize_t D, cap;
+  if (!PyArg_ParseTuple(args, "KKKKKnn", &as, &aa, &ar, &ao, &ad, &D, &cap)) return NULL;
+  Stage* st = (Stage*)PyMem_Malloc(sizeof(Stage));
+  if (!st) return PyErr_NoMemory();
+  st->s = (float*)(uintptr_t)as; st->a = (int64_t*)(uintptr_t)aa; st->r = (float*)(uintptr_t)ar;
+  st->o = (float*)(uintptr_t)ao; st->d = (uint8_t*)(uintptr_t)ad; st->D = D; st->cap = cap;
+  return PyCapsule_New(st, "dqn_b200.hoststage", stage_free);
+}
+
+/* copy D float32 values out of any C-contiguous float32 buffer (numpy row, memoryview, ...) */
+static int copy_obs(PyObject* obj, float* dst, Py_ssize_t D) {
+  Py_buffer view;
+  if (PyObject_GetBuffer(obj, &view, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) != 0) return -1;
+  const int ok = view.len == D * 4 && view.format && view.format[0] == 'f' && view.format[1] == 0;
+  if (ok) memcpy(dst, view.buf, (size_t)D * 4);
+  PyBuffer_Release(&view);
+  if (!ok) {
+    PyErr_SetString(PyExc_TypeError, "hoststage.put: observation must be a contiguous float32 buffer of D values");
+    return -1;
+  }
+  return 0;
+}
+
+static PyObject* hs_put(PyObject* self, PyObject* const* args, Py_ssize_t nargs) {
+  if (nargs != 7) { PyErr_SetString(PyExc_TypeError, "put(stage, i, state, action, reward, observation, done)"); return NULL; }
+  Stage* st = (Stage*)PyCapsule_GetPointer(args[0], "dqn_b200.hoststage");
+  if (!st) return NULL;
+  const Py_ssize_t i = PyLong_AsSsize_t(args[1]);
+  if (i < 0 || i >= st->cap) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "hoststage.put: row out of range"); return NULL; }
+  const long long action = PyLong_AsLongLong(args[3]);           /* numpy integer scalars go through __index__ */
+  if (action == -1 && PyErr_Occurred()) return NULL;
+  const double reward = PyFloat_AsDouble(args[4]);
+  if (reward == -1.0 && PyErr_Occurred()) return NULL;
+  const int done = PyObject_IsTrue(args[6]);
+  if (done < 0) return NULL;
+  if (copy_obs(args[2], st->s + i * st->D, st->D) != 0) return NULL;
+  if (copy_obs(args[5], st->o + i * st->D, st->D) != 0) return NULL;
+  st->a[i] = (int64_t)action;
+  st->r[i] = (float)reward;                                      /* the reference stores into a float32 array */
+  st->d[i] = (uint8_t)done;
+  Py_RETURN_NONE;
+}
+
+static PyMethodDef methods[] = {
+    {"new", hs_new, METH_VARARGS, "new(addr_s, addr_a, addr_r, addr_o, addr_d, D, capacity) -> stage"},
+    {"put", (PyCFunction)(void (*)(void))hs_put, METH_FASTCALL, "put(stage, i, state, action, reward, observation, done)"},
+    {NULL, NULL, 0, NULL}};
+
+static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_hoststage", "host-side staging of ReplayBuffer.add", -1, methods};
+
+PyMODINIT_FUNC PyInit__hoststage(void) { return PyModule_Create(&moddef); }

@@ -13,6 +13,11 @@ import numpy as np
 from . import _lib
 from .specs import adam
 
+try:                       # optional CPython accelerator of the host-side staging in add() (csrc/hoststage.c); no device code
+    from . import _hoststage
+except ImportError:        # not built: the numpy stores below do the same thing
+    _hoststage = None
+
 _FIELDS = ("states", "actions", "rewards", "observations", "dones")
 
 
@@ -65,6 +70,7 @@ class ReplayBuffer:
         self._ps, self._po = np.zeros((self._cap, d), np.float32), np.zeros((self._cap, d), np.float32)
         self._pa, self._pr, self._pd = np.zeros(self._cap, np.int64), np.zeros(self._cap, np.float32), np.zeros(self._cap, np.bool_)
         self._ptrs = tuple(_lib.ptr(x) for x in (self._ps, self._pa, self._pr, self._po, self._pd))
+        self._stage = _hoststage.new(*self._ptrs, d, self._cap) if _hoststage is not None else None
         self._pending = 0
         self._counter = 0
         self._num_samples = 0
@@ -83,16 +89,25 @@ class ReplayBuffer:
 
     def add(self, state, action, reward, observation, done):
         i = self._pending
-        self._ps[i] = state
-        self._pa[i] = action
-        self._pr[i] = reward
-        self._po[i] = observation
-        self._pd[i] = done
+        if self._stage is not None:
+            try:
+                _hoststage.put(self._stage, i, state, action, reward, observation, done)   # the five stores, in C
+            except TypeError:                   # arguments that are not float32 rows / plain scalars: let numpy convert
+                self._add_numpy(i, state, action, reward, observation, done)
+        else:
+            self._add_numpy(i, state, action, reward, observation, done)
         self._pending = i + 1
         self._counter += 1
         self._num_samples = min(self._counter, self._buffer_size)
         if self._pending == self._cap:
             self.flush()
+
+    def _add_numpy(self, i, state, action, reward, observation, done):
+        self._ps[i] = state
+        self._pa[i] = action
+        self._pr[i] = reward
+        self._po[i] = observation
+        self._pd[i] = done
 
     def flush(self):
         """Move staged add() transitions into the device ring (no-op when nothing is pending)."""

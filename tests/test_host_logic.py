@@ -120,3 +120,29 @@ def test_sample_batch_rejects_host_arrays():
     z = np.zeros((4, 9), np.float32)
     with pytest.raises(TypeError):
         dqn_b200.sample_batch(4, z, np.zeros(4, np.int64), np.zeros(4, np.float32), z, np.zeros(4, bool), 2)
+
+
+def test_hoststage_matches_numpy_stores():
+    """csrc/hoststage.c (optional CPython accelerator of ReplayBuffer.add's host staging) stores exactly what the numpy
+    assignments store, for the argument types the reference passes (float32 rows, python / numpy scalars)."""
+    hs = dqn_b200.pkg.replay._hoststage
+    if hs is None:
+        pytest.skip("_hoststage not built")
+    D, cap = 9, 16
+    a = [np.zeros((cap, D), np.float32), np.zeros(cap, np.int64), np.zeros(cap, np.float32), np.zeros((cap, D), np.float32), np.zeros(cap, np.bool_)]
+    b = [x.copy() for x in a]
+    st = hs.new(*[x.ctypes.data for x in a], D, cap)
+    rng = np.random.default_rng(0)
+    for i in range(cap):
+        s, o = rng.standard_normal(D).astype(np.float32), rng.standard_normal((1, D)).astype(np.float32)[0]
+        act = [3, np.int64(2), np.int32(1), -1][i % 4]
+        rew = [1.25, np.float32(-0.1), np.float64(1e-3), 7][i % 4]
+        done = [True, False, np.bool_(True), 0][i % 4]
+        hs.put(st, i, s, act, rew, o, done)
+        b[0][i], b[1][i], b[2][i], b[3][i], b[4][i] = s, act, rew, o, done
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    with pytest.raises(TypeError):
+        hs.put(st, 0, np.zeros(D, np.float64), 0, 0.0, np.zeros(D, np.float32), False)       # replay.py falls back to numpy here
+    with pytest.raises(IndexError):
+        hs.put(st, cap, np.zeros(D, np.float32), 0, 0.0, np.zeros(D, np.float32), False)
