@@ -708,8 +708,9 @@ def run_dp(args):
                                       "none": "none (1 GPU), %d floats"}[tr.collective] % (tr.P + 1),
                        "l2": "activations %.1f GB per rank >> L2" % (3 * 2 * (Bg // world) * H[0] * 4 / 1e9)},
             # 18 kernels per step on every rank (index draw, gather, layer 1, 4 GEMMs, head, targets, 2 bias finishes, dh2, 3 partial
-            # reductions, head grads, dW1, Adam) + the peer-memory all-reduce when world > 1
-            "clocks": clk.summary(), "gpu_launches": args.steps * (18 + (1 if tr.collective == "p2p" else 0)),
+            # reductions, head grads, dW1, Adam) + the W2 transpose of the tensor-core mode + the peer-memory all-reduce when world > 1
+            "clocks": clk.summary(),
+            "gpu_launches": args.steps * (18 + (1 if args.gemm == "tc3xtf32" else 0) + (1 if tr.collective == "p2p" else 0)),
             "replay_samples_per_sec": Bg * args.steps / secs_max, "loss": loss,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
                          "note": "peak = measured sustained dense bf16 (MEASURED_PEAKS.json); fp32-exact modes run at 1/%s of it at best (%s)"

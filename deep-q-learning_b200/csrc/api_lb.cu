@@ -59,9 +59,7 @@ LbCarve lb_carve(const LbDims& d) {
   take(c.colpart, (B / 128) * colw * 4);
   take(c.colred, colw * 4);
   take(c.gemmpart, (size_t)16 * d.H1 * d.H2 * 4);
-  // tcgen05 path: hi/lo splits of the largest A operand (3B x max(H1,H2)) and B operand (max(H1*H2, B*H2))
-  const size_t amax = 3 * B * (size_t)(d.H1 > d.H2 ? d.H1 : d.H2), bmax = (size_t)d.H1 * d.H2 > B * (size_t)d.H2 ? (size_t)d.H1 * d.H2 : B * (size_t)d.H2;
-  take(c.tc, (2 * amax + 2 * bmax) * 4);
+  take(c.tc, (size_t)d.H1 * d.H2 * 4);          // tcgen05 path: W2^T for the dh1 GEMM
   take(c.targets, B * d.A * 4); take(c.maxa, B * 4);
   take(c.stage, kLbStage);
   c.total = o;

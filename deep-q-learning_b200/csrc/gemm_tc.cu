@@ -425,6 +425,7 @@ cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const flo
   switch (kind) {
     case kGemmNN_BiasRelu: return launch_tc<false, true, kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
     case kGemmNT_ReluMask: return launch_tc<false, false, kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
+    case kGemmNN_ReluMask: return launch_tc<false, true, kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
     case kGemmTN_SplitK: return launch_tc<true, true, kEpiSplitK>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, splitk);
     default: return cudaErrorInvalidValue;
   }

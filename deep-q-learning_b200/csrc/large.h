@@ -5,7 +5,7 @@
 namespace dqn {
 
 enum { kEpiSplitK = 0, kEpiBiasRelu = 1, kEpiReluMask = 2 };
-enum { kGemmNN_BiasRelu = 0, kGemmNT_ReluMask = 1, kGemmTN_SplitK = 2 };
+enum { kGemmNN_BiasRelu = 0, kGemmNT_ReluMask = 1, kGemmTN_SplitK = 2, kGemmNN_ReluMask = 3 };
 enum { kGemmModeFFMA = 0, kGemmModeTC3xTF32 = 1 };
 
 struct LbDims {
@@ -33,7 +33,7 @@ struct LbWorkspace {
   float *colpart;      // column-sum partials  [B/128][max((2+kMaxA)*H2, (D+1)*H1)]
   float *colred;       // [(2+kMaxA)*H2]
   float *gemmpart;     // split-K partials [16][H1*H2]
-  float *tc_scratch;   // tcgen05 path: hi/lo operand splits
+  float *tc_scratch;   // tcgen05 path: W2^T [H2][H1] for the dh1 GEMM (so that it runs in the faster NN form)
 };
 
 // ---- peer-memory gradient all-reduce (comm_p2p.cu) ----

@@ -469,6 +469,18 @@ cudaError_t lb_gemm_ffma(cudaStream_t st, int kind, int M, int N, int K, const f
 
 #define LBCHK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
 
+// out[c][r] = in[r][c]  (32 x 32 tiles through shared memory); rows, cols multiples of 32
+__global__ void __launch_bounds__(256)
+lb_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = in[(size_t)(r0 + ty + 8 * j) * cols + c0 + tx];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[(size_t)(c0 + ty + 8 * j) * rows + r0 + tx] = tile[tx][ty + 8 * j];
+}
+
 // One forward/backward pass over the local batch already gathered into ws.s/a/r/s2/done.
 cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float gamma, float inv_global_batch,
                                 int gemm_mode, const LbTaps& taps) {
@@ -517,7 +529,15 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     LBCHK(launch_reduce_partials(st, ws.gemmpart, ws.grads + offW2, n, splitk, n));
     LBCHK(cudaGetLastError());
   }
-  LBCHK(lb_gemm(st, gemm_mode, kGemmNT_ReluMask, B, H1n, H2n, ws.dH2, H2n, ws.theta + offW2, H2n, ws.dH1, H1n, ws.H1, H1n, 1, ws));
+  if (gemm_mode == kGemmModeTC3xTF32) {
+    // dh1 = relu'(h1) * (dh2 . W2^T): the tensor-core kernel's NT form (K-major B) runs at 126 TF against 151 TF for the NN
+    // form, so W2 (4 MB) is transposed once per step and the product runs as NN
+    lb_transpose_kernel<<<dim3(H2n / 32, H1n / 32), 256, 0, st>>>(ws.theta + offW2, ws.tc_scratch, H1n, H2n);
+    LBCHK(cudaGetLastError());
+    LBCHK(lb_gemm(st, gemm_mode, kGemmNN_ReluMask, B, H1n, H2n, ws.dH2, H2n, ws.tc_scratch, H1n, ws.dH1, H1n, ws.H1, H1n, 1, ws));
+  } else {
+    LBCHK(lb_gemm(st, gemm_mode, kGemmNT_ReluMask, B, H1n, H2n, ws.dH2, H2n, ws.theta + offW2, H2n, ws.dH1, H1n, ws.H1, H1n, 1, ws));
+  }
   {
     dim3 grid(H1n / 256, nchunk);
     lb_dw1_kernel<<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
