@@ -485,6 +485,13 @@ def run_population(args):
         flops = value * mean_b * FLOP_PER_SAMPLE / 1e9
         peak, peak_src = measured_peaks()
         gbs = value * mean_b * REC_BYTES_ALGO / 1e9
+        traffic = None
+        try:      # DRAM bytes of one launch from the committed ncu capture, scaled to this rank's agents x steps per launch
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)["dqn_train_fused_kernel<4>/population"]
+            traffic = tr["dram_bytes_per_launch"] / tr["agent_steps_per_launch"] * pop.n_local * kpl
+        except Exception:
+            pass
         print(json.dumps({
             "metric": "agent_train_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": steps,
             "warmup": max(args.warmup, 3), "ms_per_step": secs_max / steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -494,7 +501,7 @@ def run_population(args):
                        "optimizer": "adam(1e-4)", "steps_per_launch": kpl, "l2": "rings total %.1f GB per rank >> L2" % (pop.n_local * ring * 96 / 1e9)},
             "clocks": clk.summary(), "gpu_launches": steps // kpl,
             "replay_samples_per_sec": value * mean_b,
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s", "frac": gbs / (peak * world), "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s", "frac": gbs / (peak * world), "traffic": traffic,
                          "kernel": "dqn_train_fused_kernel<4>", "peak_source": peak_src,
                          "note": "compute-bound on the fp32 pipe, not HBM: see fp32",
                          "fp32": {"achieved_gflops": flops, "ffma_peak_gflops": fp32_peak, "frac": flops / fp32_peak}}}))
