@@ -73,9 +73,9 @@ typedef struct dqn_config {
   int32_t opt_kind;      /* DQN_OPT_ADAM / DQN_OPT_ADAMW */
   float lr, b1, b2, eps, eps_root, weight_decay;
   uint64_t seed;         /* Philox key for minibatch indices */
-  int32_t agent_id_base; /* global id of local agent 0: the Philox counter uses (agent_id_base + agent), */
-  int32_t step_kernel;   /*   so a sharded population draws the same indices as the unsharded one       */
-                         /* step_kernel: DQN_STEP_AUTO / _CTA / _CLUSTER (which train-step kernel, see below) */
+  int32_t agent_id_base; /* global id of local agent 0: the Philox counter uses (agent_id_base + agent), so a
+                          *   sharded population draws the same indices as the unsharded one */
+  int32_t step_kernel;   /* DQN_STEP_AUTO / DQN_STEP_CTA / DQN_STEP_CLUSTER: which train-step kernel (see the enum) */
   void* stream;          /* cudaStream_t to enqueue on (NULL = default stream) */
   void* arena;           /* optional caller-allocated device memory (e.g. a torch tensor's  */
   uint64_t arena_bytes;  /*   data_ptr()); NULL => the library allocates dqn_arena_bytes() itself */
