@@ -2,8 +2,12 @@
 
 ``generate_saving(directory)`` / ``generate_loading(directory)`` keep the reference's names and file
 names (``params.pickle``, ``opt_state.pickle``).  Trees are written as plain numpy arrays inside the
-same nesting (``{module: {'w','b'}}`` and ``(ScaleByAdamState(count, mu, nu), EmptyState(), ...)``);
-the loader additionally understands the reference's own pickles, whose leaves are
+same nesting (``{module: {'w','b'}}`` and ``(ScaleByAdamState(count, mu, nu), EmptyState(), ...)``).
+The two optimiser-state classes are written under the names the REFERENCE's pickles carry
+(``optax._src.transform.ScaleByAdamState``, ``optax._src.base.EmptyState``), not under this
+package's module path, so the reference's ``generate_loading`` -- a bare ``pickle.load`` in a
+process that has optax but has never heard of this package -- reads the files
+(``tests/test_host_logic.py::test_checkpoint_loads_with_bare_pickle``).  The loader additionally understands the reference's own pickles, whose leaves are
 ``jax._src.device_array.reconstruct_device_array`` records and whose optimiser state classes live in
 ``optax._src`` (neither library is importable here) -- e.g. ``Test/lunar_lander/*.pickle``.
 """
@@ -33,6 +37,30 @@ class _Unpickler(pickle.Unpickler):
         return super().find_class(module, name)
 
 
+# class -> (module, qualified name) the reference's pickles use for it (Test/lunar_lander/opt_state.pickle)
+_REFERENCE_GLOBALS = {ScaleByAdamState: ("optax._src.transform", "ScaleByAdamState"),
+                      EmptyState: ("optax._src.base", "EmptyState")}
+
+
+class _ReferencePickler(pickle._Pickler):
+    """Pure-Python pickler (protocol 4, like the fixture) that names the optimiser-state classes the way
+    optax does.  ``save_global`` normally insists that the named module is importable HERE; optax is not,
+    so the GLOBAL record is written directly."""
+
+    def save_global(self, obj, name=None):
+        target = _REFERENCE_GLOBALS.get(obj)
+        if target is None:
+            return super().save_global(obj, name)
+        self.save(target[0])
+        self.save(target[1])
+        self.write(pickle.STACK_GLOBAL)
+        self.memoize(obj)
+
+
+def _dump(obj, f):
+    _ReferencePickler(f, protocol=4).dump(obj)
+
+
 def _to_numpy_tree(tree):
     return OrderedDict((m, {k: np.asarray(v) for k, v in leaves.items()}) for m, leaves in tree.items())
 
@@ -47,12 +75,13 @@ def generate_saving(directory):
         if not os.path.exists(directory):
             os.mkdir(directory)
         with open(os.path.join(directory, "params.pickle"), "wb") as f:
-            pickle.dump(_to_numpy_tree(params), f)
+            _dump(dict(_to_numpy_tree(params)), f)
         first = opt_state[0]
-        adam_state = ScaleByAdamState(np.asarray(first[0], dtype=np.int32), _to_numpy_tree(first[1]),
-                                      _to_numpy_tree(first[2]))
+        adam_state = ScaleByAdamState(np.asarray(first[0], dtype=np.int32), dict(_to_numpy_tree(first[1])),
+                                      dict(_to_numpy_tree(first[2])))
+        rest = tuple(EmptyState() if isinstance(x, tuple) and len(x) == 0 else x for x in opt_state[1:])
         with open(os.path.join(directory, "opt_state.pickle"), "wb") as f:
-            pickle.dump((adam_state,) + tuple(opt_state[1:]), f)
+            _dump((adam_state,) + rest, f)
     return save_state
 
 

@@ -1,6 +1,7 @@
 // api_lb.cu -- C ABI of the large-batch data-parallel mode (dqn_lb_* in include/dqn_b200.h).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -110,9 +111,16 @@ struct dqn_lb_handle {
   void* opened[kMaxWorld];     // cudaIpcOpenMemHandle results to close
   bool connected;
   unsigned epoch;
+  unsigned long long comm_timeout_ns;
 };
 
 namespace {
+// the all-reduce kernel mirrors its error flag into this word of the handle's pinned (mapped) host page
+volatile unsigned* comm_host_error(const dqn_lb_handle* h) { return reinterpret_cast<volatile unsigned*>(h->pinned) + 64; }
+int comm_failed(const dqn_lb_handle* h) {
+  return *comm_host_error(h) ? lbfail(DQN_E_CUDA, "peer-memory all-reduce timed out waiting for a rank: the parameter update was "
+                                                  "skipped and the replicas are out of step (rebuild the group)") : DQN_OK;
+}
 long long lb_size(const dqn_lb_handle* h) { return h->ring_counter < h->dims.N ? h->ring_counter : h->dims.N; }
 Dims ring_dims(const dqn_lb_handle* h) {
   Dims d; d.D = h->dims.D; d.A = h->dims.A; d.P = h->dims.P; d.PK = 0; d.recw = h->dims.recw; d.N = h->dims.N;
@@ -166,8 +174,14 @@ DQN_API int dqn_lb_create(const dqn_lb_config* cfg, dqn_lb_handle** out) {
   h->stage = a + c.stage;
   h->ring_counter = 0; h->train_steps = 0; h->adam_count = 0; h->pinned = nullptr;
   h->window = nullptr; h->connected = false; h->epoch = 0;
+  {
+    const char* ms = getenv("DQN_B200_COMM_TIMEOUT_MS");
+    const double v = ms ? atof(ms) : 20000.0;
+    h->comm_timeout_ns = (unsigned long long)((v > 0.0 ? v : 20000.0) * 1e6);
+  }
   memset(&h->peers, 0, sizeof h->peers); memset(h->opened, 0, sizeof h->opened);
   cudaError_t e = cudaMallocHost((void**)&h->pinned, 4096);
+  if (e == cudaSuccess) memset(h->pinned, 0, 4096);
   if (e == cudaSuccess) e = cudaMemsetAsync(a, 0, c.s, h->stream);          // params, moments, grads, ctl, ring
   if (e == cudaSuccess) e = cudaMemsetAsync(a + c.dhd, 0, (size_t)d.B * 32, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -367,14 +381,17 @@ DQN_API int dqn_lb_allreduce(dqn_lb_handle* h) {
   if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
   if (h->cfg.world == 1) return DQN_OK;
   if (!h->connected) return lbfail(DQN_E_INVALID, "dqn_lb_allreduce: dqn_lb_comm_connect has not been called");
+  if (int rc = comm_failed(h)) return rc;
   CU(cudaSetDevice(h->cfg.device));
   h->epoch += 1;
-  CU(lb_allreduce(h->stream, h->peers, h->cfg.world, h->cfg.rank, h->dims.PF / 4, h->epoch));
+  CU(lb_allreduce(h->stream, h->peers, h->cfg.world, h->cfg.rank, h->dims.PF / 4, h->epoch, h->comm_timeout_ns,
+                  const_cast<unsigned*>(comm_host_error(h))));
   return DQN_OK;
 }
 
 DQN_API int dqn_lb_apply(dqn_lb_handle* h) {
   if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
+  if (int rc = comm_failed(h)) return rc;
   CU(cudaSetDevice(h->cfg.device));
   const dqn_lb_config& c = h->cfg;
   const int t = h->adam_count == 0x7fffffff ? h->adam_count : h->adam_count + 1;
@@ -382,7 +399,8 @@ DQN_API int dqn_lb_apply(dqn_lb_handle* h) {
   const float c1 = 1.0f - (float)pow((double)c.b1, (double)t);
   const float c2 = 1.0f - (float)pow((double)c.b2, (double)t);
   const float wd = c.opt_kind == DQN_OPT_ADAMW ? c.weight_decay : 0.f;
-  CU(lb_adam(h->stream, h->dims, h->ws, c.b1, c.b2, c1, c2, c.eps, c.eps_root, c.lr, wd));
+  CU(lb_adam(h->stream, h->dims, h->ws, c.b1, c.b2, c1, c2, c.eps, c.eps_root, c.lr, wd,
+             h->window ? &comm_flags(h->window, h->dims.PF / 4)->error : nullptr));
   h->adam_count = t;
   h->train_steps += 1;
   return DQN_OK;

@@ -14,8 +14,13 @@
 //   phase 2   the last block of the grid to finish tells every rank "slice r is in place" and waits until every
 //             rank has said so; when the kernel retires, the whole window holds the global sum.
 //
-// Flags carry the step number (monotonic), so nothing is ever reset.  Every spin is bounded (about 2 s): a rank
-// that never shows up raises an error flag in the window instead of hanging the GPU.
+// Flags carry the step number (monotonic), so nothing is ever reset.  Every spin is bounded (wall-clock time-out,
+// DQN_B200_COMM_TIMEOUT_MS, default 20 s).  A rank that never shows up does not hang the GPU and does not corrupt
+// training either: a block that times out in phase 0 raises the error flag (in the window and in a word of mapped host
+// memory the C ABI polls) and LEAVES -- it neither sums stale peer gradients nor stores into anybody's window; a
+// time-out in phase 2 raises the same flag.  The Adam kernel behind this one is predicated on the flag (mlp_large.cu),
+// so a failed exchange never reaches the parameters, and the next dqn_lb_allreduce / dqn_lb_apply call returns
+// DQN_E_CUDA.  The flag is sticky: the replicas are no longer in step and the caller must rebuild the group.
 #include "common.cuh"
 #include "large.h"
 
@@ -23,7 +28,11 @@ namespace dqn {
 
 namespace {
 
-constexpr unsigned kSpinLimit = 1u << 24;   // x ~120 ns of __nanosleep -> ~2 s
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -43,27 +52,34 @@ __device__ __forceinline__ void st_peer4(float4* p, const float4 v) {
 }
 
 // wait until flag >= epoch (wrap-safe); false on timeout
-__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch) {
-  for (unsigned spin = 0; spin < kSpinLimit; ++spin) {
+__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, unsigned long long timeout_ns) {
+  const unsigned long long t0 = globaltimer_ns();
+  for (unsigned spin = 0;; ++spin) {
     if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return true;
+    if ((spin & 63u) == 63u && globaltimer_ns() - t0 > timeout_ns) return false;
     __nanosleep(100);
   }
-  return false;
 }
 
 template <int W>
-__global__ void __launch_bounds__(256) lb_allreduce_kernel(const CommPeers peers, int rank, int n4, unsigned epoch) {
+__global__ void __launch_bounds__(256) lb_allreduce_kernel(const CommPeers peers, int rank, int n4, unsigned epoch,
+                                                           unsigned long long timeout_ns, unsigned* host_error) {
   CommFlags* const mine = comm_flags(peers.win[rank], n4);
   const int t = threadIdx.x;
-  __shared__ int s_last;
+  __shared__ int s_last, s_fail;
+  if (t == 0) s_fail = 0;
+  __syncthreads();
 
   // ---- phase 0 ----
   if (blockIdx.x == 0 && t < W) {
     __threadfence_system();
     st_release_sys(&comm_flags(peers.win[t], n4)->ready[rank], epoch);
   }
-  if (t < W && !wait_flag(&mine->ready[t], epoch)) mine->error = 1;
+  if (t < W && (mine->error || !wait_flag(&mine->ready[t], epoch, timeout_ns))) {
+    mine->error = 1; *host_error = 1u; s_fail = 1;
+  }
   __syncthreads();
+  if (s_fail) return;                    // nothing is summed and nothing is stored anywhere; Adam is predicated on the flag
 
   // ---- phase 1: reduce my slice, broadcast it ----
   const int chunk = (n4 + W - 1) / W;
@@ -88,21 +104,22 @@ __global__ void __launch_bounds__(256) lb_allreduce_kernel(const CommPeers peers
     if (t == 0) mine->blocks_done = 0;
     if (t < W) {
       st_release_sys(&comm_flags(peers.win[t], n4)->done[rank], epoch);
-      if (!wait_flag(&mine->done[t], epoch)) mine->error = 1;
+      if (!wait_flag(&mine->done[t], epoch, timeout_ns)) { mine->error = 1; *host_error = 1u; }
     }
   }
 }
 
 }  // namespace
 
-cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, unsigned epoch) {
+cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, unsigned epoch,
+                         unsigned long long timeout_ns, unsigned* host_error) {
   const int chunk = (n4 + world - 1) / world;
   int grid = (chunk + 255) / 256;
   grid = grid < 1 ? 1 : (grid > 96 ? 96 : grid);     // all blocks co-resident on any B200 (they poll each other's progress)
   switch (world) {
-    case 2: lb_allreduce_kernel<2><<<grid, 256, 0, st>>>(peers, rank, n4, epoch); break;
-    case 4: lb_allreduce_kernel<4><<<grid, 256, 0, st>>>(peers, rank, n4, epoch); break;
-    case 8: lb_allreduce_kernel<8><<<grid, 256, 0, st>>>(peers, rank, n4, epoch); break;
+    case 2: lb_allreduce_kernel<2><<<grid, 256, 0, st>>>(peers, rank, n4, epoch, timeout_ns, host_error); break;
+    case 4: lb_allreduce_kernel<4><<<grid, 256, 0, st>>>(peers, rank, n4, epoch, timeout_ns, host_error); break;
+    case 8: lb_allreduce_kernel<8><<<grid, 256, 0, st>>>(peers, rank, n4, epoch, timeout_ns, host_error); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -46,7 +46,9 @@ struct CommFlags {                                     // lives behind the n4 * 
 };
 __host__ __device__ inline CommFlags* comm_flags(float* win, int n4) { return reinterpret_cast<CommFlags*>(win + 4 * (size_t)n4); }
 inline size_t comm_window_bytes(int n4) { return (((size_t)n4 * 16 + sizeof(CommFlags)) + 255) / 256 * 256; }
-cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, unsigned epoch);
+// host_error: a word of mapped pinned host memory that mirrors CommFlags.error (polled by the C ABI without a sync)
+cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, unsigned epoch,
+                         unsigned long long timeout_ns, unsigned* host_error);
 
 cudaError_t lb_gemm_ffma(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                          float* C, int ldc, const float* aux, int ldaux, int splitk);
@@ -57,7 +59,8 @@ cudaError_t lb_gemm(cudaStream_t st, int gemm_mode, int kind, int M, int N, int 
                     float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws);
 cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float gamma, float inv_global_batch,
                                 int gemm_mode, const LbTaps& taps);
+// comm_error: nullptr, or the window's CommFlags.error -- a non-zero value turns the update into a no-op
 cudaError_t lb_adam(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float b1, float b2, float c1, float c2,
-                    float eps, float eps_root, float lr, float wd);
+                    float eps, float eps_root, float lr, float wd, const unsigned* comm_error);
 
 }  // namespace dqn

@@ -434,9 +434,11 @@ __global__ void lb_finish_ba_kernel(const float* __restrict__ partial, int nblk,
 // optax adam / adamw, exact fp32 (memory-bound: IEEE division and sqrt are free here)
 __global__ void __launch_bounds__(256)
 lb_adam_kernel(float* __restrict__ theta, float* __restrict__ mu, float* __restrict__ nu, const float* __restrict__ g,
-               int P, float b1, float b2, float c1, float c2, float eps, float eps_root, float lr, float wd) {
+               int P, float b1, float b2, float c1, float c2, float eps, float eps_root, float lr, float wd,
+               const unsigned* __restrict__ comm_error) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
+  if (comm_error && *comm_error) return;   // the gradient exchange failed (comm_p2p.cu): g is not the global sum -- leave theta / mu / nu alone
   const float gr = g[p];
   const float m = b1 * mu[p] + (1.0f - b1) * gr;
   const float v = b2 * nu[p] + (1.0f - b2) * (gr * gr);
@@ -549,8 +551,8 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
 }
 
 cudaError_t lb_adam(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float b1, float b2, float c1, float c2,
-                    float eps, float eps_root, float lr, float wd) {
-  lb_adam_kernel<<<(d.P + 255) / 256, 256, 0, st>>>(ws.theta, ws.mu, ws.nu, ws.grads, d.P, b1, b2, c1, c2, eps, eps_root, lr, wd);
+                    float eps, float eps_root, float lr, float wd, const unsigned* comm_error) {
+  lb_adam_kernel<<<(d.P + 255) / 256, 256, 0, st>>>(ws.theta, ws.mu, ws.nu, ws.grads, d.P, b1, b2, c1, c2, eps, eps_root, lr, wd, comm_error);
   return cudaGetLastError();
 }
 

@@ -85,13 +85,30 @@ __device__ long long g_phase_clock[16];
 // Cluster barrier for this kernel's DSMEM protocol.  Everything the CTAs exchange is READ remotely (ld.shared::cluster)
 // from data its owner wrote with ordinary shared-memory stores: partial gradients, new weight slices, loss shares.
 // No CTA ever stores training data into another CTA's shared memory (the one remote store in this file is the session
-// command word, a self-contained 8-byte value the receiver polls).  The stock cluster.sync() is arrive.release + wait.acquire and
-// costs a MEMBAR.ALL.GPU per call (~700 cycles, 12 % of a step in ncu).  Here the CTA barrier first drains the CTA's
-// own shared-memory stores (they are then in the SM's shared memory, which is what a remote load reads), and the
-// cluster arrive itself is relaxed.  -DDQN_CLUSTER_STRICT restores the release/acquire form.
-__device__ __forceinline__ void cluster_barrier_after_local_stores() {
+// command word, a self-contained 8-byte value the receiver polls).  The PTX memory model wants a release at cluster
+// scope between those stores and a peer's loads; ptxas implements every cluster-scope release as MEMBAR.ALL.GPU.
+//   DQN_CLUSTER_BARRIER = 2 (default)  CTA barrier, then ONE thread executes fence.acq_rel.cluster, then every thread
+//                            arrives relaxed and waits with acquire.  The CTA barrier orders every thread's stores before
+//                            thread 0's fence, the fence + thread 0's arrive form a cumulative release pattern at cluster
+//                            scope, the peers' wait.acquire completes the synchronisation: formally ordered, and only
+//                            one warp pays the MEMBAR while the other seven are already parked at the barrier.
+//   DQN_CLUSTER_BARRIER = 1            the stock cluster.sync(): arrive.release + wait.acquire in all 256 threads.
+//   DQN_CLUSTER_BARRIER = 0            CTA barrier + relaxed arrive, no cluster-scope release at all: relies on the CTA
+//                            barrier having drained the stores into the SM's shared memory (what a remote load reads);
+//                            works on B200, outside the memory model -- kept only to measure what the fence costs.
 #ifdef DQN_CLUSTER_STRICT
+#define DQN_CLUSTER_BARRIER 1
+#endif
+#ifndef DQN_CLUSTER_BARRIER
+#define DQN_CLUSTER_BARRIER 2
+#endif
+__device__ __forceinline__ void cluster_barrier_after_local_stores() {
+#if DQN_CLUSTER_BARRIER == 1
   cg::this_cluster().sync();
+#elif DQN_CLUSTER_BARRIER == 2
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 #else
   __syncthreads();
   asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;\n" ::: "memory");

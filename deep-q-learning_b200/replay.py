@@ -92,7 +92,7 @@ class ReplayBuffer:
         if self._stage is not None:
             try:
                 _hoststage.put(self._stage, i, state, action, reward, observation, done)   # the five stores, in C
-            except TypeError:                   # arguments that are not float32 rows / plain scalars: let numpy convert
+            except (TypeError, BufferError, ValueError):   # not C-contiguous float32 rows / plain scalars: let numpy convert
                 self._add_numpy(i, state, action, reward, observation, done)
         else:
             self._add_numpy(i, state, action, reward, observation, done)

@@ -182,6 +182,39 @@ def test_peer_memory_allreduce_kernel(world):
         assert_params_close(ps[0], ora, ill, f"p2p world {world} step {step}")
 
 
+def test_allreduce_timeout_skips_the_update_and_raises(monkeypatch):
+    """A rank that never joins the exchange: the waiting rank's kernel times out WITHOUT summing or storing anything, the
+    Adam kernel behind it is a no-op (parameters, moments untouched), and the next call reports DQN_E_CUDA (sticky)."""
+    import torch
+    monkeypatch.setenv("DQN_B200_COMM_TIMEOUT_MS", "300")
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    ranks = []
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            tr, _ = make(B=256, world=2, rank=r, collective="p2p", connect=False)
+        ranks.append(tr)
+    dqn_b200.LargeBatchTrainer.connect_in_process(ranks)
+    a, b = ranks
+    a.forward_backward()
+    a.synchronize()
+    g_before, p_before = a.grads.clone(), a.get_params()
+    peer_before = b.grads.clone()
+    a.all_reduce()                   # rank 1 never calls it
+    a.apply()                        # enqueued behind the failing exchange: must not touch theta
+    a.synchronize()
+    assert torch.equal(a.grads, g_before) and torch.equal(b.grads, peer_before)       # nothing summed, nothing stored
+    p_after = a.get_params()
+    cnt, mu, _ = a.get_opt_state()
+    for m in O.MODULES:
+        assert np.array_equal(p_after[m]["w"], p_before[m]["w"]) and not mu[m]["w"].any()
+    with pytest.raises(dqn_b200.DqnError):
+        a.all_reduce()
+    with pytest.raises(dqn_b200.DqnError):
+        a.apply()
+    with pytest.raises(dqn_b200.DqnError):
+        a.loss()
+
+
 def test_lb_config_validation():
     with pytest.raises(dqn_b200.DqnError):
         dqn_b200.LargeBatchTrainer(8, 4, (100, 256), 256, 1000, 0.99, dqn_b200.adam(1e-3))

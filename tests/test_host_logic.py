@@ -104,6 +104,52 @@ def test_checkpoint_roundtrip_in_reference_layout(tmp_path, golden):
     assert int(s2[0].count) == 0 and len(s2) == 3
 
 
+def test_checkpoint_loads_with_bare_pickle(tmp_path, golden):
+    """The reference's generate_loading (General/Base/utils.py:31-38) is a bare pickle.load in a process that has optax
+    and knows nothing of this package: the files written here must name optax's state classes, not this package's."""
+    import subprocess
+    import sys
+    import textwrap
+    params = golden_tree(golden["ref_checkpoint"], "params")
+    opt = dqn_b200.adamw(2e-4)
+    d = str(tmp_path / "ckpt")
+    dqn_b200.generate_saving(d)(params, opt.init(params))
+    fake = tmp_path / "site"                       # the two optax modules the pickle names, as optax 0.1.x defines the classes
+    (fake / "optax" / "_src").mkdir(parents=True)
+    (fake / "optax" / "__init__.py").write_text("")
+    (fake / "optax" / "_src" / "__init__.py").write_text("")
+    (fake / "optax" / "_src" / "transform.py").write_text(
+        "from typing import Any, NamedTuple\nclass ScaleByAdamState(NamedTuple):\n    count: Any\n    mu: Any\n    nu: Any\n")
+    (fake / "optax" / "_src" / "base.py").write_text("from typing import NamedTuple\nclass EmptyState(NamedTuple):\n    pass\n")
+    code = textwrap.dedent("""
+        import pickle, sys
+        sys.path.insert(0, %r)
+        params = pickle.load(open(%r, "rb"))
+        st = pickle.load(open(%r, "rb"))
+        assert "deep_q_learning_b200" not in sys.modules and "dqn_b200" not in sys.modules
+        assert type(st[0]).__module__ == "optax._src.transform" and type(st[1]).__module__ == "optax._src.base"
+        assert int(st[0].count) == 0 and len(st) == 3 and st[0].mu["model/~/linear"]["w"].shape == (9, 32)
+        assert params["model/~/linear_3"]["w"].shape == (64, 4) and params["model/~/linear"]["w"].dtype.name == "float32"
+        print("ok")
+    """) % (str(fake), os.path.join(d, "params.pickle"), os.path.join(d, "opt_state.pickle"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert res.returncode == 0 and res.stdout.strip() == "ok", res.stderr
+
+
+def test_add_accepts_strided_observation_with_or_without_hoststage():
+    """ReplayBuffer.add must not depend on whether the optional C staging helper is built: a non-contiguous observation
+    makes the helper refuse the buffer (BufferError / ValueError), and the numpy path takes over."""
+    hs = dqn_b200.pkg.replay._hoststage
+    if hs is None:
+        pytest.skip("_hoststage not built")
+    D, cap = 9, 4
+    a = [np.zeros((cap, D), np.float32), np.zeros(cap, np.int64), np.zeros(cap, np.float32), np.zeros((cap, D), np.float32), np.zeros(cap, np.bool_)]
+    st = hs.new(*[x.ctypes.data for x in a], D, cap)
+    strided = np.arange(2 * D, dtype=np.float32)[::2]
+    with pytest.raises((TypeError, BufferError, ValueError)):
+        hs.put(st, 0, strided, 0, 0.0, np.zeros(D, np.float32), False)
+
+
 def test_loader_reads_the_reference_pickles_when_present(golden):
     ref = "/root/reference/Test/lunar_lander"
     if not os.path.exists(ref):
