@@ -1,25 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- DQN train-steps/sec on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload single|population|replay]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload default|single|population|dp|replay|per|episodes]
 
-Default workload = BASELINE.json configs[1]: single-agent fused dueling double-DQN train step,
-synthetic 1M-transition replay, batch 64, D=8, A=4, hidden (32,64), AdamW(2e-4), gamma .99 on one B200.
-A "step" is one train step (one minibatch: sample -> targets -> loss -> backward -> Adam).  The single
-agent does not shard ("replicas only"), so --gpus N runs N independent replicas, one process
-per GPU, no data-path collective; `value` = all ranks' steps / max-over-ranks device time.
+Main line = BASELINE.json configs[1]: single-agent fused dueling double-DQN train step, synthetic 1M-transition replay,
+batch 64, D=8, A=4, hidden (32,64), AdamW(2e-4), gamma .99 on one B200.  A "step" is one train step (one minibatch:
+sample -> targets -> loss -> backward -> Adam).  The single agent does not shard ("replicas only"), so
+--gpus N runs N independent replicas, one process per GPU, no data-path collective; `value` = all ranks' steps /
+max-over-ranks device time.
 
-  value  : steps/s with everything resident in HBM, K steps fused per persistent launch
-  e2e    : steps/s through the reference-facing API (ReplayBuffer.add x train_frequency from host
-           memory, Agent._step(), loss read back) -- host<->device copies inside the timed region
+  value    steps/s with everything resident in HBM.  One "rep" = exactly --steps train steps (fused, at most 500 per
+           persistent launch); reps are repeated -- L2 flushed before each -- until the timed region is >= 50 ms and the
+           MEDIAN rep is reported (a 20-step rep is 110 us: one sample of it says nothing).
+  e2e      steps/s through the reference-facing API (ReplayBuffer.add x train_frequency from host memory,
+           Agent._step(), loss read back), >= 4000 steps -- host<->device traffic inside the timed region
   roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md "Measurement"
+  extras   (default workload) the sharded workloads AT THE SAME N, each a full line of its own (value, clocks, roofline):
+           population = configs[2] (1024 sweep agents sharded over the ranks, no collective), dp = configs[3] (global batch
+           65536, hidden 1024^2, tcgen05 3xTF32 GEMMs, gradient all-reduce), and on rank 0 replay (>L2 ring) and per
+           (configs[4]); plus K=1/16/256 launch variants and the reference's whole inner loop.
 
-`--impl reference` times the CPU restatement of the reference path (oracle/, numpy; the reference's
-jax/haiku/optax runtime is not installable) on the host cores -- the one place besides cpu_baseline
-where bench.py executes oracle code, and only as the thing the GPU is compared against.
+`--impl reference` times the CPU path of the reference on the host cores: its own numba replay code (ReplayBuffer.add,
+sample_batch -- imported from /root/reference when that tree exists, i.e. in the build container; the oracle's numba
+restatement of the same two functions elsewhere) plus the NumPy oracle of targets / loss / backward / Adam (jax / haiku /
+optax are not installable).  That and `cpu_baseline` are the only places bench.py executes oracle code.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -37,7 +46,10 @@ GAMMA, LR = 0.99, 2e-4
 TRAIN_FREQUENCY = 4                      # Test/lunar_lander.py:30 -- env transitions stored per train step
 REC_BYTES_ALGO = 2 * 4 * D + 8 + 4 + 1   # 77 B per sampled transition in the reference's dtypes
 FLOP_PER_SAMPLE = 25728                  # D=8, H=(32,64): 3 forwards + backward
-STEPS_PER_LAUNCH = int(os.environ.get("DQN_BENCH_KPL", "500"))   # train steps fused into one persistent launch
+STEPS_PER_LAUNCH = int(os.environ.get("DQN_BENCH_KPL", "500"))   # most train steps fused into one persistent launch
+MIN_TIMED_S = 0.05                       # every timed region lasts at least this long (reps of the requested step count)
+MAX_REPS = 2000
+E2E_STEPS = 4000
 
 
 def measured_peaks():
@@ -45,12 +57,12 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1650.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled during the timed region (pynvml thread, 10 ms period)."""
+    """SM clock + throttle reasons sampled during the timed region (pynvml thread, 5 ms period)."""
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -65,24 +77,27 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def _run(self):
+    def _sample(self):
         nv = self.nv
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
                  "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10,
                  "applications_clocks_setting": 0x2}
-        while not self._stop.is_set():
+        try:
+            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
             try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
-                pass
-            time.sleep(0.01)
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for k, bit in names.items():
+                if mask & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
+            time.sleep(0.005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -91,6 +106,8 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.nv is not None and not self.samples:
+            self._sample()
         self._stop.set()
         if self._thr is not None:
             self._thr.join(1.0)
@@ -117,52 +134,147 @@ def synthetic(rng, n):
     return s, a, r, s2, d
 
 
-def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+class Ctx:
+    """Rank / device / process group of this process (one process per GPU under torchrun)."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = self.dist = self.device = None
+
+    def init_gpu(self):
+        import torch
+        self.torch = torch
+        self.device = torch.device(f"cuda:{self.local}")
+        torch.cuda.set_device(self.device)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.device)
+            self.dist = dist
+        return self
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.device)
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+            self.dist = None
+
+
+def flush_l2(torch, device, _buf={}):
+    """Write a 512 MB buffer (4x the 126 MB L2) on the current stream; enqueue only."""
+    key = str(device)
+    if key not in _buf:
+        _buf[key] = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    _buf[key].fill_(1)
+
+
+def timed_reps(ctx, rep_fn, min_seconds=MIN_TIMED_S, max_reps=MAX_REPS, flush=True, min_reps=1):
+    """Run `rep_fn` (enqueues one rep of work on the current stream) until the timed region lasts >= min_seconds.
+    Every rep is bracketed by its own CUDA events on the launching stream (the L2 flush sits between the brackets);
+    barrier + synchronize on both sides of the whole region.  Returns (median rep seconds as the max over ranks, reps,
+    total timed seconds on this rank, this rank's median, clocks)."""
+    torch, device = ctx.torch, ctx.device
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    a, b = ev(), ev()
+    if flush:
+        flush_l2(torch, device)
+    a.record(); rep_fn(); b.record()
+    torch.cuda.synchronize(device)
+    pilot = ctx.max_over_ranks(a.elapsed_time(b) * 1e-3)
+    reps = int(min(max(math.ceil(min_seconds / max(pilot, 1e-7)), min_reps, 1), max(max_reps, min_reps)))
+    starts, ends = [ev() for _ in range(reps)], [ev() for _ in range(reps)]
+    ctx.barrier()
+    with ClockSampler(ctx.local) as clk:
+        for i in range(reps):
+            if flush:
+                flush_l2(torch, device)
+            starts[i].record()
+            rep_fn()
+            ends[i].record()
+        torch.cuda.synchronize(device)
+    ctx.barrier()
+    times = np.array([s.elapsed_time(e) * 1e-3 for s, e in zip(starts, ends)])
+    med_local = float(np.median(times))
+    return ctx.max_over_ranks(med_local), reps, float(times.sum()), med_local, clk.summary()
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle restatement of Agent._step on the host cores
+# reference arm / cpu_baseline: the reference's CPU path of Agent._step on the host cores
 # ---------------------------------------------------------------------------------------------------
 def cpu_reference_steps_per_sec(max_steps, warmup, budget_s, ring=N_RING, seed=0):
+    """q_agent.py:146-169 on the CPU: train_frequency x ReplayBuffer.add + numba sample_batch (the reference's own module
+    when /root/reference exists, else the oracle's numba restatement) + the NumPy oracle of preprocessing / targets /
+    loss / grad / optax update.  numba JIT compile and warm-up excluded; BLAS threads 1 and all are both tried."""
     from threadpoolctl import threadpool_limits
     from oracle import dqn_oracle as O
-    from oracle.agent_oracle import OracleAgent
+    from oracle import replay_oracle as R
     rng = np.random.default_rng(seed)
     params = O.init_params(rng, D, A)
-    ora = OracleAgent(params, O.init_opt_state(params), O.OptSpec("adamw", LR), ring, D, GAMMA, B, seed=seed)
-    data = synthetic(rng, ring)
-    r = ora.replay                                              # bulk-fill (equivalent to `ring` add() calls)
-    r.states[:], r.actions[:], r.rewards[:], r.observations[:], r.dones[:] = data
-    r.counter = r.size = ring
+    target = O.tree_copy(params)
+    opt, opt_state = O.OptSpec("adamw", LR), O.init_opt_state(params)
+    ref = R.reference_replay_module()
+    if ref is not None:
+        rb, sample, replay_src = ref.ReplayBuffer(ring, (ring, D), (ring,)), ref.sample_batch, "reference module (General/Base/replay_buffer.py, numba)"
+    else:
+        rb, sample, replay_src = R.OracleReplay(ring, (ring, D), (ring,)), R.numba_sample_batch(), "oracle numba restatement of replay_buffer.py"
+    s, a, r, s2, d = synthetic(rng, ring)
+    a_py, r_py, d_py = a.tolist(), r.tolist(), d.tolist()
+    for i in range(ring):                                        # ReplayBuffer.add x ring (replay_buffer.py:58-65)
+        rb.add(s[i], a_py[i], r_py[i], s2[i], d_py[i])
+    state = {"params": params, "opt": opt_state, "k": 0}
+
+    def step():
+        for _ in range(TRAIN_FREQUENCY):                         # q_agent.py:182
+            k = state["k"] = (state["k"] + 1) % ring
+            rb.add(s[k], a_py[k], r_py[k], s2[k], d_py[k])
+        batch = sample(rb.size, rb.states, rb.actions, rb.rewards, rb.observations, rb.dones, B)   # q_agent.py:147-153
+        state["params"], state["opt"] = O.train_step(state["params"], target, state["opt"], batch, GAMMA, opt)
+
+    step()                                                       # numba compile
     best = None
     ncores = os.cpu_count() or 1
     for threads in sorted({1, ncores}):
         with threadpool_limits(limits=threads):
             for _ in range(max(warmup, 3)):
-                ora.step()
+                step()
             t0 = time.perf_counter()
             done = 0
             while done < max_steps and time.perf_counter() - t0 < budget_s / 2:
-                ora.step()
+                step()
                 done += 1
             dt = time.perf_counter() - t0
         rate = done / dt
         if best is None or rate > best[0]:
             best = (rate, threads, done, dt)
-    return best
+    return best + (replay_src,)
 
 
-def run_reference(args):
-    rank, world, _ = dist_env()
-    if rank != 0:
-        return
-    rate, threads, done, dt = cpu_reference_steps_per_sec(args.steps, args.warmup, budget_s=120.0)
-    sample = f"{done} oracle train steps (B=64, D=8, 1M-slot ring) in {dt:.1f} s, BLAS threads={threads}"
-    line = {
+def run_reference(args, ctx):
+    if ctx.rank != 0:
+        return None
+    rate, threads, done, dt, src = cpu_reference_steps_per_sec(max(args.steps, 20000), args.warmup, budget_s=40.0)
+    sample = (f"{done} CPU steps (4 x ReplayBuffer.add + numba sample_batch + NumPy train step; B=64, D=8, 1M-slot ring) "
+              f"in {dt:.1f} s, BLAS threads={threads} (better of 1 and {os.cpu_count()}); replay half: {src}")
+    return {
         "impl": "reference", "metric": "train_steps_per_sec", "value": rate, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": done, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 / rate, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -170,9 +282,9 @@ def run_reference(args):
         "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "replay_samples_per_sec": rate * B,
-        "note": "numpy restatement of the reference step (jax/haiku/optax not installable); host cores: %d" % (os.cpu_count() or 1),
+        "note": "restated CPU reference (jax/haiku/optax not installable; the numba replay path is the reference's own "
+                "code where /root/reference exists); host cores: %d" % (os.cpu_count() or 1),
     }
-    print(json.dumps(line))
 
 
 def workload_config():
@@ -180,12 +292,12 @@ def workload_config():
             "obs_dim": D, "num_actions": A, "hidden": [32, 64], "batch": B, "ring_slots": N_RING, "gamma": GAMMA,
             "optimizer": "adamw(2e-4, wd 1e-4)", "steps_per_launch": STEPS_PER_LAUNCH,
             "step_kernel": os.environ.get("DQN_B200_STEP_KERNEL", "auto"),
-            "multi_gpu": "replicas only (single agent does not shard)",
-            "l2": "ring 96 MB < 126 MB L2: L2 flushed (512 MB write) before each timed region; every step gathers 64 random, mostly first-touch records"}
+            "multi_gpu": "replicas only (single agent does not shard); the sharded workloads at this N are in extras",
+            "l2": "ring 96 MB < 126 MB L2: L2 flushed (512 MB write) before every timed rep; every step gathers 64 random, mostly first-touch records"}
 
 
 # ---------------------------------------------------------------------------------------------------
-# GPU arm
+# configs[1]: single agent
 # ---------------------------------------------------------------------------------------------------
 def build_agent(dqn_b200, device, seed, session=False):
     rng = np.random.default_rng(seed)
@@ -205,72 +317,36 @@ def build_agent(dqn_b200, device, seed, session=False):
     return agent, data
 
 
-def flush_l2(torch, device):
-    buf = torch.empty(512 << 20, dtype=torch.uint8, device=device)
-    buf.fill_(1)
-    torch.cuda.synchronize(device)
-    del buf
-
-
-def timed_fused(torch, agent, steps, device):
-    """K train steps, STEPS_PER_LAUNCH per persistent launch; CUDA events on the launching stream."""
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    start.record()
-    left = steps
-    while left > 0:
-        k = min(left, STEPS_PER_LAUNCH)
-        agent._steps(k)
-        left -= k
-        launches += 1
-    end.record()
-    torch.cuda.synchronize(device)
-    return start.elapsed_time(end) * 1e-3, launches
-
-
-def run_single(args):
-    import torch
+def run_single(args, ctx, with_extras=True):
     import dqn_b200
-    rank, world, local = dist_env()
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    device = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(device)
-    agent, data = build_agent(dqn_b200, local, seed=rank, session=not args.no_session)
+    torch, device = ctx.torch, ctx.device
+    agent, data = build_agent(dqn_b200, ctx.local, seed=ctx.rank, session=not args.no_session)
     eng = agent._engine
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(device)
+    steps = args.steps
 
     # ---- value: device-resident, fused ----------------------------------------------------------
+    def rep():
+        left = steps
+        while left > 0:
+            k = min(left, STEPS_PER_LAUNCH)
+            agent._steps(k)
+            left -= k
+    launches_per_rep = -(-steps // STEPS_PER_LAUNCH)
     agent._steps(max(args.warmup, 3))
-    flush_l2(torch, device)
-    barrier()
-    with ClockSampler(local) as clk:
-        secs, launches = timed_fused(torch, agent, args.steps, device)
-    barrier()
-    clocks = clk.summary()
-    tmax = torch.tensor([secs], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    secs_max = float(tmax.item())
-    value = world * args.steps / secs_max
+    rep_s, reps, timed_s, rep_local, clocks = timed_reps(ctx, rep)
+    value = ctx.world * steps / rep_s
 
     if args.profile:
-        if rank == 0:
-            print(json.dumps({"profile_only": True, "steps_per_sec": value, "launches": launches}))
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        ctx.barrier()
+        return {"profile_only": True, "steps_per_sec": value, "launches": reps * launches_per_rep} if ctx.rank == 0 else None
 
     # ---- e2e: reference-facing API, host buffers, copies inside the timed region ------------------
-    e2e_steps = int(min(max(args.steps // 20, 200), 5000))
+    e2e_steps = E2E_STEPS
+    nloop = 2000
     rb = agent._replay_buffer
-    s, a, r, s2, d = [x[:TRAIN_FREQUENCY * (e2e_steps + 8)] for x in data]
-    a_py, r_py, d_py = [int(x) for x in a], [float(x) for x in r], [bool(x) for x in d]
+    nhost = TRAIN_FREQUENCY * (max(e2e_steps, nloop) + 16)
+    s, a, r, s2, d = [x[:nhost] for x in data]
+    a_py, r_py, d_py = a.tolist(), r.tolist(), d.tolist()
 
     def e2e_loop(n, off=0):
         last = 0.0
@@ -285,7 +361,7 @@ def run_single(args):
     e2e_loop(8)
     eng.synchronize()                       # (session mode: retire the resident kernel before other work uses the stream)
     flush_l2(torch, device)
-    barrier()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t0 = time.perf_counter()
@@ -294,38 +370,36 @@ def run_single(args):
     e1.record()
     torch.cuda.synchronize(device)
     e2e_wall = time.perf_counter() - t0
-    e2e_secs = max(e0.elapsed_time(e1) * 1e-3, e2e_wall)
-    te = torch.tensor([e2e_secs], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps / float(te.item())
+    e2e_secs = ctx.max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, e2e_wall))
+    e2e_value = ctx.world * e2e_steps / e2e_secs
+    ctx.barrier()
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    extras = {}
+    if ctx.rank == 0 and with_extras:
+        single_extras(args, ctx, dqn_b200, agent, (s, a_py, r_py, s2, d_py), nloop, extras)
+    eng.synchronize()
+    agent._engine.close()
+    del agent, eng, rb
+    if with_extras:                          # every rank takes part in the sharded workloads
+        sharded_extras(args, ctx, extras)
+    if ctx.rank != 0:
+        return None
 
-    # ---- roofline of the dominant kernel (dqn_train_fused_kernel), measured live ---------------
-    peak, peak_src = measured_peaks()
-    launch_s = secs / launches
-    steps_per_launch = args.steps / launches
+    # ---- roofline of the dominant kernel, measured live ---------------------------------------------
+    pk, peak_src = measured_peaks()
+    peak = float(pk["hbm_gbs"])
+    launch_s = rep_local / launches_per_rep
+    steps_per_launch = steps / launches_per_rep
     algo_bytes = steps_per_launch * (B * REC_BYTES_ALGO + 4)          # gathered records + one loss store per step
     achieved = algo_bytes / launch_s / 1e9
     sm_hz = (clocks["sm_mhz"] or 1965) * 1e6
     fp32_one_sm = 128 * 2 * sm_hz / 1e9
-    flops = B * FLOP_PER_SAMPLE / (secs / args.steps) / 1e9
+    flops = B * FLOP_PER_SAMPLE / (rep_local / steps) / 1e9
     cluster = args.step_kernel in ("auto", "cluster")
     n_sm = 4 if cluster else 1
     kname = "dqn_train_cluster_kernel<4>" if cluster else "dqn_train_fused_kernel<4>"
-    traffic = None
-    try:      # DRAM bytes of one launch from the committed ncu --set full capture, scaled to this run's steps per launch
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tr = json.load(f)[kname]
-        traffic = tr["dram_bytes_per_launch"] / tr["steps_per_launch"] * steps_per_launch
-    except Exception:
-        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": kname, "peak_source": peak_src,
+                "traffic": traffic_from_profile(kname, "steps_per_launch", steps_per_launch), "kernel": kname, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": launch_s * 1e3,
                 "note": "latency-bound by construction: one agent's steps are a serial chain (step t+1 needs theta_t) on %s; "
                         "theta/theta^-/grads stay in shared memory, so the only HBM traffic is 64 gathered records per step "
@@ -333,36 +407,83 @@ def run_single(args):
                 "fp32": {"achieved_gflops": flops, "sms_used": n_sm, "ffma_peak_gflops_of_sms_used": n_sm * fp32_one_sm,
                          "frac_of_sms_used": flops / (n_sm * fp32_one_sm), "flop_per_step": B * FLOP_PER_SAMPLE}}
 
-    # ---- K=1 launches (launch-bound variant) and replay-gather throughput, for the record -----------
-    extras = {}
+    # ---- CPU baseline on the host cores, bounded sample (rank 0, N = 1 only) ---------------------------
+    cpu = None
+    if ctx.world == 1 and not args.no_cpu_baseline:
+        rate, threads, done, dt, src = cpu_reference_steps_per_sec(20000, 50, budget_s=24.0)
+        cpu = {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
+               "sample": f"{done} CPU steps of the same workload (4 x ReplayBuffer.add + numba sample_batch + NumPy train step) in {dt:.1f} s, "
+                         f"BLAS threads={threads} (better of 1 and {os.cpu_count()}), host cores={os.cpu_count()}; replay half: {src}"}
+
+    return {
+        "metric": "train_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": ctx.world, "steps": steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": rep_s / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+        "clocks": clocks,
+        "timing": {"reps": reps, "steps_per_rep": steps, "launches_per_rep": launches_per_rep, "statistic": "median rep, max over ranks",
+                   "timed_region_s": timed_s, "min_timed_region_s": MIN_TIMED_S},
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": TRAIN_FREQUENCY * REC_BYTES_ALGO,
+                "d2h_bytes_per_step": 4, "steps": e2e_steps, "timed_region_s": e2e_secs,
+                "api": "ReplayBuffer.add x4 (host numpy) + Agent._step() + loss readback per step"
+                       + ("" if args.no_session else "; Agent(session=True): commands served by the resident train-step kernel")},
+        "gpu_launches": reps * launches_per_rep, "replay_samples_per_sec": value * B,
+        "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
+    }
+
+
+def traffic_from_profile(kname, per_key, units):
+    """DRAM bytes of one launch from the committed ncu --set full capture, scaled to this run's work per launch."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f)[kname]
+            return tr["dram_bytes_per_launch"] / tr[per_key] * units
+        except Exception:
+            continue
+    return None
+
+
+def guarded(extras, key, fn):
+    """One failing extra never drops the others (nor the main line)."""
     try:
-        k1 = 2000
-        eng.set_session(0)                                         # K = 1 launches: one kernel launch per Agent._step()
-        agent._steps(1)
-        torch.cuda.synchronize(device)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(k1):
-            agent._step()
-        s1.record()
-        torch.cuda.synchronize(device)
-        extras["k1_steps_per_sec"] = k1 / (s0.elapsed_time(s1) * 1e-3)
-        for kk in (16, 256):                                       # K fused steps per launch
+        extras[key] = fn()
+    except Exception as ex:
+        extras[key] = {"error": repr(ex)}
+
+
+def single_extras(args, ctx, dqn_b200, agent, host, nloop, extras):
+    """Rank 0: launch-count variants of the single-agent step and the reference's whole inner loop."""
+    torch, device = ctx.torch, ctx.device
+    eng, rb = agent._engine, agent._replay_buffer
+    s, a_py, r_py, s2, d_py = host
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def k_variant(kk):
+        def run():
+            eng.set_session(0)                                     # launches, not the resident kernel
             agent._steps(kk)
             torch.cuda.synchronize(device)
-            n_l = max(4096 // kk, 8)
+            n_l = max(8192 // kk, 16)
             s0.record()
             for _ in range(n_l):
-                agent._steps(kk)
+                if kk == 1:
+                    agent._step()                                  # one kernel launch per Agent._step()
+                else:
+                    agent._steps(kk)
             s1.record()
             torch.cuda.synchronize(device)
-            extras["k%d_steps_per_sec" % kk] = n_l * kk / (s0.elapsed_time(s1) * 1e-3)
-        eng.set_session(0 if args.no_session else 1)
+            return n_l * kk / (s0.elapsed_time(s1) * 1e-3)
+        return run
+    for kk in (1, 16, 256):                                        # SURVEY 8(d) config 2: K fused steps per launch
+        guarded(extras, "k%d_steps_per_sec" % kk, k_variant(kk))
+
+    def env_loop_run():
         # the reference's whole inner loop (q_agent.py:174-189) with a greedy policy call per env transition:
         # train_frequency x (_policy -> add) + _step + loss read
-        nloop = 2000
+        eng.set_session(0 if args.no_session else 1)
         agent._epsilon = 0.0
-        states1 = s[:TRAIN_FREQUENCY * (nloop + 8)].reshape(-1, 1, D)
+        states1 = s.reshape(-1, 1, D)
+
         def env_loop(n, off):
             for i in range(n):
                 for j in range(TRAIN_FREQUENCY):
@@ -375,37 +496,48 @@ def run_single(args):
         c0 = time.perf_counter()
         env_loop(nloop, 8 * TRAIN_FREQUENCY)
         eng.synchronize()
-        extras["env_loop_steps_per_sec"] = nloop / (time.perf_counter() - c0)
-        extras["env_loop_note"] = "%d x (greedy Agent._policy + ReplayBuffer.add) + Agent._step + loss per step, wall clock" % TRAIN_FREQUENCY
-        extras["replay_gather"] = bench_gather(torch, dqn_b200, eng, device, peak)
-    except Exception as ex:       # extras never invalidate the main line
-        extras["error"] = repr(ex)
+        return {"value": nloop / (time.perf_counter() - c0), "unit": "steps/s", "steps": nloop,
+                "note": "%d x (greedy Agent._policy + ReplayBuffer.add) + Agent._step + loss per step, wall clock" % TRAIN_FREQUENCY}
+    guarded(extras, "env_loop", env_loop_run)
+    pk, _ = measured_peaks()
+    guarded(extras, "replay_gather_l2_resident", lambda: bench_gather(torch, dqn_b200, eng, device, float(pk["hbm_gbs"])))
 
-    # ---- CPU baseline (oracle port on the host cores), bounded sample ---------------------------------
-    rate, threads, done, dt = cpu_reference_steps_per_sec(20000, 50, budget_s=30.0)
-    cpu = {"value": rate, "unit": "steps/s", "cores": threads, "kind": "port",
-           "sample": f"{done} oracle train steps (same workload) in {dt:.1f} s, BLAS threads={threads}, host cores={os.cpu_count()}"}
 
-    line = {
-        "metric": "train_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": TRAIN_FREQUENCY * REC_BYTES_ALGO,
-                "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "api": "ReplayBuffer.add x4 (host numpy) + Agent._step() + loss readback per step"
-                       + ("" if args.no_session else "; Agent(session=True): commands served by the resident train-step kernel")},
-        "gpu_launches": launches, "replay_samples_per_sec": value * B,
-        "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
-    }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+def sharded_extras(args, ctx, extras):
+    """Every rank: the workloads that DO shard, at this N, each under its own guard; rank 0 alone: replay, per."""
+    sub = argparse.Namespace(**vars(args))
+    sub.steps, sub.warmup, sub.agents, sub.steps_per_launch = 256, 3, 1024, 128
+    for key, fn in (("population", run_population),):
+        try:
+            line = fn(sub, ctx)
+        except Exception as ex:
+            line = {"error": repr(ex)}
+        if ctx.rank == 0:
+            extras[key] = line
+        ctx.torch.cuda.empty_cache()
+    sub = argparse.Namespace(**vars(args))
+    sub.steps, sub.warmup, sub.gemm, sub.collective, sub.batch, sub.hidden = 20, 3, "tc3xtf32", "auto", 65536, 1024
+    try:
+        line = run_dp(sub, ctx)
+    except Exception as ex:
+        line = {"error": repr(ex)}
+    if ctx.rank == 0:
+        extras["dp"] = line
+    ctx.torch.cuda.empty_cache()
+    if ctx.rank == 0:
+        sub = argparse.Namespace(**vars(args))
+        sub.steps, sub.warmup = 40, 3
+        guarded(extras, "replay", lambda: run_replay(sub, ctx))
+        ctx.torch.cuda.empty_cache()
+        sub.steps = 400
+        guarded(extras, "per", lambda: run_per(sub, ctx))
+        ctx.torch.cuda.empty_cache()
+    ctx.barrier()
 
 
 def bench_gather(torch, dqn_b200, eng, device, peak):
-    """sample_batch as a standalone HBM-bound kernel: 65536 Philox-indexed samples per launch from the
-    1M-slot ring into SoA outputs (reads 77 B + writes 77 B algorithmic per sample)."""
+    """sample_batch as a standalone kernel: 65536 Philox-indexed samples per launch from the (L2-resident) 1M-slot ring
+    into SoA outputs (reads 77 B + writes 77 B algorithmic per sample); the HBM-bound figure is extras.replay."""
     import ctypes as C
     nb = 65536
     outs = [torch.empty(nb * D, dtype=torch.float32, device=device), torch.empty(nb, dtype=torch.int64, device=device),
@@ -413,10 +545,10 @@ def bench_gather(torch, dqn_b200, eng, device, peak):
             torch.empty(nb, dtype=torch.uint8, device=device)]
     lib, chk = eng.lib, dqn_b200.pkg._lib.check
     ptrs = [C.c_void_p(t.data_ptr()) for t in outs]
+    eng.set_session(0)
     for i in range(5):
         chk(lib.dqn_sample_batch_device(eng.h, 0, None, i, nb, *ptrs))
-    flush_l2(torch, device)
-    reps = 50
+    reps = 200
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for i in range(reps):
@@ -426,24 +558,21 @@ def bench_gather(torch, dqn_b200, eng, device, peak):
     dt = s0.elapsed_time(s1) * 1e-3 / reps
     gbs = nb * 2 * REC_BYTES_ALGO / dt / 1e9
     return {"samples_per_sec": nb / dt, "batch": nb, "us_per_launch": dt * 1e6, "achieved_gbs": gbs,
-            "frac_of_hbm_peak": gbs / peak, "note": "ring (96 MB) fits in L2; see profiles/ for the >L2 ring measurement"}
+            "frac_of_hbm_peak": gbs / peak, "note": "ring (96 MB) fits in L2"}
 
 
-def run_population(args):
-    """BASELINE configs[2]: 1024 independent agents of the hyper-parameter sweep (per-agent gamma, batch in
-    [38,70), Adam 1e-4, 40k-slot ring each), one CTA per agent, sharded over the ranks with NO data-path
-    collective.  `value` = aggregate agent-train-steps/s; total work is fixed -> strong scaling."""
+# ---------------------------------------------------------------------------------------------------
+# configs[2]: population of sweep agents, sharded, no collective
+# ---------------------------------------------------------------------------------------------------
+def run_population(args, ctx):
+    """1024 independent agents of the hyper-parameter sweep (per-agent gamma, batch in [38,70], Adam 1e-4, 40k-slot ring
+    each), sharded over the ranks with NO data-path collective.  `value` = aggregate agent-train-steps/s; total work is
+    fixed -> strong scaling.  One rep = `steps` train steps of every agent (steps_per_launch per launch)."""
     import ctypes as C
-    import torch
     import dqn_b200
-    rank, world, local = dist_env()
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    device = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(device)
+    torch, device = ctx.torch, ctx.device
     n_global, ring = args.agents, 40_000                         # Test/lunar_lander_hyper_params.py:22
-    pop = dqn_b200.Population(n_global, D, A, ring, dqn_b200.adam(1e-4), rank=rank, world_size=world, seed=1, device=local)
+    pop = dqn_b200.Population(n_global, D, A, ring, dqn_b200.adam(1e-4), rank=ctx.rank, world_size=ctx.world, seed=1, device=ctx.local)
     eng, lib, chk = pop.engine, pop.engine.lib, dqn_b200.pkg._lib.check
     # synthetic transitions generated on the device (torch as RNG/allocator only), one block per agent
     g = torch.Generator(device=device)
@@ -457,68 +586,63 @@ def run_population(args):
         chk(lib.dqn_store_device(eng.h, i, ring, C.c_void_p(s.data_ptr()), C.c_void_p(a.data_ptr()), C.c_void_p(r.data_ptr()),
                                  C.c_void_p(s2.data_ptr()), C.c_void_p(d.data_ptr())))
     torch.cuda.synchronize(device)
-    kpl = args.steps_per_launch
+    kpl = max(1, min(args.steps_per_launch, args.steps))
     steps = max(kpl, (args.steps // kpl) * kpl)
     pop.train_steps(max(args.warmup, 3))
-    flush_l2(torch, device)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(device)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record()
+
+    def rep():
         for _ in range(steps // kpl):
             pop.train_steps(kpl)
-        e1.record()
-        torch.cuda.synchronize(device)
-    secs = e0.elapsed_time(e1) * 1e-3
-    t = torch.tensor([secs], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    secs_max = float(t.item())
-    if rank == 0:
-        mean_b = float(np.mean([h["batch_size"] for h in dqn_b200.sweep_hparams(n_global)]))
-        value = n_global * steps / secs_max
-        sm_hz = (clk.summary()["sm_mhz"] or 1965) * 1e6
-        fp32_peak = world * 148 * 128 * 2 * sm_hz / 1e9
-        flops = value * mean_b * FLOP_PER_SAMPLE / 1e9
-        peak, peak_src = measured_peaks()
-        gbs = value * mean_b * REC_BYTES_ALGO / 1e9
-        traffic = None
-        try:      # DRAM bytes of one launch from the committed ncu capture, scaled to this rank's agents x steps per launch
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                tr = json.load(f)["dqn_train_fused_kernel<4>/population"]
-            traffic = tr["dram_bytes_per_launch"] / tr["agent_steps_per_launch"] * pop.n_local * kpl
-        except Exception:
-            pass
-        print(json.dumps({
-            "metric": "agent_train_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": secs_max / steps * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[2]: population of %d independent sweep agents, one CTA per agent, sharded over ranks, no collective" % n_global,
-                       "obs_dim": D, "num_actions": A, "hidden": [32, 64], "ring_slots_per_agent": ring, "mean_batch": mean_b,
-                       "optimizer": "adam(1e-4)", "steps_per_launch": kpl, "l2": "rings total %.1f GB per rank >> L2" % (pop.n_local * ring * 96 / 1e9)},
-            "clocks": clk.summary(), "gpu_launches": steps // kpl,
-            "replay_samples_per_sec": value * mean_b,
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s", "frac": gbs / (peak * world), "traffic": traffic,
-                         "kernel": "dqn_train_fused_kernel<4>", "peak_source": peak_src,
-                         "note": "compute-bound on the fp32 pipe, not HBM: see fp32",
-                         "fp32": {"achieved_gflops": flops, "ffma_peak_gflops": fp32_peak, "frac": flops / fp32_peak}}}))
-    if world > 1:
-        dist.destroy_process_group()
+    rep_s, reps, timed_s, rep_local, clocks = timed_reps(ctx, rep)
+    hp_all = dqn_b200.sweep_hparams(n_global)
+    local_tiles = sum((hp["batch_size"] + 63) // 64 for hp in pop.hparams)
+    max_tiles = ctx.max_over_ranks(local_tiles)
+    # every rank's parameters after the run, hashed: a sharded run must reproduce the unsharded one agent by agent
+    digest = float(np.frombuffer(pop.params_flat(0).tobytes()[:8], dtype=np.uint32)[0] & 0xFFFFFF)
+    digest_sum = ctx.sum_over_ranks(digest)
+    n_local = pop.n_local
+    pop.engine.close()
+    del pop, eng
+    if ctx.rank != 0:
+        return None
+    mean_b = float(np.mean([h["batch_size"] for h in hp_all]))
+    two_tile = float(np.mean([h["batch_size"] > 64 for h in hp_all]))
+    value = n_global * steps / rep_s
+    sm_hz = (clocks["sm_mhz"] or 1965) * 1e6
+    fp32_peak = ctx.world * 148 * 128 * 2 * sm_hz / 1e9
+    flops = value * mean_b * FLOP_PER_SAMPLE / 1e9
+    pk, peak_src = measured_peaks()
+    peak = float(pk["hbm_gbs"])
+    gbs = value * mean_b * REC_BYTES_ALGO / 1e9
+    return {
+        "metric": "agent_train_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": ctx.world, "steps": steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": rep_s / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: population of %d independent sweep agents, one CTA per agent, sharded over ranks, no collective" % n_global,
+                   "obs_dim": D, "num_actions": A, "hidden": [32, 64], "ring_slots_per_agent": ring, "mean_batch": mean_b,
+                   "agents_with_batch_over_64": two_tile, "agents_per_rank": n_local, "tiles_on_busiest_rank": max_tiles,
+                   "optimizer": "adam(1e-4)", "steps_per_launch": kpl, "l2": "rings total %.1f GB per rank >> L2; flushed before every rep" % (n_local * ring * 96 / 1e9)},
+        "clocks": clocks, "gpu_launches": reps * (steps // kpl),
+        "timing": {"reps": reps, "steps_per_rep": steps, "statistic": "median rep, max over ranks", "timed_region_s": timed_s},
+        "replay_samples_per_sec": value * mean_b, "param_digest_sum": digest_sum,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * ctx.world, "unit": "GB/s", "frac": gbs / (peak * ctx.world),
+                     "traffic": traffic_from_profile("dqn_train_fused_kernel<4>/population", "agent_steps_per_launch", n_local * kpl),
+                     "kernel": "dqn_train_fused_kernel<4>", "peak_source": peak_src,
+                     "note": "compute-bound on the fp32 pipe, not HBM: see fp32",
+                     "fp32": {"achieved_gflops": flops, "ffma_peak_gflops": fp32_peak, "frac": flops / fp32_peak}}}
 
 
-def run_replay(args):
-    """Replay path alone, HBM-bound: 16M-slot ring (1.5 GB >> L2), 1M transitions per launch.  store = ReplayBuffer.add x 1M
-    (SoA device arrays -> AoS ring), gather = sample_batch with Philox indices (ring -> the reference's five SoA arrays)."""
+# ---------------------------------------------------------------------------------------------------
+# replay path alone (HBM-bound)
+# ---------------------------------------------------------------------------------------------------
+def run_replay(args, ctx):
+    """16M-slot ring (1.5 GB >> L2), 1M transitions per launch.  store = ReplayBuffer.add x 1M (SoA device arrays -> AoS
+    ring), gather = sample_batch with Philox indices (ring -> the reference's five SoA arrays)."""
     import ctypes as C
-    import torch
     import dqn_b200
-    device = torch.device("cuda:0")
-    torch.cuda.set_device(device)
+    torch, device = ctx.torch, ctx.device
     ring, nb = 16 * 2**20, 2**20
-    eng = dqn_b200.DqnEngine(D, A, ring, B, GAMMA, dqn_b200.adamw(LR), seed=0, device=0)
+    eng = dqn_b200.DqnEngine(D, A, ring, B, GAMMA, dqn_b200.adamw(LR), seed=0, device=ctx.local)
     lib, chk = eng.lib, dqn_b200.pkg._lib.check
     g = torch.Generator(device=device); g.manual_seed(0)
     src = [torch.randn(nb, D, generator=g, device=device), torch.randint(0, A, (nb,), generator=g, device=device, dtype=torch.int64),
@@ -532,8 +656,9 @@ def run_replay(args):
         chk(lib.dqn_sample_batch_device(eng.h, 0, None, i, nb, *op))
     steps = max(min(args.steps, 200), 10)
     flush_l2(torch, device)
+    torch.cuda.synchronize(device)
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    with ClockSampler(0) as clk:
+    with ClockSampler(ctx.local) as clk:
         e[0].record()
         for i in range(steps):
             chk(lib.dqn_sample_batch_device(eng.h, 0, None, 100 + i, nb, *op))
@@ -543,38 +668,40 @@ def run_replay(args):
         e[2].record()
         torch.cuda.synchronize(device)
     tg, ts = e[0].elapsed_time(e[1]) * 1e-3 / steps, e[1].elapsed_time(e[2]) * 1e-3 / steps
-    peak, peak_src = measured_peaks()
+    eng.close()
+    pk, peak_src = measured_peaks()
+    peak = float(pk["hbm_gbs"])
     gbs_g, gbs_s = nb * 2 * REC_BYTES_ALGO / tg / 1e9, nb * 2 * REC_BYTES_ALGO / ts / 1e9
-    print(json.dumps({
+    return {
         "metric": "replay_samples_per_sec", "value": nb / tg, "unit": "samples/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": tg * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "replay path alone: 16M-slot ring (1.5 GB), 1M Philox-indexed samples per launch (sample_batch), 1M transitions per store",
-                   "obs_dim": D, "l2": "ring 1.5 GB >> 126 MB L2; 512 MB flush before the timed region"},
+                   "obs_dim": D, "l2": "ring 1.5 GB >> 126 MB L2 (every launch streams 100+ MB of random records); 512 MB flush before the timed region"},
         "clocks": clk.summary(), "gpu_launches": 2 * steps, "replay_stores_per_sec": nb / ts,
-        "roofline": {"bound": "hbm", "achieved": gbs_g, "peak": peak, "unit": "GB/s", "frac": gbs_g / peak, "traffic": None, "peak_source": peak_src,
+        "timing": {"timed_region_s": (tg + ts) * steps},
+        "roofline": {"bound": "hbm", "achieved": gbs_g, "peak": peak, "unit": "GB/s", "frac": gbs_g / peak, "peak_source": peak_src,
+                     "traffic": traffic_from_profile("replay_gather_kernel", "samples_per_launch", nb),
                      "kernel": "replay_gather_kernel", "algorithmic_bytes_per_launch": nb * 2 * REC_BYTES_ALGO,
-                     "note": "77 B read + 77 B written per sample (reference dtypes); records are 96-byte AoS, so a random sample moves 3 sectors "
-                             "= 96 B of DRAM for 77 B; store kernel: %.0f GB/s algorithmic (%.3f of peak)" % (gbs_s, gbs_s / peak)}}))
+                     "store": {"achieved": gbs_s, "frac": gbs_s / peak, "kernel": "replay_store_kernel"},
+                     "note": "77 B read + 77 B written per sample (reference dtypes); records are 96-byte AoS, so a random sample moves two 64-byte "
+                             "DRAM atoms = 128 B for 77 B"}}
 
 
-def run_episodes(args):
+# ---------------------------------------------------------------------------------------------------
+# episode loop of a population on the device
+# ---------------------------------------------------------------------------------------------------
+def run_episodes(args, ctx):
     """The reference's whole per-env-step loop (q_agent.py:174-203) for a population, on the device: epsilon-greedy policy ->
     (synthetic vectorised env) -> observe (store + episode bookkeeping + train gate) -> gated train step + hard sync.
     `value` = aggregate env steps/s; train steps happen on each agent's own train_frequency cadence (sweep draw, 2..15)."""
-    import torch
     import dqn_b200
     from threadpoolctl import threadpool_limits
-    rank, world, local = dist_env()
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    device = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(device)
+    torch, device = ctx.torch, ctx.device
     n_global, ring, T = args.agents, 40_000, 64
-    pop = dqn_b200.Population(n_global, D, A, ring, dqn_b200.adam(1e-4), rank=rank, world_size=world, seed=1, device=local)
+    pop = dqn_b200.Population(n_global, D, A, ring, dqn_b200.adam(1e-4), rank=ctx.rank, world_size=ctx.world, seed=1, device=ctx.local)
     n = pop.n_local
     pop.configure_episodes(max_episodes=10000, max_steps=1500, training_start=500, reward_to_reach=240.0)   # lunar_lander_hyper_params.py:22-30
-    g = torch.Generator(device=device); g.manual_seed(77 + rank)
+    g = torch.Generator(device=device); g.manual_seed(77 + ctx.rank)
     obs = torch.randn(T, n, D, generator=g, device=device)
     rew = 2.0 * torch.randn(T, n, generator=g, device=device)
     done = (torch.rand(T, n, generator=g, device=device) < 0.01).to(torch.uint8)
@@ -592,77 +719,66 @@ def run_episodes(args):
     warm = 520                                                    # past training_start = 500: the train gate is live
     env_steps(warm, 0)
     torch.cuda.synchronize(device)
-    steps = max(args.steps, 64)
+    steps = max(args.steps, 1024)
     trained0 = sum(pop.engine.train_step_count(i) for i in range(n))
     flush_l2(torch, device)
-    if world > 1:
-        dist.barrier()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with ClockSampler(ctx.local) as clk:
         e0.record()
         env_steps(steps, warm)
         e1.record()
         torch.cuda.synchronize(device)
-    secs = e0.elapsed_time(e1) * 1e-3
-    trained = sum(pop.engine.train_step_count(i) for i in range(n)) - trained0
-    t = torch.tensor([secs, float(trained)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.barrier()
-        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        secs, trained = float(tm[0].item()), float(ts[1].item())
-    if rank == 0:
-        # CPU side: the restated reference loop (oracle) for one agent on one core, same cadence parameters
-        from oracle import dqn_oracle as O
-        from oracle.agent_oracle import OracleAgent
-        from oracle.episode_oracle import EpisodeOracle
-        hp = pop.hparams[0]
-        rng = np.random.default_rng(0)
-        theta = O.init_params(rng, D, A)
-        oa = OracleAgent(theta, O.init_opt_state(theta), O.OptSpec("adam", 1e-4), ring, D, hp["gamma"], hp["batch_size"], seed=1)
-        eo = EpisodeOracle(oa, hp["epsilon"], hp["epsilon_decay_rate"], hp["min_epsilon"], 10000, 1500, 500, hp["train_frequency"],
-                           hp["replace_frequency"], 240.0, A, seed=1)
-        so, ro = rng.standard_normal((4096, D)).astype(np.float32), (2 * rng.standard_normal(4096)).astype(np.float32)
-        with threadpool_limits(limits=1):
-            for i in range(520):
-                eo.observe(so[i], eo.policy(so[i])[0], ro[i], so[i + 1], False)
-            c0 = time.perf_counter(); k = 0
-            while time.perf_counter() - c0 < 10.0:
-                i = 520 + k % 3000
-                eo.observe(so[i], eo.policy(so[i])[0], ro[i], so[i + 1], False)
-                k += 1
-            cpu_rate = k / (time.perf_counter() - c0)
-        print(json.dumps({
-            "metric": "env_steps_per_sec", "value": n_global * steps / secs, "unit": "agent-env-steps/s", "n_gpus": world, "steps": steps,
-            "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "population of %d sweep agents, full device-side episode loop (policy -> observe -> gated train -> sync), "
-                                   "synthetic vectorised env" % n_global, "obs_dim": D, "num_actions": A, "ring_slots_per_agent": ring,
-                       "l2": "rings %.1f GB per rank >> L2" % (n * ring * 96 / 1e9)},
-            "clocks": clk.summary(), "gpu_launches": int(steps * 3.5), "agent_train_steps_per_sec": trained / secs,
-            "cpu_baseline": {"value": cpu_rate, "unit": "agent-env-steps/s", "cores": 1, "kind": "port",
-                             "sample": "%d env steps of ONE agent (train_frequency %d) through oracle/episode_oracle.py in 10 s" % (k, hp["train_frequency"])}}))
-    if world > 1:
-        dist.destroy_process_group()
+    secs = ctx.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    trained = ctx.sum_over_ranks(sum(pop.engine.train_step_count(i) for i in range(n)) - trained0)
+    ctx.barrier()
+    if ctx.rank != 0:
+        return None
+    # CPU side: the restated reference loop (oracle) for one agent on one core, same cadence parameters
+    from oracle import dqn_oracle as O
+    from oracle.agent_oracle import OracleAgent
+    from oracle.episode_oracle import EpisodeOracle
+    hp = pop.hparams[0]
+    rng = np.random.default_rng(0)
+    theta = O.init_params(rng, D, A)
+    oa = OracleAgent(theta, O.init_opt_state(theta), O.OptSpec("adam", 1e-4), ring, D, hp["gamma"], hp["batch_size"], seed=1)
+    eo = EpisodeOracle(oa, hp["epsilon"], hp["epsilon_decay_rate"], hp["min_epsilon"], 10000, 1500, 500, hp["train_frequency"],
+                       hp["replace_frequency"], 240.0, A, seed=1)
+    so, ro = rng.standard_normal((4096, D)).astype(np.float32), (2 * rng.standard_normal(4096)).astype(np.float32)
+    with threadpool_limits(limits=1):
+        for i in range(520):
+            eo.observe(so[i], eo.policy(so[i])[0], ro[i], so[i + 1], False)
+        c0 = time.perf_counter(); k = 0
+        while time.perf_counter() - c0 < 10.0:
+            i = 520 + k % 3000
+            eo.observe(so[i], eo.policy(so[i])[0], ro[i], so[i + 1], False)
+            k += 1
+        cpu_rate = k / (time.perf_counter() - c0)
+    return {
+        "metric": "env_steps_per_sec", "value": n_global * steps / secs, "unit": "agent-env-steps/s", "n_gpus": ctx.world, "steps": steps,
+        "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "population of %d sweep agents, full device-side episode loop (policy -> observe -> gated train -> sync), "
+                               "synthetic vectorised env" % n_global, "obs_dim": D, "num_actions": A, "ring_slots_per_agent": ring,
+                   "l2": "rings %.1f GB per rank >> L2" % (n * ring * 96 / 1e9)},
+        "clocks": clk.summary(), "gpu_launches": int(steps * 3.5), "agent_train_steps_per_sec": trained / secs,
+        "cpu_baseline": {"value": cpu_rate, "unit": "agent-env-steps/s", "cores": 1, "kind": "port",
+                         "sample": "%d env steps of ONE agent (train_frequency %d) through oracle/episode_oracle.py in 10 s" % (k, hp["train_frequency"])}}
 
 
-def run_dp(args):
-    """BASELINE configs[3]: large-batch data-parallel DDQN, global batch 65536, hidden 1024x1024, D=8, A=4.
-    Each rank: forward+backward on B/world rows -> ONE NCCL all-reduce of P+1 floats -> identical Adam.
-    `value` = global train steps/s (strong scaling: the global batch is fixed)."""
-    import ctypes as C
-    import torch
+# ---------------------------------------------------------------------------------------------------
+# configs[3]: large-batch data-parallel step
+# ---------------------------------------------------------------------------------------------------
+def run_dp(args, ctx):
+    """Large-batch data-parallel DDQN, global batch 65536, hidden 1024x1024, D=8, A=4.  Each rank: forward+backward on
+    B/world rows -> ONE all-reduce of P+1 floats -> identical Adam.  `value` = global train steps/s (strong scaling:
+    the global batch is fixed).  One rep = one step; the median of max(steps, 50 ms worth) reps is reported."""
+    import hashlib
     import dqn_b200
-    rank, world, local = dist_env()
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    device = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(device)
+    torch, device = ctx.torch, ctx.device
     Bg, H, ring = args.batch, (args.hidden, args.hidden), 1_000_000
-    tr = dqn_b200.LargeBatchTrainer(D, A, H, Bg, ring, GAMMA, dqn_b200.adamw(LR), rank=rank, world_size=world, seed=3,
-                                    device=local, gemm_mode=args.gemm, collective=args.collective)
-    params = dqn_b200.Model(A, hidden=H).init(np.random.default_rng(0), np.zeros((1, D), np.float32)) if False else None
+    tr = dqn_b200.LargeBatchTrainer(D, A, H, Bg, ring, GAMMA, dqn_b200.adamw(LR), rank=ctx.rank, world_size=ctx.world, seed=3,
+                                    device=ctx.local, gemm_mode=args.gemm, collective=args.collective)
     rng = np.random.default_rng(0)
     tree = {}
     for name, (fi, fo) in zip(dqn_b200.pkg.specs.MODULES, dqn_b200.pkg.specs.layer_shapes(D, A, H)):
@@ -680,74 +796,71 @@ def run_dp(args):
     del s, s2, r, a, d
     for _ in range(max(args.warmup, 3)):
         tr.step()
-    flush_l2(torch, device)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(device)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            tr.step()
-        e1.record()
-        torch.cuda.synchronize(device)
-    secs = e0.elapsed_time(e1) * 1e-3
-    t = torch.tensor([secs], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    secs_max = float(t.item())
+    rep_s, reps, timed_s, rep_local, clocks = timed_reps(ctx, tr.step, min_reps=args.steps, max_reps=max(args.steps, 200))
     loss = tr.loss()
-    if rank == 0:
-        flop_per_sample = 3 * 2 * (D * H[0] + H[0] * H[1] + H[1] * (1 + A)) + (2 * (D * H[0] + H[0] * H[1] + H[1] * (1 + A)) + 2 * (H[0] * H[1] + H[1] * (1 + A)))
-        tflops = Bg * flop_per_sample * args.steps / secs_max / 1e12
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            pk = json.load(f)
-        mode_factor = {"fp32": None, "tc3xtf32": 6.0}[args.gemm]      # tf32 = 1/2 of bf16, 3 MMAs per product
-        peak = pk["bf16_tflops_sustained"] * world
-        print(json.dumps({
-            "metric": "train_steps_per_sec", "value": args.steps / secs_max, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else "f32 via 3xTF32 tensor-core split", "data": "synthetic",
-            "config": {"workload": "configs[3]: large-batch data-parallel DDQN, global batch %d, hidden %dx%d" % (Bg, H[0], H[1]),
-                       "obs_dim": D, "num_actions": A, "batch_local": Bg // world, "gemm": args.gemm,
-                       "collective": {"p2p": "own kernel over NVLink peer memory (csrc/comm_p2p.cu), %d floats", "nccl": "NCCL all-reduce of %d floats",
-                                      "none": "none (1 GPU), %d floats"}[tr.collective] % (tr.P + 1),
-                       "l2": "activations %.1f GB per rank >> L2" % (3 * 2 * (Bg // world) * H[0] * 4 / 1e9)},
-            # 18 kernels per step on every rank (index draw, gather, layer 1, 4 GEMMs, head, targets, 2 bias finishes, dh2, 3 partial
-            # reductions, head grads, dW1, Adam) + the W2 transpose of the tensor-core mode + the peer-memory all-reduce when world > 1
-            "clocks": clk.summary(),
-            "gpu_launches": args.steps * (18 + (1 if args.gemm == "tc3xtf32" else 0) + (1 if tr.collective == "p2p" else 0)),
-            "replay_samples_per_sec": Bg * args.steps / secs_max, "loss": loss,
-            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
-                         "note": "peak = measured sustained dense bf16 (MEASURED_PEAKS.json); fp32-exact modes run at 1/%s of it at best (%s)"
-                                 % ("n/a" if mode_factor is None else int(mode_factor), "FFMA pipe, 74 TF/GPU" if mode_factor is None else "tf32 = 1/2 bf16, x3 split"),
-                         "flop_per_step": Bg * flop_per_sample}}))
-    if world > 1:
-        dist.destroy_process_group()
+    # replicas must stay bit-identical: hash every rank's parameters and compare
+    flat = np.concatenate([np.concatenate([v["w"].ravel(), v["b"].ravel()]) for v in tr.get_params(0).values()])
+    digest = int.from_bytes(hashlib.sha1(flat.tobytes()).digest()[:6], "little")
+    digests = [digest]
+    if ctx.dist is not None:
+        t = torch.tensor([digest], dtype=torch.int64, device=device)
+        allt = [torch.zeros_like(t) for _ in range(ctx.world)]
+        ctx.dist.all_gather(allt, t)
+        digests = [int(x.item()) for x in allt]
+    collective, P = tr.collective, tr.P
+    tr.close()
+    del tr
+    if ctx.rank != 0:
+        return None
+    flop_per_sample = 3 * 2 * (D * H[0] + H[0] * H[1] + H[1] * (1 + A)) + (2 * (D * H[0] + H[0] * H[1] + H[1] * (1 + A)) + 2 * (H[0] * H[1] + H[1] * (1 + A)))
+    tflops = Bg * flop_per_sample / rep_s / 1e12
+    pk, peak_src = measured_peaks()
+    mode_factor = {"fp32": None, "tc3xtf32": 6.0}[args.gemm]      # tf32 = 1/2 of bf16, 3 MMAs per product
+    peak = float(pk["bf16_tflops_sustained"]) * ctx.world
+    launches_per_step = 18 + (1 if args.gemm == "tc3xtf32" else 0) + (1 if collective == "p2p" else 0)
+    return {
+        "metric": "train_steps_per_sec", "value": 1.0 / rep_s, "unit": "steps/s", "n_gpus": ctx.world, "steps": reps,
+        "warmup": max(args.warmup, 3), "ms_per_step": rep_s * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else "f32 via 3xTF32 tensor-core split", "data": "synthetic",
+        "config": {"workload": "configs[3]: large-batch data-parallel DDQN, global batch %d, hidden %dx%d" % (Bg, H[0], H[1]),
+                   "obs_dim": D, "num_actions": A, "batch_local": Bg // ctx.world, "gemm": args.gemm,
+                   "collective": {"p2p": "own kernel over NVLink peer memory (csrc/comm_p2p.cu), %d floats", "nccl": "NCCL all-reduce of %d floats",
+                                  "none": "none (1 GPU), %d floats"}[collective] % (P + 1),
+                   "l2": "activations %.1f GB per rank >> L2; flushed before every step" % (3 * 2 * (Bg // ctx.world) * H[0] * 4 / 1e9)},
+        "clocks": clocks, "gpu_launches": reps * launches_per_step,
+        "timing": {"reps": reps, "steps_per_rep": 1, "statistic": "median step, max over ranks", "timed_region_s": timed_s},
+        "replay_samples_per_sec": Bg / rep_s, "loss": loss,
+        "replicas": {"param_digests": digests, "identical": len(set(digests)) == 1},
+        "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
+                     "peak_source": peak_src,
+                     "frac_of_mode_ceiling": None if mode_factor is None else tflops / (peak / mode_factor),
+                     "note": "peak = measured sustained dense bf16 (MEASURED_PEAKS.json); fp32-exact modes run at 1/%s of it at best (%s)"
+                             % ("n/a" if mode_factor is None else int(mode_factor), "FFMA pipe, 74 TF/GPU" if mode_factor is None else "tf32 = 1/2 bf16, x3 split"),
+                     "flop_per_step": Bg * flop_per_sample}}
 
 
-def run_per(args):
-    """BASELINE configs[4]: prioritized-replay stress -- 16M-leaf sum tree, batch 32768: sample + priority update.
-    No reference counterpart (the reference samples uniformly); one GPU (1.2 GB of ring + 134 MB tree fit)."""
-    import torch
+# ---------------------------------------------------------------------------------------------------
+# configs[4]: prioritized replay stress (no reference counterpart)
+# ---------------------------------------------------------------------------------------------------
+def run_per(args, ctx):
+    """16M-leaf sum tree, batch 32768: sample + priority update.  No reference counterpart (the reference samples
+    uniformly); one GPU (1.2 GB of ring + 134 MB tree fit)."""
     import dqn_b200
-    device = torch.device("cuda:0")
+    torch, device = ctx.torch, ctx.device
     cap, Bp = 16 * 2**20, 32768
-    per = dqn_b200.PrioritizedSampler(cap, seed=1)
+    per = dqn_b200.PrioritizedSampler(cap, seed=1, device=ctx.local)
     g = torch.Generator(device=device); g.manual_seed(0)
     per.fill_device(torch.rand(cap, generator=g, device=device) + 1e-3)
     idx = torch.empty(Bp, dtype=torch.int64, device=device); pr = torch.empty(Bp, dtype=torch.float32, device=device)
     td = torch.randn(Bp, generator=g, device=device)
-    def step(i):
+    for i in range(max(args.warmup, 3)):
         per.sample_device(i, idx, pr)
         per.update_device(idx, td, is_td=True)
-    for i in range(max(args.warmup, 3)):
-        step(i)
     flush_l2(torch, device)
+    torch.cuda.synchronize(device)
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     steps = max(min(args.steps, 2000), 10)
-    with ClockSampler(0) as clk:
+    with ClockSampler(ctx.local) as clk:
         e[0].record()
         for i in range(steps):
             per.sample_device(1000 + i, idx, pr)
@@ -757,67 +870,75 @@ def run_per(args):
         e[2].record()
         torch.cuda.synchronize(device)
     ts, tu = e[0].elapsed_time(e[1]) * 1e-3 / steps, e[1].elapsed_time(e[2]) * 1e-3 / steps
-    peak, peak_src = measured_peaks()
+    pk, peak_src = measured_peaks()
+    peak = float(pk["hbm_gbs"])
     levels = 24
     gbs_s = Bp * levels * 4 / ts / 1e9
     gbs_u = Bp * (levels * 12 + 4) / tu / 1e9
-    print(json.dumps({
+    launches_per_update = getattr(per, "launches_per_update", 1 + levels)
+    return {
         "metric": "per_samples_per_sec", "value": Bp / ts, "unit": "samples/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": (ts + tu) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[4]: prioritized replay stress, 16M-leaf sum tree, batch 32768 (no reference counterpart)",
                    "l2": "tree 134 MB ~ L2 126 MB; 512 MB flush before the timed region"},
-        "clocks": clk.summary(), "gpu_launches": steps * (1 + 1 + levels),
+        "clocks": clk.summary(), "gpu_launches": steps * (1 + launches_per_update),
+        "timing": {"timed_region_s": (ts + tu) * steps},
         "priority_updates_per_sec": Bp / tu, "us_per_sample_launch": ts * 1e6, "us_per_update": tu * 1e6,
         "roofline": {"bound": "hbm", "achieved": gbs_s, "peak": peak, "unit": "GB/s", "frac": gbs_s / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "per_sample_kernel", "note": "24 dependent 4-byte loads per sample: latency-bound pointer chase; update: %.1f GB/s algorithmic" % gbs_u}}))
+                     "kernel": "per_sample_kernel", "note": "24 dependent 4-byte loads per sample: latency-bound pointer chase; update: %.1f GB/s algorithmic" % gbs_u}}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200_000)
-    ap.add_argument("--warmup", type=int, default=2_000)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid (ncu): only the fused timed region, no e2e / extras / cpu baseline; not a bench value")
-    ap.add_argument("--workload", default="single", choices=["single", "population", "dp", "per", "episodes", "replay"])
+    ap.add_argument("--workload", default="default", choices=["default", "single", "population", "dp", "per", "episodes", "replay"],
+                    help="default = the single-agent line with the sharded workloads at the same N embedded in extras")
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--hidden", type=int, default=1024)
-    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tc3xtf32"])
+    ap.add_argument("--gemm", default="tc3xtf32", choices=["fp32", "tc3xtf32"])
     ap.add_argument("--agents", type=int, default=1024)
-    ap.add_argument("--steps-per-launch", type=int, default=16)
+    ap.add_argument("--steps-per-launch", type=int, default=128)
     ap.add_argument("--no-session", action="store_true",
                     help="single workload: e2e through one launch per Agent._step() instead of the resident session kernel")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
                     help="dp workload: gradient all-reduce by the library's own peer-memory kernel (p2p) or by NCCL")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "cta", "cluster"],
                     help="train-step kernel of the single/population workloads: one CTA per agent, or one agent over a 4-CTA cluster "
                          "(auto = cluster while 4 * agents <= SMs)")
     args = ap.parse_args()
+    defaults = {"default": (200_000, 2_000), "single": (200_000, 2_000), "population": (256, 3), "dp": (20, 3), "per": (400, 3),
+                "episodes": (1024, 3), "replay": (40, 3)}[args.workload]
+    if args.steps is None:
+        args.steps = defaults[0]
+    if args.warmup is None:
+        args.warmup = defaults[1]
     os.environ["DQN_B200_STEP_KERNEL"] = args.step_kernel
+    ctx = Ctx()
     if args.impl == "reference":
-        return run_reference(args)
-    _, world, _ = dist_env()
-    if args.gpus != world and world == 1 and args.gpus > 1:
+        line = run_reference(args, ctx)
+        if line is not None:
+            print(json.dumps(line))
+        return
+    if args.gpus != ctx.world and ctx.world == 1 and args.gpus > 1:
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-               "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--workload", args.workload, "--agents", str(args.agents), "--steps-per-launch", str(args.steps_per_launch),
-               "--batch", str(args.batch), "--hidden", str(args.hidden), "--gemm", args.gemm, "--step-kernel", args.step_kernel,
-               "--collective", args.collective] + (["--no-session"] if args.no_session else [])
+               "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.workload == "population":
-        return run_population(args)
-    if args.workload == "dp":
-        return run_dp(args)
-    if args.workload == "per":
-        return run_per(args)
-    if args.workload == "episodes":
-        return run_episodes(args)
-    if args.workload == "replay":
-        return run_replay(args)
-    run_single(args)
+    ctx.init_gpu()
+    try:
+        fn = {"default": lambda a, c: run_single(a, c, True), "single": lambda a, c: run_single(a, c, False),
+              "population": run_population, "dp": run_dp, "per": run_per, "episodes": run_episodes, "replay": run_replay}[args.workload]
+        line = fn(args, ctx)
+        if ctx.rank == 0 and line is not None:
+            print(json.dumps(line))
+    finally:
+        ctx.close()
 
 
 if __name__ == "__main__":

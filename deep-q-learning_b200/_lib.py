@@ -13,6 +13,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dqn_b200.h")
 
 DQN_OPT_ADAM, DQN_OPT_ADAMW = 0, 1
 DQN_PARAMS_ONLINE, DQN_PARAMS_TARGET = 0, 1
+LOSS_KINDS = {"huber": 0, "l2": 1, "mse": 1}     # "huber" = the reference (q_learning_functions.py:36); "l2"/"mse" = 0.5 e^2, an extension
 DQN_STEP_AUTO, DQN_STEP_CTA, DQN_STEP_CLUSTER = 0, 1, 2
 STEP_KERNELS = {"auto": DQN_STEP_AUTO, "cta": DQN_STEP_CTA, "cluster": DQN_STEP_CLUSTER}
 DQN_MAX_BATCH, DQN_MAX_OBS_DIM, DQN_MAX_ACTIONS = 1024, 16, 7
@@ -111,6 +112,8 @@ PROTOTYPES = {
     "dqn_train_step_device_idx": (C.c_int, [_H, _i32, _i32, _i32, _P]),
     "dqn_get_losses": (C.c_int, [_H, _i32, _i32, _P, C.POINTER(_i64)]),
     "dqn_sync_target": (C.c_int, [_H, _i32, _i32]),
+    "dqn_polyak_target": (C.c_int, [_H, _i32, _i32, C.c_float]),
+    "dqn_set_loss_kind": (C.c_int, [_H, _i32, _i32, _i32]),
     "dqn_act": (C.c_int, [_H, _i32, _P, C.POINTER(_i32)]),
     "dqn_act_batch": (C.c_int, [_H, _i32, _i32, _P, _P]),
     # episode-loop control on the device
@@ -138,6 +141,8 @@ PROTOTYPES = {
     "dqn_lb_allreduce": (C.c_int, [_H]),
     "dqn_lb_apply": (C.c_int, [_H]),
     "dqn_lb_sync_target": (C.c_int, [_H]),
+    "dqn_lb_polyak_target": (C.c_int, [_H, C.c_float]),
+    "dqn_lb_set_loss_kind": (C.c_int, [_H, _i32]),
     "dqn_lb_get_loss": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "dqn_lb_debug_read": (C.c_int, [_H, _i32, _P, C.c_uint64]),
     "dqn_lb_synchronize": (C.c_int, [_H]),

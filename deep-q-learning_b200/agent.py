@@ -35,7 +35,7 @@ class Agent:
                  gamma, epsilon, epsilon_decay_rate, min_epsilon, max_episodes, max_steps,
                  training_start, batch_size, train_frequency, back_up_frequency, replace_frequency,
                  reward_to_reach, num_actions, saving_directory, monitoring=False, verbose=1,
-                 *, device=0, seed=0, session=False):
+                 *, device=0, seed=0, session=False, loss="huber", tau=None):
         self._network = network
         self._optimizer = optimizer
         self._env = env
@@ -46,6 +46,11 @@ class Agent:
         self._engine = DqnEngine(obs_dim, num_actions, buffer_size, max(int(batch_size), 1), gamma,
                                  optimizer, n_agents=1, seed=seed, device=device, session=session)
         self._lib, self._h = self._engine.lib, self._engine.h
+        # Extensions the reference does not have, off by default: loss="l2" trains on 0.5 e^2 instead of
+        # Huber(1); tau in (0,1) makes _update_target_model a Polyak step theta^- := tau theta + (1 - tau) theta^-.
+        self._tau = None if tau is None else float(tau)
+        if loss != "huber":
+            self._engine.set_loss(loss)
         self._params = params
         self._opt_state = opt_state
         self._target_params = params                                  # q_agent.py:91
@@ -142,7 +147,10 @@ class Agent:
             return randint(0, self._num_actions)
 
     def _sync_target(self):
-        _lib.check(self._lib.dqn_sync_target(self._h, 0, 1))
+        if self._tau is None:
+            _lib.check(self._lib.dqn_sync_target(self._h, 0, 1))          # q_agent.py:143-144: hard copy
+        else:
+            self._engine.polyak_target(self._tau, 0, 1)
 
     async def _update_target_model(self):
         self._sync_target()

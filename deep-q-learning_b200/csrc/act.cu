@@ -28,6 +28,27 @@ dqn_sync_target_kernel(float* __restrict__ params, int PK, int agent_begin) {
   for (int i = threadIdx.x; i < n4; i += blockDim.x) base[n4 + i] = base[i];
 }
 
+// Polyak / soft target update (not in the reference; optax.incremental_update semantics):
+//   theta^- := tau * theta + (1 - tau) * theta^-   with every product and the sum rounded to fp32 separately (no FMA
+// contraction), so that the NumPy oracle reproduces it bit for bit.  tau = 1 is the hard sync.
+__global__ void __launch_bounds__(256)
+dqn_polyak_target_kernel(float* __restrict__ params, int PK, int agent_begin, float tau) {
+  float4* base = reinterpret_cast<float4*>(params + (size_t)(agent_begin + blockIdx.x) * 4 * PK);
+  const int n4 = PK >> 2;
+  const float omt = __fsub_rn(1.0f, tau);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 w = base[i], t = base[n4 + i];
+    base[n4 + i] = make_float4(__fadd_rn(__fmul_rn(tau, w.x), __fmul_rn(omt, t.x)), __fadd_rn(__fmul_rn(tau, w.y), __fmul_rn(omt, t.y)),
+                               __fadd_rn(__fmul_rn(tau, w.z), __fmul_rn(omt, t.z)), __fadd_rn(__fmul_rn(tau, w.w), __fmul_rn(omt, t.w)));
+  }
+}
+
+cudaError_t launch_polyak_target(cudaStream_t st, float* params, const Dims& d, int agent_begin, int n_sel, float tau) {
+  if (n_sel <= 0) return cudaSuccess;
+  dqn_polyak_target_kernel<<<n_sel, 256, 0, st>>>(params, d.PK, agent_begin, tau);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_act(cudaStream_t st, const float* params, const Dims& d, int agent_begin, int n_sel,
                        const float* states, int* actions_out, float* q_out) {
   if (n_sel <= 0) return cudaSuccess;

@@ -763,6 +763,26 @@ DQN_API int dqn_sync_target(dqn_handle* h, int32_t agent_begin, int32_t agent_en
   return DQN_OK;
 }
 
+DQN_API int dqn_polyak_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end, float tau) {
+  if (int rc = check_range(h, agent_begin, agent_end)) return rc;      // (ends a session: the resident kernel serves the hard sync only)
+  if (!(tau >= 0.f && tau <= 1.f)) return fail(DQN_E_INVALID, "dqn_polyak_target: tau must be in [0,1]");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(launch_polyak_target(h->stream, h->params, h->dims, agent_begin, agent_end - agent_begin, tau));
+  return DQN_OK;
+}
+
+DQN_API int dqn_set_loss_kind(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t kind) {
+  if (int rc = check_range(h, agent_begin, agent_end)) return rc;
+  if (kind != DQN_LOSS_HUBER && kind != DQN_LOSS_L2) return fail(DQN_E_INVALID, "dqn_set_loss_kind: kind must be DQN_LOSS_HUBER or DQN_LOSS_L2");
+  CU(cudaSetDevice(h->cfg.device));
+  for (int a = agent_begin; a < agent_end; ++a) {
+    h->hctl[a].loss_kind = kind;
+    CU(cudaMemcpyAsync(&h->ctl[a].loss_kind, &h->hctl[a].loss_kind, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return DQN_OK;
+}
+
 DQN_API int dqn_act_batch(dqn_handle* h, int32_t agent_begin, int32_t agent_end, const float* states, int32_t* actions_out) {
   if (int rc = check_range(h, agent_begin, agent_end)) return rc;
   if (!states || !actions_out) return fail(DQN_E_INVALID, "dqn_act: NULL argument");

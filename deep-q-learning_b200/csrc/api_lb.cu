@@ -112,6 +112,7 @@ struct dqn_lb_handle {
   bool connected;
   unsigned epoch;
   unsigned long long comm_timeout_ns;
+  int loss_kind;
 };
 
 namespace {
@@ -173,7 +174,7 @@ DQN_API int dqn_lb_create(const dqn_lb_config* cfg, dqn_lb_handle** out) {
   h->taps.targets = (float*)(a + c.targets); h->taps.max_actions = (int*)(a + c.maxa); h->taps.enabled = 0;
   h->stage = a + c.stage;
   h->ring_counter = 0; h->train_steps = 0; h->adam_count = 0; h->pinned = nullptr;
-  h->window = nullptr; h->connected = false; h->epoch = 0;
+  h->window = nullptr; h->connected = false; h->epoch = 0; h->loss_kind = kLossHuber;
   {
     const char* ms = getenv("DQN_B200_COMM_TIMEOUT_MS");
     const double v = ms ? atof(ms) : 20000.0;
@@ -315,7 +316,7 @@ DQN_API int dqn_lb_forward_backward(dqn_lb_handle* h, const int64_t* idx, int32_
   CU(launch_replay_gather(h->stream, h->ring, ring_dims(h), 0, h->ws.idx, 0, 0, 0, size, B, h->ws.s, h->ws.a, h->ws.r, h->ws.s2, h->ws.done));
   h->taps.enabled = debug ? 1 : 0;
   const float inv = 1.0f / ((float)B * (float)h->cfg.world);
-  CU(lb_forward_backward(h->stream, h->dims, h->ws, h->cfg.gamma, inv, h->cfg.gemm_mode, h->taps));
+  CU(lb_forward_backward(h->stream, h->dims, h->ws, h->cfg.gamma, inv, h->cfg.gemm_mode, h->loss_kind, h->taps));
   return DQN_OK;
 }
 
@@ -410,6 +411,21 @@ DQN_API int dqn_lb_sync_target(dqn_lb_handle* h) {
   if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaMemcpyAsync(h->ws.theta_t, h->ws.theta, (size_t)h->dims.P * 4, cudaMemcpyDeviceToDevice, h->stream));
+  return DQN_OK;
+}
+
+DQN_API int dqn_lb_polyak_target(dqn_lb_handle* h, float tau) {
+  if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
+  if (!(tau >= 0.f && tau <= 1.f)) return lbfail(DQN_E_INVALID, "dqn_lb_polyak_target: tau must be in [0,1]");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(lb_polyak(h->stream, h->dims, h->ws, tau));
+  return DQN_OK;
+}
+
+DQN_API int dqn_lb_set_loss_kind(dqn_lb_handle* h, int32_t kind) {
+  if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
+  if (kind != DQN_LOSS_HUBER && kind != DQN_LOSS_L2) return lbfail(DQN_E_INVALID, "dqn_lb_set_loss_kind: kind must be DQN_LOSS_HUBER or DQN_LOSS_L2");
+  h->loss_kind = kind;
   return DQN_OK;
 }
 

@@ -23,12 +23,13 @@ constexpr int kH2 = 64;        // LunarLander/dddqn.py:20
 constexpr int kMaxD = 16;
 constexpr int kMaxA = 7;
 constexpr int kLossCap = 4096; // per-agent ring of recent losses
+enum { kLossHuber = 0, kLossL2 = 1 };
 
 struct AgentCtl {
   float gamma, lr, b1, b2, eps, eps_root, wd;
   int batch_size;
+  int loss_kind;           // kLossHuber (the reference, q_learning_functions.py:36) or kLossL2 (0.5 e^2, optax.l2_loss)
   int adam_count;          // optax ScaleByAdamState.count (int32, saturating)
-  int pad0;
   long long ring_counter;  // ReplayBuffer._counter (total adds)
   long long train_steps;   // number of _step() calls so far == Philox step counter
   double pb1, pb2;         // b1**adam_count, b2**adam_count carried in double (one DMUL per step instead of a pow() per

@@ -86,6 +86,7 @@ cudaError_t launch_act(cudaStream_t st, const float* params, const Dims& d, int 
                        const float* states /* device [n_sel][D] */, int* actions_out /* device [n_sel] */,
                        float* q_out /* device [n_sel][A] or nullptr */);
 cudaError_t launch_sync_target(cudaStream_t st, float* params, const Dims& d, int agent_begin, int n_sel);
+cudaError_t launch_polyak_target(cudaStream_t st, float* params, const Dims& d, int agent_begin, int n_sel, float tau);
 
 // episode-loop control on the device (episode.cu)
 cudaError_t launch_policy(cudaStream_t st, const float* params, const Dims& d, EpisodeCtl* ep, int agent_begin, int n_sel,

@@ -58,7 +58,8 @@ cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const flo
 cudaError_t lb_gemm(cudaStream_t st, int gemm_mode, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                     float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws);
 cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float gamma, float inv_global_batch,
-                                int gemm_mode, const LbTaps& taps);
+                                int gemm_mode, int loss_kind, const LbTaps& taps);
+cudaError_t lb_polyak(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float tau);
 // comm_error: nullptr, or the window's CommFlags.error -- a non-zero value turns the update into a no-op
 cudaError_t lb_adam(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float b1, float b2, float c1, float c2,
                     float eps, float eps_root, float lr, float wd, const unsigned* comm_error);

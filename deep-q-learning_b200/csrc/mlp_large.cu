@@ -289,7 +289,7 @@ lb_head_kernel(const float* __restrict__ H2, const float* __restrict__ theta, co
 __global__ void __launch_bounds__(256)
 lb_targets_kernel(const float* __restrict__ Q, const long long* __restrict__ act, const float* __restrict__ rew,
                   const uint8_t* __restrict__ done, float* __restrict__ dhd, float* __restrict__ partial,
-                  int B, int A, float gamma, float inv_global_batch, LbTaps taps) {
+                  int B, int A, float gamma, float inv_global_batch, int loss_kind, LbTaps taps) {
   __shared__ float red[8][2 + kMaxA];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -315,8 +315,9 @@ lb_targets_kernel(const float* __restrict__ Q, const long long* __restrict__ act
     const float tgt = qa + tv;
     const float e = qa - tgt;
     const float ae = fabsf(e), quad = fminf(ae, 1.0f);
-    vals[0] = (0.5f * quad * quad + (ae - quad)) * inv_global_batch;
-    const float gi = fminf(fmaxf(e, -1.0f), 1.0f) * inv_global_batch;
+    const bool l2loss = loss_kind == kLossL2;
+    vals[0] = (l2loss ? 0.5f * e * e : 0.5f * quad * quad + (ae - quad)) * inv_global_batch;
+    const float gi = (l2loss ? e : fminf(fmaxf(e, -1.0f), 1.0f)) * inv_global_batch;
     dhd[(size_t)i * 8 + 0] = gi;
     vals[1] = gi;
 #pragma unroll
@@ -485,7 +486,7 @@ lb_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int r
 
 // One forward/backward pass over the local batch already gathered into ws.s/a/r/s2/done.
 cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float gamma, float inv_global_batch,
-                                int gemm_mode, const LbTaps& taps) {
+                                int gemm_mode, int loss_kind, const LbTaps& taps) {
   const int B = d.B, H1n = d.H1, H2n = d.H2, D = d.D, A = d.A;
   const int offb1 = D * H1n, offW2 = offb1 + H1n, offb2 = offW2 + H1n * H2n, offWv = offb2 + H2n;
   const int offbv = offWv + H2n, offba = offbv + 1 + H2n * A;
@@ -507,7 +508,7 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
   lb_head_kernel<<<(3 * B / kHeadRows + 7) / 8, 256, 0, st>>>(ws.H2, ws.theta, ws.theta_t, ws.Q, B, H2n, A, offWv);
   LBCHK(cudaGetLastError());
   const int nblk = (B + 255) / 256;
-  lb_targets_kernel<<<nblk, 256, 0, st>>>(ws.Q, ws.a, ws.r, ws.done, ws.dhd, ws.partial, B, A, gamma, inv_global_batch, taps);
+  lb_targets_kernel<<<nblk, 256, 0, st>>>(ws.Q, ws.a, ws.r, ws.done, ws.dhd, ws.partial, B, A, gamma, inv_global_batch, loss_kind, taps);
   LBCHK(cudaGetLastError());
   lb_finish_kernel<<<1, 32, 0, st>>>(ws.partial, nblk, ws.grads, d.P, A, offbv);
   lb_finish_ba_kernel<<<1, 32, 0, st>>>(ws.partial, nblk, ws.grads, A, offba);
@@ -548,6 +549,17 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     LBCHK(launch_reduce_partials(st, ws.colpart, ws.grads, n, nchunk, n));
   }
   return cudaSuccess;
+}
+
+// theta^- := tau theta + (1 - tau) theta^-, products and sum rounded separately (see dqn_polyak_target_kernel, act.cu)
+__global__ void __launch_bounds__(256) lb_polyak_kernel(const float* __restrict__ theta, float* __restrict__ theta_t, int P, float tau) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  theta_t[p] = __fadd_rn(__fmul_rn(tau, theta[p]), __fmul_rn(__fsub_rn(1.0f, tau), theta_t[p]));
+}
+cudaError_t lb_polyak(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float tau) {
+  lb_polyak_kernel<<<(d.P + 255) / 256, 256, 0, st>>>(ws.theta, ws.theta_t, d.P, tau);
+  return cudaGetLastError();
 }
 
 cudaError_t lb_adam(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float b1, float b2, float c1, float c2,

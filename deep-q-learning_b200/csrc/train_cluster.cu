@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   const float gamma = ctl->gamma, lr = ctl->lr, b1 = ctl->b1, b2 = ctl->b2;
   const float eps = ctl->eps, eps_root = ctl->eps_root, wd = ctl->wd;
   const int B = ctl->batch_size;
+  const bool l2loss = ctl->loss_kind == kLossL2;
   const long long step0 = ctl->train_steps;
   const int count0 = ctl->adam_count;
   // ReplayBuffer.add x ist.n (replay_buffer.py:58-65) for transitions that arrived in the parameter buffer.  Every
@@ -472,8 +473,8 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         const float ae = fabsf(e), quad = fminf(ae, 1.0f);
         const int grow = tile * BT + rank * R + i;
         const bool valid = grow < B;
-        const float l = valid ? 0.5f * quad * quad + (ae - quad) : 0.f;
-        const float gi = valid ? fminf(fmaxf(e, -1.0f), 1.0f) / fB : 0.f;
+        const float l = valid ? (l2loss ? 0.5f * e * e : 0.5f * quad * quad + (ae - quad)) : 0.f;
+        const float gi = valid ? (l2loss ? e : fminf(fmaxf(e, -1.0f), 1.0f)) / fB : 0.f;
         DhdT[0 * RS + i] = gi;
         float dsum[1 + A];
         dsum[0] = gi;

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   const float gamma = ctl->gamma, lr = ctl->lr, b1 = ctl->b1, b2 = ctl->b2;
   const float eps = ctl->eps, eps_root = ctl->eps_root, wd = ctl->wd;
   const int B = ctl->batch_size;
+  const bool l2loss = ctl->loss_kind == kLossL2;
   const long long step0 = ctl->train_steps;
   const int count0 = ctl->adam_count;
   const long long rc = ctl->ring_counter;
@@ -337,8 +338,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
           const float ae = fabsf(e);
           const float quad = fminf(ae, 1.0f);
           const bool valid = tile * BT + i < B;
-          const float l = valid ? 0.5f * quad * quad + (ae - quad) : 0.f;
-          const float gi = valid ? fminf(fmaxf(e, -1.0f), 1.0f) / fB : 0.f;     // d mean_i sum_j huber / d pred[i,a]
+          // (l2 loss: 0.5 e^2 = the Huber expression without the clip at delta; not in the reference)
+          const float l = valid ? (l2loss ? 0.5f * e * e : 0.5f * quad * quad + (ae - quad)) : 0.f;
+          const float gi = valid ? (l2loss ? e : fminf(fmaxf(e, -1.0f), 1.0f)) / fB : 0.f;     // d mean_i sum_j loss / d pred[i,a]
           // ---- backward through the dueling head: dV = sum_j dQ_j, dAdv = dQ - dV/A ----
           const float dval = gi;
           DhdT[0 * RS1 + i] = dval;

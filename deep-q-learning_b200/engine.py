@@ -235,6 +235,16 @@ class DqnEngine:
         agent_end = self.n_agents if agent_end is None else agent_end
         _lib.check(self.lib.dqn_sync_target(self.h, agent_begin, agent_end))
 
+    def polyak_target(self, tau, agent_begin=0, agent_end=None):
+        """Soft target update theta^- := tau theta + (1 - tau) theta^- (extension; the reference hard-copies)."""
+        agent_end = self.n_agents if agent_end is None else agent_end
+        _lib.check(self.lib.dqn_polyak_target(self.h, agent_begin, agent_end, float(tau)))
+
+    def set_loss(self, kind, agent_begin=0, agent_end=None):
+        """``"huber"`` (the reference's loss, default) or ``"l2"`` / ``"mse"`` (0.5 e^2, extension)."""
+        agent_end = self.n_agents if agent_end is None else agent_end
+        _lib.check(self.lib.dqn_set_loss_kind(self.h, agent_begin, agent_end, _lib.LOSS_KINDS[kind]))
+
     # -- episode-loop control on the device (torch CUDA tensors in, torch CUDA tensors out; enqueue only) ----------
     def configure_episodes(self, configs, agent_begin=0, reset_counters=True):
         """``configs``: one dict per agent with the reference's kwarg names (epsilon, epsilon_decay_rate, min_epsilon,

@@ -167,6 +167,12 @@ class LargeBatchTrainer:
     def sync_target(self):
         _lib.check(self.lib.dqn_lb_sync_target(self.h))
 
+    def polyak_target(self, tau):
+        _lib.check(self.lib.dqn_lb_polyak_target(self.h, float(tau)))
+
+    def set_loss(self, kind):
+        _lib.check(self.lib.dqn_lb_set_loss_kind(self.h, _lib.LOSS_KINDS[kind]))
+
     def loss(self):
         out = C.c_float(0)
         _lib.check(self.lib.dqn_lb_get_loss(self.h, C.byref(out)))

@@ -28,6 +28,9 @@ class PrioritizedSampler:
         lb = C.c_int64(0)
         _lib.check(self.lib.dqn_per_leaf_base(self.h, C.byref(lb)))
         self.leaf_base = int(lb.value)
+        levels = self.leaf_base.bit_length() - 1
+        # kernels per priority update (csrc/per.cu): leaves, warp-per-update bottom 8 levels, full recompute of the top
+        self.launches_per_update = 1 + levels if levels < 8 or levels > 28 else (3 if levels > 8 else 2)
 
     def close(self):
         if getattr(self, "h", None):

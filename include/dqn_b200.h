@@ -49,6 +49,10 @@ enum {
 
 enum { DQN_OPT_ADAM = 0, DQN_OPT_ADAMW = 1 };
 enum { DQN_PARAMS_ONLINE = 0, DQN_PARAMS_TARGET = 1 };
+/* Loss of the train step.  HUBER (delta = 1, summed over actions, mean over the batch) is the reference's
+ * (q_learning_functions.py:36) and the default; L2 = optax.l2_loss = 0.5 e^2 in its place is an extension the reference
+ * does not have: same reduction, gradient e / B instead of clip(e, -1, 1) / B. */
+enum { DQN_LOSS_HUBER = 0, DQN_LOSS_L2 = 1 };
 /* Train-step kernel: one CTA per agent (throughput form, used for populations), or one agent spread over a
  * 4-CTA thread-block cluster (latency form, used for a single agent).  AUTO = cluster while 4*agents <= SMs.
  * Both compute the same update; summation orders differ (results agree to fp32 round-off). */
@@ -200,6 +204,12 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
 
 /* Agent._update_target_model (q_agent.py:143-144): theta^- := theta for agents in the range. */
 DQN_API int dqn_sync_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end);
+/* Soft (Polyak) target update, an extension: the reference only has the hard copy above (q_agent.py:143-144).
+ * theta^- := tau * theta + (1 - tau) * theta^- (optax.incremental_update: two fp32 products and one fp32 sum per
+ * element, no fused multiply-add).  tau in [0,1]; tau = 1 reproduces dqn_sync_target bit for bit. */
+DQN_API int dqn_polyak_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end, float tau);
+/* Select the loss (DQN_LOSS_*) of the agents in the range; takes effect with the next train step. */
+DQN_API int dqn_set_loss_kind(dqn_handle* h, int32_t agent_begin, int32_t agent_end, int32_t kind);
 
 /* compute_action (q_learning_functions.py:67-73) as used by Agent._policy (q_agent.py:139):
  * greedy argmax_a Q(theta, state) for ONE state f32[D] (host pointer).  Synchronises. */
@@ -297,6 +307,9 @@ DQN_API int dqn_lb_allreduce(dqn_lb_handle* h);
 /* optimizer.update + apply_updates (q_learning_functions.py:24-25) with whatever is in the gradient buffer. */
 DQN_API int dqn_lb_apply(dqn_lb_handle* h);
 DQN_API int dqn_lb_sync_target(dqn_lb_handle* h);
+/* Extensions, as for the small-batch handle: soft target update and the L2 loss. */
+DQN_API int dqn_lb_polyak_target(dqn_lb_handle* h, float tau);
+DQN_API int dqn_lb_set_loss_kind(dqn_lb_handle* h, int32_t kind);
 DQN_API int dqn_lb_get_loss(dqn_lb_handle* h, float* loss_out);
 /* parity taps after dqn_lb_forward_backward(debug = 1): `what` = DQN_LB_READ_*; Q is [3*B][A] (q | next_q | next_q_tm). */
 DQN_API int dqn_lb_debug_read(dqn_lb_handle* h, int32_t what, void* host_out, uint64_t nbytes);

@@ -15,7 +15,7 @@ from .replay_oracle import OracleReplay, gather
 
 class OracleAgent:
     def __init__(self, params, opt_state, opt, buffer_size, obs_dim, gamma, batch_size,
-                 seed=0, agent_id=0):
+                 seed=0, agent_id=0, loss="huber"):
         self.params = O.tree_copy(params)
         self.target_params = O.tree_copy(params)            # q_agent.py:91
         self.opt_state = {"count": np.int32(opt_state["count"]),
@@ -27,6 +27,7 @@ class OracleAgent:
         self.seed, self.agent_id = seed, agent_id
         self.train_steps = 0
         self.last = None
+        self.loss = loss                                            # "huber" = the reference; "l2" = extension (dqn_oracle.l2_loss)
 
     def add(self, state, action, reward, observation, done):        # q_agent.py:182
         self.replay.add(state, action, reward, observation, done)
@@ -34,8 +35,8 @@ class OracleAgent:
     def policy_greedy(self, state):                                 # q_agent.py:139
         return O.compute_action(self.params, state)
 
-    def update_target_model(self):                                  # q_agent.py:143-144
-        self.target_params = O.tree_copy(self.params)
+    def update_target_model(self, tau=None):                        # q_agent.py:143-144 (tau: Polyak extension, dqn_oracle.polyak)
+        self.target_params = O.tree_copy(self.params) if tau is None else O.polyak(self.target_params, self.params, tau)
 
     def step(self, indices=None):                                   # q_agent.py:146-169
         if indices is None:
@@ -44,7 +45,7 @@ class OracleAgent:
         batch = gather(indices, *self.replay.arrays())
         self.params, self.opt_state, parts = O.train_step(
             self.params, self.target_params, self.opt_state, batch, self.gamma, self.opt,
-            return_parts=True)
+            return_parts=True, loss=self.loss)
         parts["indices"] = np.asarray(indices, dtype=np.int64)
         self.last = parts
         self.train_steps += 1

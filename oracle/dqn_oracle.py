@@ -141,22 +141,31 @@ def huber(pred, tgt, delta=1.0):
     return (F32(0.5) * quad * quad + F32(delta) * (ae - quad)).astype(F32), e
 
 
-def compute_loss(params, states, q_targets):
+def l2_loss(pred, tgt):
+    """``optax.l2_loss``: ``0.5 (pred - tgt)^2``.  NOT in the reference -- the self-specified "MSE" extension
+    behind ``loss="l2"``; parity unpinned."""
+    e = (pred - tgt).astype(F32)
+    return (F32(0.5) * e * e).astype(F32), e
+
+
+def compute_loss(params, states, q_targets, loss="huber"):
     pred = forward(params, states)                   # :35
-    l, _ = huber(pred, q_targets)
+    l, _ = huber(pred, q_targets) if loss == "huber" else l2_loss(pred, q_targets)
     return F32(np.mean(np.sum(l, axis=1, dtype=F32), axis=0, dtype=F32))   # :36
 
 
 # ------------------------------------------------------------------------------------------------
 # A.4 backward  (jax.grad(compute_loss), q_learning_functions.py:23)  -- hand-derived
 # ------------------------------------------------------------------------------------------------
-def loss_and_grads(params, states, q_targets):
+def loss_and_grads(params, states, q_targets, loss="huber"):
     """Loss and d(loss)/d(params) with the targets held constant (they are inputs)."""
     pred, (x, h1, h2) = forward(params, states, return_cache=True)
     b, a = pred.shape
-    l, e = huber(pred, q_targets)
-    loss = F32(np.mean(np.sum(l, axis=1, dtype=F32), axis=0, dtype=F32))
-    dq = (np.clip(e, F32(-1), F32(1)) / F32(b)).astype(F32)           # d huber = clip(e,-1,1); mean over B
+    l, e = huber(pred, q_targets) if loss == "huber" else l2_loss(pred, q_targets)
+    loss_value = F32(np.mean(np.sum(l, axis=1, dtype=F32), axis=0, dtype=F32))
+    de = np.clip(e, F32(-1), F32(1)) if loss == "huber" else e        # d huber = clip(e,-1,1); d l2 = e
+    dq = (de / F32(b)).astype(F32)                                    # mean over B
+    loss = loss_value
     dval = np.sum(dq, axis=1, keepdims=True, dtype=F32)               # Q = V + A - mean(A)
     dadv = (dq - dval / F32(a)).astype(F32)
     l1, l2, lv, la = (params[m] for m in MODULES)
@@ -229,11 +238,18 @@ def adam_update(params, grads, opt_state, opt):
 # ------------------------------------------------------------------------------------------------
 # Agent._step body  (General/QLearning/q_agent.py:154-169), given an already sampled batch
 # ------------------------------------------------------------------------------------------------
-def train_step(params, target_params, opt_state, batch, gamma, opt, return_parts=False):
+def polyak(target_params, params, tau):
+    """``optax.incremental_update(params, target_params, tau)``: ``tau * new + (1 - tau) * old`` leaf by leaf in fp32 (two
+    rounded products, one rounded sum).  NOT in the reference (hard copy only) -- self-specified extension."""
+    t = F32(tau)
+    return tree_map(lambda new, old: (t * new + (F32(1.0) - t) * old).astype(F32), params, target_params)
+
+
+def train_step(params, target_params, opt_state, batch, gamma, opt, return_parts=False, loss="huber"):
     s, a, r, s2, d = preprocessing(*batch)                                   # q_agent.py:154-158
     targets, parts = compute_q_targets(params, target_params, s, a, r, s2, d, gamma,
                                        return_parts=True)                   # :159-165
-    loss, grads = loss_and_grads(params, s, targets)                         # :166 (grad)
+    loss, grads = loss_and_grads(params, s, targets, loss)                   # :166 (grad)
     new_params, new_opt_state = adam_update(params, grads, opt_state, opt)   # :166 (update/apply)
     if return_parts:
         parts.update(targets=targets, loss=loss, grads=grads)

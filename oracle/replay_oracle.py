@@ -54,6 +54,38 @@ def sample_batch(rng, num_samples, states, actions, rewards, observations, dones
     return gather(idx, states, actions, rewards, observations, dones)
 
 
+def numba_sample_batch():
+    """The reference's sampler on the reference's engine: a numba-njit function drawing with numba's own
+    ``numpy.random.randint`` (its private MT19937) and gathering the five arrays by fancy index
+    (``replay_buffer.py:68-85``).  Used by ``bench.py``'s CPU baseline on boxes where ``/root/reference`` does not
+    exist, so that the baseline's replay half costs what the reference's costs (the NumPy/Philox ``sample_indices`` is ~6x
+    slower and is only there for index parity with the kernels).  Compiled on first call; returns the jitted function."""
+    import numba
+
+    @numba.njit
+    def sample(num_samples, states, actions, rewards, observations, dones, batch_size):
+        idx = np.random.randint(0, num_samples, batch_size)
+        return states[idx], actions[idx], rewards[idx], observations[idx], dones[idx]
+
+    return sample
+
+
+def reference_replay_module(path="/root/reference/General/Base/replay_buffer.py"):
+    """The reference's own ``replay_buffer`` module (real ``ReplayBuffer.add`` + numba ``sample_batch``), imported
+    unmodified from where it lies -- only possible in the build container; ``None`` elsewhere."""
+    import importlib.util
+    import os
+    if not os.path.exists(path):
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_replay_buffer", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception:
+        return None
+
+
 def synthetic_transitions(rng, n, obs_dim, num_actions=4, done_p=0.01):
     """Synthetic transitions of SURVEY section 8(d): s,s'~N(0,1); a~U{0..A-1}; r~2N(0,1); done~Bern(p)."""
     s = rng.standard_normal((n, obs_dim), dtype=np.float32)

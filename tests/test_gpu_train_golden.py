@@ -15,6 +15,11 @@ from oracle import dqn_oracle as O
 pytestmark = pytest.mark.gpu
 CASES = ["lunar_lander", "sweep", "gamma0_terminal", "d8_b70"]
 
+# nu = b2 nu + (1 - b2) g^2 is QUADRATIC in the gradient: a gradient entry that meets the 1e-5 relative bar has its square
+# within 2e-5 (first order), so nu's bar is twice the gradient's ("tolerances"); the Adam arithmetic
+# itself is checked to 1e-6 against the kernel's own gradient in tests/test_gpu_train_step.py::test_adam_update_from_own_gradient
+NU_RTOL = 2e-5
+
 
 @pytest.fixture(autouse=True, params=["cta", "cluster"])
 def step_kernel(request, monkeypatch):
@@ -42,7 +47,7 @@ def test_kernel_reproduces_the_reference_sources(case):
         flat = lambda tree: np.concatenate([np.ravel(tree[m][k]) for m in O.MODULES for k in ("w", "b")])
         assert int(cnt) == int(g[f"count{t}"])
         assert_close(flat(mu), g[f"mu{t}"], what=f"{case} step {t} mu")
-        assert_close(flat(nu), g[f"nu{t}"], rtol=3e-5, what=f"{case} step {t} nu")       # quadratic in the gradient
+        assert_close(flat(nu), g[f"nu{t}"], rtol=NU_RTOL, what=f"{case} step {t} nu")
         if t in set(g["sync_at"].tolist()):
             eng.sync_target()
             assert np.array_equal(eng.get_params_flat(0, 1), eng.get_params_flat(0, 0))

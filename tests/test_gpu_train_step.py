@@ -337,3 +337,122 @@ def test_resume_state_continues_bitwise(tmp_path, golden):
     for x, y in zip(e1.buffer_export(), e2.buffer_export()):
         assert np.array_equal(x, y)
     assert np.array_equal(e1.losses(50), e2.losses(50))
+
+
+def test_adam_update_from_own_gradient():
+    """The optimiser arithmetic in isolation: mu', nu', theta' recomputed on the host (oracle adam_update, fp32) FROM THE
+    KERNEL'S OWN gradient must match the kernel's state to 1e-6 -- nu is quadratic in the gradient, so against the
+    oracle's gradient it can only be held to twice the gradient bar (NU_RTOL in the golden tests)."""
+    eng, ora, rng = make_pair(D=8, A=4, B=64, kind="adamw", lr=1e-3, seed=41)
+    for step in range(3):
+        p0 = eng.get_params(0, 0)
+        cnt, mu0, nu0 = eng.get_opt_state(0)
+        got = eng.train_step_debug()
+        want_p, want_s = O.adam_update(p0, got["grads"], {"count": cnt, "mu": mu0, "nu": nu0}, O.OptSpec("adamw", 1e-3))
+        p1 = eng.get_params(0, 0)
+        cnt1, mu1, nu1 = eng.get_opt_state(0)
+        assert int(cnt1) == int(want_s["count"]) == step + 1
+        for m in O.MODULES:
+            for k in ("w", "b"):
+                assert_close(mu1[m][k], want_s["mu"][m][k], rtol=1e-6, atol_scale=1e-7, what=f"mu {m}/{k}")
+                assert_close(nu1[m][k], want_s["nu"][m][k], rtol=1e-6, atol_scale=1e-7, what=f"nu {m}/{k}")
+                assert_close(p1[m][k], want_p[m][k], rtol=1e-6, atol_scale=1e-7, what=f"theta {m}/{k}")
+
+
+def test_denormal_second_moment():
+    """Adam with a DENORMAL nu (the quotient uses sqrt.approx.ftz / rcp.approx.ftz, which flush denormal inputs): a dead
+    hidden unit has an exactly-zero gradient, its nu decays through the denormal range.  sqrt(denormal) < 1.1e-19 is far
+    below eps = 1e-8, so flushing it changes the update by < 1e-11 relative: the kernel must agree with the oracle."""
+    eng, ora, rng = make_pair(D=8, A=4, B=64, kind="adam", lr=1e-3, seed=43)
+    p = eng.get_params(0, 0)
+    p[O.MODULES[0]]["b"][0] = -50.0                      # unit 0 of layer 1 never fires: dW2[0, :] == 0 exactly
+    eng.set_params(p, 0, 0); ora.params = O.tree_copy(p)
+    cnt, mu, nu = eng.get_opt_state(0)
+    mu[O.MODULES[1]]["w"][0, :] = np.float32(1e-12)
+    nu[O.MODULES[1]]["w"][0, :32] = np.float32(1e-42)    # denormal
+    nu[O.MODULES[1]]["w"][0, 32:] = np.float32(2e-38)    # normal now, denormal after a few decays... of 0.999 (stays normal): both paths
+    eng.set_opt_state(0, mu, nu, 0)
+    ora.opt_state = {"count": np.int32(0), "mu": O.tree_copy(mu), "nu": O.tree_copy(nu)}
+    for step in range(3):
+        ref = ora.step()
+        got = eng.train_step_debug()
+        assert not got["grads"][O.MODULES[1]]["w"][0].any() and not ref["grads"][O.MODULES[1]]["w"][0].any()
+        p1 = eng.get_params(0, 0)
+        _, mu1, nu1 = eng.get_opt_state(0)
+        w_got, w_ref = p1[O.MODULES[1]]["w"][0], ora.params[O.MODULES[1]]["w"][0]
+        np.testing.assert_allclose(w_got, w_ref, rtol=1e-6, atol=0)                       # update = lr * m_hat / (~0 + eps)
+        assert np.all(np.abs(w_got - p[O.MODULES[1]]["w"][0]) > 1e-8)                     # and it is a real, finite move
+        nu_got, nu_ref = nu1[O.MODULES[1]]["w"][0], ora.opt_state["nu"][O.MODULES[1]]["w"][0]
+        ulp = np.abs(nu_got.view(np.int32).astype(np.int64) - nu_ref.view(np.int32).astype(np.int64))
+        assert ulp.max() <= 1 and (nu_got[:32] > 0).all() and (nu_got[:32] < 1.2e-38).all()   # still denormal, not flushed
+        p = p1
+
+
+@pytest.mark.parametrize("loss", ["l2", "mse"])
+def test_l2_loss_extension(loss):
+    """loss="l2" (0.5 e^2; the reference only has Huber): self-specified, oracle = dqn_oracle.l2_loss."""
+    eng, ora, rng = make_pair(D=8, A=4, B=70, kind="adam", lr=1e-3, seed=47)
+    eng.set_loss(loss)
+    ora.loss = "l2"
+    for step in range(3):
+        compare_step(eng, ora, what=f"l2 step{step}")
+    eng.set_loss("huber")
+    ora.loss = "huber"
+    compare_step(eng, ora, what="back to huber")
+
+
+def test_polyak_target_extension():
+    """dqn_polyak_target (the reference only hard-copies): bit-exact against the oracle's
+    tau * theta + (1 - tau) * theta^- in fp32; tau = 1 equals the hard sync."""
+    eng, ora, rng = make_pair(D=9, A=4, B=64, seed=53)
+    for step in range(4):
+        compare_step(eng, ora, what=f"polyak step{step}")
+        eng.polyak_target(0.005)
+        ora.update_target_model(tau=0.005)
+        t = eng.get_params(0, 1)
+        for m in O.MODULES:
+            for k in ("w", "b"):
+                assert np.array_equal(t[m][k], ora.target_params[m][k]), f"{m}/{k}"
+    eng.polyak_target(1.0)
+    t, o = eng.get_params(0, 1), eng.get_params(0, 0)
+    for m in O.MODULES:
+        assert np.array_equal(t[m]["w"], o[m]["w"]) and np.array_equal(t[m]["b"], o[m]["b"])
+    with pytest.raises(dqn_b200.DqnError):
+        eng.polyak_target(1.5)
+
+
+def test_agent_tau_and_loss_kwargs(golden):
+    """Agent(..., tau=, loss=): _update_target_model becomes a Polyak step; session mode serves the rest."""
+    import asyncio
+    theta0 = golden_tree(golden["ref_checkpoint"], "params")
+    opt = dqn_b200.adamw(2e-4)
+    agent = dqn_b200.Agent(network=dqn_b200.Model(4), params=theta0, optimizer=opt, opt_state=opt.init(theta0), env=None,
+                           buffer_size=500, obs_shape=(500, 9), ac_shape=(500,), gamma=0.99, epsilon=1.0, epsilon_decay_rate=0.99,
+                           min_epsilon=0.15, max_episodes=1, max_steps=10, training_start=64, batch_size=64, train_frequency=4,
+                           back_up_frequency=50, replace_frequency=20, reward_to_reach=230.0, num_actions=4,
+                           saving_directory="/tmp/dqn_b200_tau", seed=3, tau=0.01, loss="l2")
+    ora = OracleAgent(theta0, O.init_opt_state(theta0), O.OptSpec("adamw", 2e-4), 500, 9, 0.99, 64, seed=3, loss="l2")
+    data = synthetic_transitions(np.random.default_rng(1), 300, 9, 4, done_p=0.2)
+    agent._replay_buffer.add_many(*data)
+    ora.replay.add_many(*data)
+    for _ in range(3):
+        agent._step()
+        ora.step()
+        asyncio.run(agent._update_target_model())
+        ora.update_target_model(tau=0.01)
+    t = agent._target_params
+    for m in O.MODULES:
+        assert_close(t[m]["w"], ora.target_params[m]["w"], what=f"target {m}")
+    assert not np.array_equal(t[O.MODULES[1]]["w"], agent._params[O.MODULES[1]]["w"])
+
+
+def test_add_accepts_strided_observation():
+    """ReplayBuffer.add with a non-contiguous observation: the optional C staging helper refuses the buffer, the numpy path
+    takes over -- identical ring contents either way."""
+    rb = dqn_b200.ReplayBuffer(16, (16, 9), (16,))
+    base = np.arange(36, dtype=np.float32)
+    rb.add(base[::4], 2, 0.5, base[1::4], True)
+    rb.add(base[:9].astype(np.float64), np.int64(1), np.float32(-1.0), base[9:18], False)
+    s, a, r, s2, d = (np.asarray(x) for x in (rb.states, rb.actions, rb.rewards, rb.observations, rb.dones))
+    assert np.array_equal(s[0], base[::4]) and np.array_equal(s2[0], base[1::4]) and a[0] == 2 and r[0] == 0.5 and d[0]
+    assert np.array_equal(s[1], base[:9]) and a[1] == 1 and r[1] == -1.0 and not d[1] and rb.size == 2

@@ -24,7 +24,7 @@ def to_torch(tree, requires_grad=False):
                 for k, v in tree[m].items()} for m in O.MODULES}
 
 
-def torch_step(params, target_params, batch, gamma):
+def torch_step(params, target_params, batch, gamma, loss_kind="huber"):
     """loss and grads of the reference's _step, by autograd (float64)."""
     s, a, r, s2, d = batch
     tp, tt = to_torch(params, True), to_torch(target_params)
@@ -40,7 +40,10 @@ def torch_step(params, target_params, batch, gamma):
         tv = r_t + (1.0 - d_t) * (gamma * nqt[rows, astar] - q[rows, a_t])
         targets = q + tv[:, None] * torch.nn.functional.one_hot(a_t, q.shape[1]).to(torch.float64)
     pred = torch_forward(tp, s_t)
-    loss = torch.nn.functional.huber_loss(pred, targets, reduction="none", delta=1.0).sum(dim=1).mean()
+    if loss_kind == "huber":
+        loss = torch.nn.functional.huber_loss(pred, targets, reduction="none", delta=1.0).sum(dim=1).mean()
+    else:                                                   # optax.l2_loss: 0.5 e^2
+        loss = (0.5 * (pred - targets) ** 2).sum(dim=1).mean()
     loss.backward()
     return loss.item(), tp, targets.numpy(), astar.numpy()
 
@@ -65,6 +68,36 @@ def test_loss_and_grads_match_autograd(D, B, seed):
     e = np.abs(targets - parts["q"]).max(axis=1)
     if B >= 38:
         assert (e > 1).any() and (e < 1).any()
+
+
+def test_l2_loss_extension_matches_autograd():
+    """loss="l2" (0.5 e^2 in place of Huber; not in the reference): oracle vs torch autograd."""
+    rng = np.random.default_rng(7)
+    D, A, B = 8, 4, 64
+    params = O.init_params(rng, D, A, bias_std=0.05)
+    target = O.tree_map(lambda x: (x + 0.02 * rng.standard_normal(x.shape)).astype(np.float32), params)
+    batch = synthetic_transitions(rng, B, D, A, done_p=0.2)
+    targets = O.compute_q_targets(params, target, *O.preprocessing(*batch), 0.99)
+    loss, grads = O.loss_and_grads(params, batch[0], targets, loss="l2")
+    tloss, tp, _, _ = torch_step(params, target, batch, 0.99, loss_kind="l2")
+    assert abs(float(loss) - tloss) <= 1e-5 * abs(tloss)
+    assert float(loss) > float(O.loss_and_grads(params, batch[0], targets)[0])      # |TD| > 1 rows: quadratic > Huber
+    for m in O.MODULES:
+        for k in ("w", "b"):
+            assert_close(grads[m][k], tp[m][k].grad.numpy().reshape(grads[m][k].shape), what=f"l2 grad {m}/{k}")
+
+
+def test_polyak_extension():
+    """theta^- := tau theta + (1 - tau) theta^- (optax.incremental_update); tau = 1 is the hard copy, tau = 0 a no-op."""
+    rng = np.random.default_rng(8)
+    p = O.init_params(rng, 9, 4, bias_std=0.05)
+    t = O.tree_map(lambda x: (x + 0.1 * rng.standard_normal(x.shape)).astype(np.float32), p)
+    for m in O.MODULES:
+        assert np.array_equal(O.polyak(t, p, 1.0)[m]["w"], p[m]["w"]) and np.array_equal(O.polyak(t, p, 0.0)[m]["w"], t[m]["w"])
+        got = O.polyak(t, p, 0.005)[m]["w"]
+        want = 0.005 * p[m]["w"].astype(np.float64) + 0.995 * t[m]["w"].astype(np.float64)
+        assert got.dtype == np.float32
+        np.testing.assert_allclose(got, want, rtol=3e-7, atol=1e-9)
 
 
 def test_terminal_state_quirk_F5():

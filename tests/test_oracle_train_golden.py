@@ -12,6 +12,11 @@ from oracle import dqn_oracle as O
 
 CASES = ["lunar_lander", "sweep", "gamma0_terminal", "d8_b70"]
 
+# nu = b2 nu + (1 - b2) g^2 is QUADRATIC in the gradient: a gradient entry that meets the 1e-5 relative bar has its square
+# within 2e-5 (first order), so nu's bar is twice the gradient's ("tolerances"); the Adam arithmetic
+# itself is checked to 1e-6 against the kernel's own gradient in tests/test_gpu_train_step.py::test_adam_update_from_own_gradient
+NU_RTOL = 2e-5
+
 
 def unflat(flat, D, A):
     tree, o = {}, 0
@@ -47,8 +52,7 @@ def test_oracle_reproduces_the_reference_sources(case):
         assert_close(flat(parts["grads"]), g[f"grads{t}"], what=f"{case} step {t} grads")
         assert_close(flat(params), g[f"theta{t}"], what=f"{case} step {t} params")
         assert_close(flat(opt_state["mu"]), g[f"mu{t}"], what=f"{case} step {t} mu")
-        # nu is quadratic in the gradient: a gradient entry at 0.7e-5 relative is at 1.4e-5 in nu
-        assert_close(flat(opt_state["nu"]), g[f"nu{t}"], rtol=3e-5, what=f"{case} step {t} nu")
+        assert_close(flat(opt_state["nu"]), g[f"nu{t}"], rtol=NU_RTOL, what=f"{case} step {t} nu")
         assert int(opt_state["count"]) == int(g[f"count{t}"]) == t + 1
         if t in set(g["sync_at"].tolist()):
             target = O.tree_copy(params)                         # q_agent.py:143-144
