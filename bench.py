@@ -200,7 +200,7 @@ def timed_reps(ctx, rep_fn, min_seconds=MIN_TIMED_S, max_reps=MAX_REPS, flush=Tr
     a.record(); rep_fn(); b.record()
     torch.cuda.synchronize(device)
     pilot = ctx.max_over_ranks(a.elapsed_time(b) * 1e-3)
-    reps = int(min(max(math.ceil(min_seconds / max(pilot, 1e-7)), min_reps, 1), max(max_reps, min_reps)))
+    reps = int(min(max(math.ceil(1.15 * min_seconds / max(pilot, 1e-7)), min_reps, 1), max(max_reps, min_reps)))   # the flushed pilot is the slowest rep
     starts, ends = [ev() for _ in range(reps)], [ev() for _ in range(reps)]
     ctx.barrier()
     with ClockSampler(ctx.local) as clk:
@@ -526,10 +526,10 @@ def sharded_extras(args, ctx, extras):
     ctx.torch.cuda.empty_cache()
     if ctx.rank == 0:
         sub = argparse.Namespace(**vars(args))
-        sub.steps, sub.warmup = 40, 3
+        sub.steps, sub.warmup = 600, 3
         guarded(extras, "replay", lambda: run_replay(sub, ctx))
         ctx.torch.cuda.empty_cache()
-        sub.steps = 400
+        sub.steps = 2000
         guarded(extras, "per", lambda: run_per(sub, ctx))
         ctx.torch.cuda.empty_cache()
     ctx.barrier()
@@ -654,7 +654,7 @@ def run_replay(args, ctx):
         chk(lib.dqn_store_device(eng.h, 0, nb, *sp))
     for i in range(max(args.warmup, 3)):
         chk(lib.dqn_sample_batch_device(eng.h, 0, None, i, nb, *op))
-    steps = max(min(args.steps, 200), 10)
+    steps = max(min(args.steps, 2000), 10)
     flush_l2(torch, device)
     torch.cuda.synchronize(device)
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -912,8 +912,8 @@ def main():
                     help="train-step kernel of the single/population workloads: one CTA per agent, or one agent over a 4-CTA cluster "
                          "(auto = cluster while 4 * agents <= SMs)")
     args = ap.parse_args()
-    defaults = {"default": (200_000, 2_000), "single": (200_000, 2_000), "population": (256, 3), "dp": (20, 3), "per": (400, 3),
-                "episodes": (1024, 3), "replay": (40, 3)}[args.workload]
+    defaults = {"default": (200_000, 2_000), "single": (200_000, 2_000), "population": (256, 3), "dp": (20, 3), "per": (2000, 3),
+                "episodes": (1024, 3), "replay": (600, 3)}[args.workload]
     if args.steps is None:
         args.steps = defaults[0]
     if args.warmup is None:

@@ -452,6 +452,8 @@ DQN_API int dqn_lb_debug_read(dqn_lb_handle* h, int32_t what, void* host_out, ui
     case DQN_LB_READ_MAX_ACTIONS: src = h->taps.max_actions; avail = B * 4; break;
     case DQN_LB_READ_GRADS: src = h->ws.grads; avail = (size_t)(h->dims.P + 1) * 4; break;
     case DQN_LB_READ_INDICES: src = h->ws.idx; avail = B * 8; break;
+    case DQN_LB_READ_H1: src = h->ws.H1; avail = B * h->dims.H1 * 4; break;
+    case DQN_LB_READ_H2: src = h->ws.H2; avail = B * h->dims.H2 * 4; break;
     default: return lbfail(DQN_E_INVALID, "dqn_lb_debug_read: unknown `what`");
   }
   if (nbytes > avail) return lbfail(DQN_E_INVALID, "dqn_lb_debug_read: nbytes exceeds the buffer");

@@ -7,10 +7,15 @@
 //   every CTA   gathers its 16 transitions (cp.async, one step ahead), runs the three forwards on its rows
 //               (48 "forward rows": (theta,s) | (theta,s') | (theta^-,s')), targets / Huber, and the whole backward,
 //               producing a FULL-SIZE partial gradient in its own shared memory;
-//   cluster     barrier -> reduce-scatter over distributed shared memory: CTA r sums slice r of the four partial
-//               gradients (fixed order 0..3: deterministic), applies Adam to its slice (mu / nu of the slice live in
-//               its registers) and stores the new weights into the shared-memory replica of ALL four CTAs
-//               -> barrier -> next step.
+//   cluster     reduce-scatter + all-gather over distributed shared memory as PUSHES by the bulk-copy engine
+//               (cp.async.bulk shared::cta -> shared::cluster), each completing on an mbarrier of the receiving CTA:
+//               every CTA sends slice r of its partial gradient to CTA r; CTA r waits for the three slices, sums the four
+//               in rank order 0..3 (deterministic), applies Adam to its slice (mu / nu of the slice live in its
+//               registers), and sends the new slice of theta to the three peers' replicas; everybody waits for the three
+//               slices it does not own -> next step.  No cluster barrier and no cluster-scope fence inside the step loop:
+//               data movement and its completion signal are one operation of the async proxy, which is what the PTX
+//               memory model sanctions for cross-CTA shared memory (the previous pull form needed a release at cluster
+//               scope = MEMBAR.ALL.GPU twice per step, 12 % of the step, or relied on unstated hardware behaviour).
 // theta and theta^- stay replicated in every CTA's shared memory; HBM sees only the gathered records and the loss.
 // Same arithmetic and same Philox sampling as train_fused.cu; summation orders differ, results agree to fp32 round-off.
 #include <cooperative_groups.h>
@@ -44,7 +49,7 @@ constexpr int NPC = 4;            // slice parameters per thread: one 16-byte ch
 
 struct CLay {
   int pW2, pWh, PS, SL;
-  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oScr, oMeta, oDummy, oRed, oCmd, oStage, total;
+  int oW, oWt, oG, oGin, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oScr, oMeta, oDummy, oRed, oCmd, oBar, oStage, total;
 };
 
 __host__ __device__ inline CLay make_clayout(int D, int recw) {
@@ -58,6 +63,7 @@ __host__ __device__ inline CLay make_clayout(int D, int recw) {
   L.oW = o; o += PSa;
   L.oWt = o; o += PSa;
   L.oG = o; o += PSa;
+  L.oGin = o; o += (CS - 1) * L.SL;      // gradient slices pushed in by the three peers
   L.oX = o; o += (D + 1) * XS;
   L.oH1 = o; o += kH1 * HS;
   L.oH2 = o; o += (kH2 + 1) * HS;
@@ -70,6 +76,7 @@ __host__ __device__ inline CLay make_clayout(int D, int recw) {
   L.oDummy = o; o += 4;
   L.oRed = o; o += 64;
   L.oCmd = o; o += 8;
+  L.oBar = o; o += 4;                     // two mbarriers: [0] peers' gradient slices have landed, [1] peers' weight slices have landed
   L.oStage = o; o += R * recw;
   L.total = o;
   return L;
@@ -82,38 +89,39 @@ __device__ long long g_phase_clock[16];
 #define PHASE_CLOCK(i) do { } while (0)
 #endif
 
-// Cluster barrier for this kernel's DSMEM protocol.  Everything the CTAs exchange is READ remotely (ld.shared::cluster)
-// from data its owner wrote with ordinary shared-memory stores: partial gradients, new weight slices, loss shares.
-// No CTA ever stores training data into another CTA's shared memory (the one remote store in this file is the session
-// command word, a self-contained 8-byte value the receiver polls).  The PTX memory model wants a release at cluster
-// scope between those stores and a peer's loads; ptxas implements every cluster-scope release as MEMBAR.ALL.GPU.
-//   DQN_CLUSTER_BARRIER = 2 (default)  CTA barrier, then ONE thread executes fence.acq_rel.cluster, then every thread
-//                            arrives relaxed and waits with acquire.  The CTA barrier orders every thread's stores before
-//                            thread 0's fence, the fence + thread 0's arrive form a cumulative release pattern at cluster
-//                            scope, the peers' wait.acquire completes the synchronisation: formally ordered, and only
-//                            one warp pays the MEMBAR while the other seven are already parked at the barrier.
-//   DQN_CLUSTER_BARRIER = 1            the stock cluster.sync(): arrive.release + wait.acquire in all 256 threads.
-//   DQN_CLUSTER_BARRIER = 0            CTA barrier + relaxed arrive, no cluster-scope release at all: relies on the CTA
-//                            barrier having drained the stores into the SM's shared memory (what a remote load reads);
-//                            works on B200, outside the memory model -- kept only to measure what the fence costs.
-#ifdef DQN_CLUSTER_STRICT
-#define DQN_CLUSTER_BARRIER 1
-#endif
-#ifndef DQN_CLUSTER_BARRIER
-#define DQN_CLUSTER_BARRIER 2
-#endif
-__device__ __forceinline__ void cluster_barrier_after_local_stores() {
-#if DQN_CLUSTER_BARRIER == 1
-  cg::this_cluster().sync();
-#elif DQN_CLUSTER_BARRIER == 2
-  __syncthreads();
-  if (threadIdx.x == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-#else
-  __syncthreads();
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;\n" ::: "memory");
-#endif
+// Cluster barrier with release / acquire semantics (MEMBAR.ALL.GPU): used outside the step loop only -- the session's
+// SYNC command and the exit.  The per-step exchange needs none (push + mbarrier, see the file header).
+__device__ __forceinline__ void cluster_barrier_after_local_stores() { cg::this_cluster().sync(); }
+
+// ---- mbarrier / bulk-copy primitives of the push exchange ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, int rank) {      // shared::cta address -> shared::cluster address of CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// this CTA's shared memory -> a peer's shared memory, completion (bytes) signalled on the PEER's mbarrier
+__device__ __forceinline__ void bulk_push(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+// generic-proxy stores of this thread -> visible to the async proxy (the bulk copy that will read them)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- session ("serve") mode: the kernel stays resident and takes commands from mapped host memory (kernels.h) ----
 __device__ __forceinline__ unsigned long long ld_sys_u64(const volatile unsigned long long* p) {
@@ -145,6 +153,14 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   const CLay L = make_clayout(D, recw);
   if (args.gate && !args.gate[agent].train_flag) return;   // episode gate closed (q_agent.py:186): uniform over the CTA / cluster
   PHASE_CLOCK(0);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_addr(sm + L.oBar), 1);          // one arrive.expect_tx by thread 0 per phase + the peers' complete_tx bytes
+    mbar_init(smem_addr(sm + L.oBar) + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (SERVE) *reinterpret_cast<volatile unsigned long long*>(sm + L.oCmd) = 0ull;   // session command word: exists before rank 0 may store into it
+  }
+  // every CTA's mbarriers exist before any peer may push into it: arrive here, wait just before the first step
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 
   float* const W = sm + L.oW;
   float* const Wt = sm + L.oWt;
@@ -214,14 +230,16 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   const float fB = (float)B;
   const int cpr = recw >> 2;
 
-  // remote views of the replicated / partial buffers
-  const float* Wr[CS];
-  const float* Gr[CS];
+  // push exchange: slice c of the packed parameter vector is [c * SL, c * SL + slice_floats(c)), owned by CTA c
+  float* const Gin = sm + L.oGin;      // [3][SL]: slot of source rank s is s - (s > rank)
+  const uint32_t bar_g = smem_addr(sm + L.oBar), bar_w = bar_g + 8;
+  auto slice_bytes = [&](int c) { const int n = L.PS - c * L.SL; return (uint32_t)(4 * (n < L.SL ? n : L.SL)); };
+  uint32_t bytes_w_in = 0;
 #pragma unroll
-  for (int c = 0; c < CS; ++c) { Wr[c] = cluster.map_shared_rank(W, c); Gr[c] = cluster.map_shared_rank(G, c); }
-  const float* Redr[CS];
-#pragma unroll
-  for (int c = 0; c < CS; ++c) Redr[c] = cluster.map_shared_rank(Red, c);
+  for (int c = 0; c < CS; ++c) if (c != rank) bytes_w_in += slice_bytes(c);
+  const int pLoss = L.pW2 + kH2;       // a padding slot of the packed layout inside slice 0 (row 0 of [W2;b2], column 64): carries
+                                       //   each CTA's loss share through the gradient exchange; masked out before Adam
+  uint32_t par_g = 0, par_w = 0;       // phase parities of the two mbarriers
 
   // staged-record word -> smem destination (threads 0..63: 4 lanes per row)
   const int urow = t >> 2, ul4 = t & 3;
@@ -260,8 +278,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
 
   PHASE_CLOCK(1);
   if (!serve) prefetch(0, 0);
-  // (no cluster barrier here: the first remote access comes after the first step's cluster barrier, which every CTA
-  //  reaches only after its own shared memory is initialised)
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // pairs with the arrive at the top: all mbarriers are initialised
   PHASE_CLOCK(2);
 
   // ---- session mode -------------------------------------------------------------------------------------------------
@@ -274,10 +291,6 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   volatile unsigned long long* CmdWordR[CS];
 #pragma unroll
   for (int c = 0; c < CS; ++c) CmdWordR[c] = cluster.map_shared_rank(const_cast<unsigned long long*>(CmdWord), c);
-  if (serve) {
-    if (t == 0) *CmdWord = 0ull;
-    cluster.sync();                      // every CTA's command word exists before rank 0 may store into it
-  }
 
   int kstep = 0;
   for (;; ++kstep) {
@@ -363,10 +376,13 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       size = rc < args.dims.N ? rc : args.dims.N;
       prefetch(kstep, 0);
     }
+    const bool gather_after = serve || kstep + 1 < args.K;      // the last step of a K-step launch needs no all-gather
     if (t == 0) {
       if (count0 + kstep < 0x7fffffff) { pb1 *= (double)b1; pb2 *= (double)b2; }
       Red[8 + 2 * (kstep & 1)] = 1.0f - (float)pb1;
       Red[9 + 2 * (kstep & 1)] = 1.0f - (float)pb2;
+      mbar_arrive_expect_tx(bar_g, (CS - 1) * slice_bytes(rank));        // this step's incoming gradient slices
+      if (gather_after) mbar_arrive_expect_tx(bar_w, bytes_w_in);         // ... and weight slices
     }
     float loss_acc = 0.f;    // warp 0 only
 
@@ -591,19 +607,36 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     }  // tiles
 
     if (kstep == args.K - 1) PHASE_CLOCK(4);
-    if (t == 0) Red[0] = loss_acc;           // this CTA's share of the loss; rank 0 pulls the four shares after the barrier
-    cluster_barrier_after_local_stores();
-    if (kstep == args.K - 1) PHASE_CLOCK(5);                          // all partial gradients (and loss shares) are complete and visible
+    if (t == 0) G[pLoss] = loss_acc;         // this CTA's share of the loss rides in a padding slot of slice 0
+    fence_proxy_async();                     // this thread's stores into G -> visible to the bulk copies issued below
+    __syncthreads();                         // the partial gradient of this CTA is complete
+    // ---- reduce-scatter (push): slice c of this CTA's partial gradient -> slot of CTA c ----
+    if (t < CS && t != rank)
+      bulk_push(map_to_rank(smem_addr(Gin + (rank - (rank > t ? 1 : 0)) * L.SL), t), smem_addr(G + t * L.SL), slice_bytes(t), map_to_rank(bar_g, t));
+    mbar_wait(bar_g, par_g);                 // the three peers' slices of MY slice have landed
+    par_g ^= 1u;
+    if (kstep == args.K - 1) PHASE_CLOCK(5);
 
-    // ---- reduce-scatter (pull) + Adam on this CTA's slice; the new slice goes to the LOCAL replica only ----
+    // ---- Adam on this CTA's slice; the new slice goes to the local replica, then to the peers ----
     if (owner) {
       const float c1 = Red[8 + 2 * (kstep & 1)], c2 = Red[9 + 2 * (kstep & 1)];
       const float rc1 = 1.0f / c1, rc2 = 1.0f / c2;
       const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
-      const float4 g0 = ld4(Gr[0] + pown), g1 = ld4(Gr[1] + pown), g2 = ld4(Gr[2] + pown), g3 = ld4(Gr[3] + pown);
+      float4 gs[CS];
+#pragma unroll
+      for (int c = 0; c < CS; ++c) gs[c] = c == rank ? ld4(G + pown) : ld4(Gin + (c - (c > rank ? 1 : 0)) * L.SL + 4 * t);
       const float4 th4 = ld4(W + pown);
-      const float g[4] = {((g0.x + g1.x) + g2.x) + g3.x, ((g0.y + g1.y) + g2.y) + g3.y,      // fixed rank order: deterministic
-                          ((g0.z + g1.z) + g2.z) + g3.z, ((g0.w + g1.w) + g2.w) + g3.w};
+      float g[4] = {((gs[0].x + gs[1].x) + gs[2].x) + gs[3].x, ((gs[0].y + gs[1].y) + gs[2].y) + gs[3].y,      // fixed rank order: deterministic
+                    ((gs[0].z + gs[1].z) + gs[2].z) + gs[3].z, ((gs[0].w + gs[1].w) + gs[2].w) + gs[3].w};
+      if (rank == 0 && 4 * t == (pLoss & ~3)) {      // the thread whose chunk holds the loss slot (pLoss % 4 == 0: component 0)
+        const float loss = g[0] / fB;
+        g[0] = 0.f;                                   // padding parameter: no gradient, stays 0
+        args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
+        if (serve || kstep == args.K - 1)
+          args.loss_mailbox[agent] = ((unsigned long long)(uint32_t)(step0 + kstep + 1) << 32) | __float_as_uint(loss);
+        if (serve) st_sys_u64(&sess->response, (next_seq << 32) | __float_as_uint(loss));
+        if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
+      }
       const float th[4] = {th4.x, th4.y, th4.z, th4.w};
       float nw[4];
 #pragma unroll
@@ -617,32 +650,25 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       st4(W + pown, nw[0], nw[1], nw[2], nw[3]);
       if (args.taps.enabled && args.taps.grads) st4(args.taps.grads + pown, g[0], g[1], g[2], g[3]);
     }
-    if (rank == 0 && t == 0) {
-      const float loss = (((Redr[0][0] + Redr[1][0]) + Redr[2][0]) + Redr[3][0]) / fB;
-      args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
-      if (serve || kstep == args.K - 1)
-        args.loss_mailbox[agent] = ((unsigned long long)(uint32_t)(step0 + kstep + 1) << 32) | __float_as_uint(loss);
-      if (serve) st_sys_u64(&sess->response, (next_seq << 32) | __float_as_uint(loss));
-      if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
-    }
-    cluster_barrier_after_local_stores();    // every slice of theta_{t+1} is in its owner's replica; nobody reads the partial gradients any more
     if (serve) ++next_seq;
-    if (serve || kstep + 1 < args.K) {
-      // all-gather (pull): the three slices the peers own, 16-byte DSMEM loads.  Peers rewrite their slices only after
-      // the next step's first cluster barrier, which this CTA reaches after these loads.
-      const int pp = 4 * t;
-      float4 ws[CS];
-#pragma unroll
-      for (int c = 0; c < CS; ++c)
-        if (c != rank && pp < L.SL && c * L.SL + pp < L.PS) ws[c] = ld4(Wr[c] + c * L.SL + pp);
-#pragma unroll
-      for (int c = 0; c < CS; ++c)
-        if (c != rank && pp < L.SL && c * L.SL + pp < L.PS) st4(W + c * L.SL + pp, ws[c].x, ws[c].y, ws[c].z, ws[c].w);
+    if (gather_after) {
+      // ---- all-gather (push): my new slice -> the three peers' replicas; wait for theirs ----
+      fence_proxy_async();
+      __syncthreads();                       // the whole slice is written
+      if (t < CS && t != rank)
+        bulk_push(map_to_rank(smem_addr(W + rank * L.SL), t), smem_addr(W + rank * L.SL), slice_bytes(rank), map_to_rank(bar_w, t));
+      mbar_wait(bar_w, par_w);
+      par_w ^= 1u;
+      // Only now may the partial gradient be cleared: a bulk copy signals completion at its DESTINATION, so the sender
+      // learns that its pushes out of G were consumed through the peers' weight slices -- each of which was sent behind
+      // an Adam step that had waited for exactly those pushes.
       for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) st4(G + 4 * p4, 0.f, 0.f, 0.f, 0.f);
     }
   }  // steps
   PHASE_CLOCK(6);
-  if (serve) cluster_barrier_after_local_stores();   // peers may still be pulling this CTA's weight slice of the last step
+  // No CTA may leave while a bulk copy still reads its shared memory or a peer may still push into it: every push of
+  // the last step has completed once all four CTAs are past their last mbarrier wait.
+  cluster.sync();
 
   // ---- write back this CTA's slice (the last cluster barrier above was the last DSMEM access: CTAs may exit freely) ----
   if (owner) {

@@ -181,6 +181,15 @@ class LargeBatchTrainer:
     def synchronize(self):
         _lib.check(self.lib.dqn_lb_synchronize(self.h))
 
+    def debug_read_activations(self):
+        """Hidden activations h1, h2 of the (theta, s) rows of the last forward_backward (numpy) -- parity tests use their
+        signs to follow the device's branch of relu' where a pre-activation is within fp32 round-off of zero."""
+        h1 = np.empty((self.batch_local, self.hidden[0]), np.float32)
+        h2 = np.empty((self.batch_local, self.hidden[1]), np.float32)
+        _lib.check(self.lib.dqn_lb_debug_read(self.h, 5, _lib.ptr(h1), h1.nbytes))
+        _lib.check(self.lib.dqn_lb_debug_read(self.h, 6, _lib.ptr(h2), h2.nbytes))
+        return h1, h2
+
     def debug_read(self):
         """Intermediates of the last forward_backward(debug=True) as numpy (parity tests)."""
         B, A = self.batch_local, self.num_actions

@@ -276,7 +276,8 @@ typedef struct dqn_lb_config {
 } dqn_lb_config;
 
 typedef struct dqn_lb_handle dqn_lb_handle;
-enum { DQN_LB_READ_Q = 0, DQN_LB_READ_TARGETS = 1, DQN_LB_READ_MAX_ACTIONS = 2, DQN_LB_READ_GRADS = 3, DQN_LB_READ_INDICES = 4 };
+enum { DQN_LB_READ_Q = 0, DQN_LB_READ_TARGETS = 1, DQN_LB_READ_MAX_ACTIONS = 2, DQN_LB_READ_GRADS = 3, DQN_LB_READ_INDICES = 4,
+       DQN_LB_READ_H1 = 5, DQN_LB_READ_H2 = 6 };   /* hidden activations of the (theta, s) rows: [B][hidden1], [B][hidden2] */
 
 DQN_API int dqn_lb_arena_bytes(const dqn_lb_config* cfg, uint64_t* bytes_out);
 DQN_API int dqn_lb_create(const dqn_lb_config* cfg, dqn_lb_handle** out);

@@ -38,14 +38,14 @@ class OracleAgent:
     def update_target_model(self, tau=None):                        # q_agent.py:143-144 (tau: Polyak extension, dqn_oracle.polyak)
         self.target_params = O.tree_copy(self.params) if tau is None else O.polyak(self.target_params, self.params, tau)
 
-    def step(self, indices=None):                                   # q_agent.py:146-169
+    def step(self, indices=None, device_h=None, tie_tol=0.0):      # q_agent.py:146-169 (device_h: see dqn_oracle.relu_masks)
         if indices is None:
             indices = sample_indices(self.seed, self.agent_id, self.train_steps,
                                      self.batch_size, self.replay.size)
         batch = gather(indices, *self.replay.arrays())
         self.params, self.opt_state, parts = O.train_step(
             self.params, self.target_params, self.opt_state, batch, self.gamma, self.opt,
-            return_parts=True, loss=self.loss)
+            return_parts=True, loss=self.loss, device_h=device_h, tie_tol=tie_tol)
         parts["indices"] = np.asarray(indices, dtype=np.int64)
         self.last = parts
         self.train_steps += 1

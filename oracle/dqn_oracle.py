@@ -72,7 +72,7 @@ def tree_leaves(tree):
 # ------------------------------------------------------------------------------------------------
 # A.1 forward  (LunarLander/dddqn.py:24-34)
 # ------------------------------------------------------------------------------------------------
-def forward(params, x, return_cache=False):
+def forward(params, x, return_cache=False, return_pre=False):
     x = np.asarray(x, dtype=F32)
     l1, l2, lv, la = (params[m] for m in MODULES)
     z1 = x @ l1["w"] + l1["b"]                       # dddqn.py:25
@@ -83,6 +83,8 @@ def forward(params, x, return_cache=False):
     adv = h2 @ la["w"] + la["b"]                     # :30  [B,A]
     q = val + adv - np.mean(adv, axis=1, keepdims=True, dtype=F32)   # :31
     q = q.astype(F32)
+    if return_pre:
+        return q, (x, h1, h2), (z1, z2)
     if return_cache:
         return q, (x, h1, h2)
     return q
@@ -157,9 +159,28 @@ def compute_loss(params, states, q_targets, loss="huber"):
 # ------------------------------------------------------------------------------------------------
 # A.4 backward  (jax.grad(compute_loss), q_learning_functions.py:23)  -- hand-derived
 # ------------------------------------------------------------------------------------------------
-def loss_and_grads(params, states, q_targets, loss="huber"):
+def relu_masks(z1, z2, device_h=None, tie_tol=0.0):
+    """relu'(z) = [z > 0] for both hidden layers.  ``device_h = (h1, h2)`` (activations computed by the implementation
+    under test) resolves NEAR-TIES: where ``|z| <= tie_tol * max|z|`` -- a pre-activation within fp32 round-off of zero,
+    where the derivative of ReLU is discontinuous and either branch is a correctly rounded result -- the device's branch
+    ``[h > 0]`` is taken; everywhere else the two must agree (asserted).  Returns (m1, m2, number of near-ties)."""
+    out, ties = [], 0
+    for i, z in enumerate((z1, z2)):
+        m = z > 0
+        if device_h is not None:
+            near = np.abs(z) <= F32(tie_tol) * np.abs(z).max()
+            dm = np.asarray(device_h[i]) > 0
+            assert np.array_equal(dm[~near], m[~near]), "relu masks differ away from zero"
+            m = np.where(near, dm, m)
+            ties += int((near & (dm != (z > 0))).sum())
+        out.append(m)
+    return out[0], out[1], ties
+
+
+def loss_and_grads(params, states, q_targets, loss="huber", device_h=None, tie_tol=0.0):
     """Loss and d(loss)/d(params) with the targets held constant (they are inputs)."""
-    pred, (x, h1, h2) = forward(params, states, return_cache=True)
+    pred, (x, h1, h2), (z1, z2) = forward(params, states, return_pre=True)
+    m1, m2, _ = relu_masks(z1, z2, device_h, tie_tol)
     b, a = pred.shape
     l, e = huber(pred, q_targets) if loss == "huber" else l2_loss(pred, q_targets)
     loss_value = F32(np.mean(np.sum(l, axis=1, dtype=F32), axis=0, dtype=F32))
@@ -172,10 +193,10 @@ def loss_and_grads(params, states, q_targets, loss="huber"):
     grads = OrderedDict()
     grads[MODULES[2]] = {"w": (h2.T @ dval).astype(F32), "b": dval.sum(axis=0, dtype=F32)}
     grads[MODULES[3]] = {"w": (h2.T @ dadv).astype(F32), "b": dadv.sum(axis=0, dtype=F32)}
-    dh2 = (dval @ lv["w"].T + dadv @ la["w"].T).astype(F32) * (h2 > 0)  # relu'(0) = 0
+    dh2 = (dval @ lv["w"].T + dadv @ la["w"].T).astype(F32) * m2         # relu'(0) = 0
     dh2 = dh2.astype(F32)
     grads[MODULES[1]] = {"w": (h1.T @ dh2).astype(F32), "b": dh2.sum(axis=0, dtype=F32)}
-    dh1 = ((dh2 @ l2["w"].T) * (h1 > 0)).astype(F32)
+    dh1 = ((dh2 @ l2["w"].T) * m1).astype(F32)
     grads[MODULES[0]] = {"w": (x.T @ dh1).astype(F32), "b": dh1.sum(axis=0, dtype=F32)}
     return loss, OrderedDict((m, grads[m]) for m in MODULES)
 
@@ -245,11 +266,11 @@ def polyak(target_params, params, tau):
     return tree_map(lambda new, old: (t * new + (F32(1.0) - t) * old).astype(F32), params, target_params)
 
 
-def train_step(params, target_params, opt_state, batch, gamma, opt, return_parts=False, loss="huber"):
+def train_step(params, target_params, opt_state, batch, gamma, opt, return_parts=False, loss="huber", device_h=None, tie_tol=0.0):
     s, a, r, s2, d = preprocessing(*batch)                                   # q_agent.py:154-158
     targets, parts = compute_q_targets(params, target_params, s, a, r, s2, d, gamma,
                                        return_parts=True)                   # :159-165
-    loss, grads = loss_and_grads(params, s, targets, loss)                   # :166 (grad)
+    loss, grads = loss_and_grads(params, s, targets, loss, device_h, tie_tol)   # :166 (grad)
     new_params, new_opt_state = adam_update(params, grads, opt_state, opt)   # :166 (update/apply)
     if return_parts:
         parts.update(targets=targets, loss=loss, grads=grads)

@@ -122,15 +122,21 @@ def test_real_layer_shapes_consecutive_steps(gemm_mode):
     8192-row reduction in dW2 (8192 rows = one rank's share of the 65 536-row batch on 8 GPUs) -- in both GEMM modes, and
     THREE CONSECUTIVE steps without re-seeding the device state from the oracle: step t starts from the device's own
     theta_{t-1} / mu / nu.  This is the shape where a K-dependent error (TMEM accumulation truncates) would show.
-    Weights whose Adam quotient is ill-conditioned (IllConditioned above) carry their offset forward, so they stay masked."""
+    Weights whose Adam quotient is ill-conditioned (IllConditioned above) carry their offset forward, so they stay masked.
+
+    At this size (8192 x 2048 hidden pre-activations per step) a few pre-activations land within fp32 round-off of zero,
+    where relu' is discontinuous: one flipped unit moves a column of dW2 by ~1e-3 of its largest entry and every entry of
+    dW1 by ~1e-4 (profiles/r2_lb_error_growth.md).  Either branch is a correctly rounded result, so the oracle follows the
+    device's branch for |z| <= TIE_TOL * max|z| and asserts that the masks agree everywhere else (dqn_oracle.relu_masks)."""
+    TIE_TOL = {"fp32": 2e-6, "tc3xtf32": 1e-5}[gemm_mode]
     H = (1024, 1024)
     tr, ora = make(B=8192, kind="adamw", gemm_mode=gemm_mode, N=20000, fill=20000, HID=H, seed=9)
     atol = ATOL_SCALE[gemm_mode]
     ill = IllConditioned()
     for step in range(3):
-        ref = ora.step()
         tr.forward_backward(debug=True)
         got = tr.debug_read()
+        ref = ora.step(device_h=tr.debug_read_activations(), tie_tol=TIE_TOL)
         what = f"{gemm_mode} H=1024 step {step}"
         assert np.array_equal(got["indices"], ref["indices"]), what
         assert np.array_equal(got["max_actions"], ref["max_actions"]), what
