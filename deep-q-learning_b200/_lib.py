@@ -140,6 +140,7 @@ PROTOTYPES = {
     "dqn_lb_comm_connect": (C.c_int, [_H, _P, C.POINTER(C.c_void_p)]),
     "dqn_lb_allreduce": (C.c_int, [_H]),
     "dqn_lb_apply": (C.c_int, [_H]),
+    "dqn_lb_train_step": (C.c_int, [_H, _P, _i32]),
     "dqn_lb_sync_target": (C.c_int, [_H]),
     "dqn_lb_polyak_target": (C.c_int, [_H, C.c_float]),
     "dqn_lb_set_loss_kind": (C.c_int, [_H, _i32]),

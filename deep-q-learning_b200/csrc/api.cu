@@ -63,7 +63,7 @@ int validate(const dqn_config* cfg, Dims* d) {
   d->A = cfg->num_actions;
   d->P = flat_param_count(d->D, d->A);
   d->PK = packed_count(d->D);
-  d->recw = record_words(d->D);
+  d->recw = record_words_host(d->D);
   d->N = cfg->buffer_size;
   return DQN_OK;
 }

@@ -82,7 +82,7 @@ int lb_validate(const dqn_lb_config* cfg, LbDims* d) {
   d->D = cfg->obs_dim; d->A = cfg->num_actions; d->H1 = cfg->hidden1; d->H2 = cfg->hidden2; d->B = cfg->batch_local;
   d->P = d->D * d->H1 + d->H1 + d->H1 * d->H2 + d->H2 + d->H2 + 1 + d->H2 * d->A + d->A;
   d->PF = (d->P + 1 + 3) & ~3;      // +1: the loss rides behind the gradients through the all-reduce
-  d->recw = record_words(d->D);
+  d->recw = record_words_host(d->D);
   d->N = cfg->buffer_size;
   return DQN_OK;
 }
@@ -110,7 +110,9 @@ struct dqn_lb_handle {
   CommPeers peers;
   void* opened[kMaxWorld];     // cudaIpcOpenMemHandle results to close
   bool connected;
-  unsigned epoch;
+  unsigned epoch[kCommChannels];
+  cudaStream_t comm_stream;      // second stream: the W2 gradient is exchanged here while the main stream finishes backward
+  cudaEvent_t ev_dw2, ev_comm;
   unsigned long long comm_timeout_ns;
   int loss_kind;
 };
@@ -174,7 +176,8 @@ DQN_API int dqn_lb_create(const dqn_lb_config* cfg, dqn_lb_handle** out) {
   h->taps.targets = (float*)(a + c.targets); h->taps.max_actions = (int*)(a + c.maxa); h->taps.enabled = 0;
   h->stage = a + c.stage;
   h->ring_counter = 0; h->train_steps = 0; h->adam_count = 0; h->pinned = nullptr;
-  h->window = nullptr; h->connected = false; h->epoch = 0; h->loss_kind = kLossHuber;
+  h->window = nullptr; h->connected = false; h->epoch[0] = h->epoch[1] = 0; h->loss_kind = kLossHuber;
+  h->comm_stream = nullptr; h->ev_dw2 = h->ev_comm = nullptr;
   {
     const char* ms = getenv("DQN_B200_COMM_TIMEOUT_MS");
     const double v = ms ? atof(ms) : 20000.0;
@@ -201,6 +204,9 @@ DQN_API int dqn_lb_destroy(dqn_lb_handle* h) {
   if (!h) return DQN_OK;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
+  if (h->comm_stream) { cudaStreamSynchronize(h->comm_stream); cudaStreamDestroy(h->comm_stream); }
+  if (h->ev_dw2) cudaEventDestroy(h->ev_dw2);
+  if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   for (int q = 0; q < kMaxWorld; ++q) if (h->opened[q]) cudaIpcCloseMemHandle(h->opened[q]);
   if (h->window) cudaFree(h->window);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -384,10 +390,60 @@ DQN_API int dqn_lb_allreduce(dqn_lb_handle* h) {
   if (!h->connected) return lbfail(DQN_E_INVALID, "dqn_lb_allreduce: dqn_lb_comm_connect has not been called");
   if (int rc = comm_failed(h)) return rc;
   CU(cudaSetDevice(h->cfg.device));
-  h->epoch += 1;
-  CU(lb_allreduce(h->stream, h->peers, h->cfg.world, h->cfg.rank, h->dims.PF / 4, h->epoch, h->comm_timeout_ns,
+  CommRange whole = {{0, 0}, {h->dims.PF / 4, 0}};
+  h->epoch[1] += 1;
+  CU(lb_allreduce(h->stream, h->peers, h->cfg.world, h->cfg.rank, h->dims.PF / 4, whole, 1, h->epoch[1], h->comm_timeout_ns,
                   const_cast<unsigned*>(comm_host_error(h))));
   return DQN_OK;
+}
+
+// One whole train step: forward + backward, gradient exchange, Adam -- with the exchange of the W2 gradient overlapped
+// with the rest of backward.  world = 1: no exchange.  Needs the peer-memory windows (dqn_lb_comm_*)
+// when world > 1; with an external collective (NCCL) the caller uses forward_backward / its all-reduce / apply instead.
+DQN_API int dqn_lb_train_step(dqn_lb_handle* h, const int64_t* idx, int32_t debug) {
+  if (!h) return lbfail(DQN_E_INVALID, "handle is NULL");
+  const int W = h->cfg.world;
+  if (W == 1) {
+    if (int rc = dqn_lb_forward_backward(h, idx, debug)) return rc;
+    return dqn_lb_apply(h);
+  }
+  if (!h->connected) return lbfail(DQN_E_INVALID, "dqn_lb_train_step: dqn_lb_comm_connect has not been called");
+  if (int rc = comm_failed(h)) return rc;
+  CU(cudaSetDevice(h->cfg.device));
+  if (!h->comm_stream) {
+    CU(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_dw2, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+  }
+  const long long size = lb_size(h);
+  if (size == 0) return lbfail(DQN_E_INVALID, "dqn_lb_train_step: the replay ring is empty");
+  const int B = h->dims.B;
+  if (idx) {
+    for (int i = 0; i < B; ++i) if (idx[i] < 0 || idx[i] >= size) return lbfail(DQN_E_INVALID, "dqn_lb_train_step: index outside [0, size)");
+    if ((size_t)B * 8 > kLbStage) return lbfail(DQN_E_INVALID, "index block exceeds the staging buffer");
+    CU(cudaMemcpyAsync(h->ws.idx, idx, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CU(launch_philox_indices(h->stream, h->ws.idx, B, h->cfg.seed, 0, h->train_steps, size, h->cfg.rank * B));
+  }
+  CU(launch_replay_gather(h->stream, h->ring, ring_dims(h), 0, h->ws.idx, 0, 0, 0, size, B, h->ws.s, h->ws.a, h->ws.r, h->ws.s2, h->ws.done));
+  h->taps.enabled = debug ? 1 : 0;
+  const float inv = 1.0f / ((float)B * (float)W);
+  CU(lb_forward_backward(h->stream, h->dims, h->ws, h->cfg.gamma, inv, h->cfg.gemm_mode, h->loss_kind, h->taps, h->ev_dw2));
+  const LbDims& d = h->dims;
+  const int offW2 = d.D * d.H1 + d.H1, nW2 = d.H1 * d.H2;          // both multiples of 4 (hidden widths are multiples of 256)
+  unsigned* herr = const_cast<unsigned*>(comm_host_error(h));
+  // channel 0, second stream: the W2 gradient, as soon as it is final
+  CU(cudaStreamWaitEvent(h->comm_stream, h->ev_dw2, 0));
+  CommRange big = {{offW2 / 4, 0}, {nW2 / 4, 0}};
+  h->epoch[0] += 1;
+  CU(lb_allreduce(h->comm_stream, h->peers, W, h->cfg.rank, d.PF / 4, big, 0, h->epoch[0], h->comm_timeout_ns, herr));
+  CU(cudaEventRecord(h->ev_comm, h->comm_stream));
+  // channel 1, main stream: everything else (W1, b1 | b2, heads, loss), behind the dW1 pass
+  CommRange rest = {{0, (offW2 + nW2) / 4}, {offW2 / 4, d.PF / 4 - (offW2 + nW2) / 4}};
+  h->epoch[1] += 1;
+  CU(lb_allreduce(h->stream, h->peers, W, h->cfg.rank, d.PF / 4, rest, 1, h->epoch[1], h->comm_timeout_ns, herr));
+  CU(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+  return dqn_lb_apply(h);
 }
 
 DQN_API int dqn_lb_apply(dqn_lb_handle* h) {

@@ -14,6 +14,11 @@
 //   phase 2   the last block of the grid to finish tells every rank "slice r is in place" and waits until every
 //             rank has said so; when the kernel retires, the whole window holds the global sum.
 //
+// One launch covers a RANGE of the vector on one of two flag CHANNELS, so that two exchanges can be in flight at once:
+// dqn_lb_train_step sends the W2 gradient (4 MB of the 4.26 MB) on channel 0 from a second stream as soon as the dW2
+// GEMM's split-K partials are reduced -- the transfer then runs under the dh1 GEMM and the dW1 pass -- and the small
+// remainder (W1, biases, heads, loss) on channel 1 behind them.
+//
 // Flags carry the step number (monotonic), so nothing is ever reset.  Every spin is bounded (wall-clock time-out,
 // DQN_B200_COMM_TIMEOUT_MS, default 20 s).  A rank that never shows up does not hang the GPU and does not corrupt
 // training either: a block that times out in phase 0 raises the error flag (in the window and in a word of mapped host
@@ -62,7 +67,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, 
 }
 
 template <int W>
-__global__ void __launch_bounds__(256) lb_allreduce_kernel(const CommPeers peers, int rank, int n4, unsigned epoch,
+__global__ void __launch_bounds__(256) lb_allreduce_kernel(const CommPeers peers, int rank, int n4, const CommRange range, int ch, unsigned epoch,
                                                            unsigned long long timeout_ns, unsigned* host_error) {
   CommFlags* const mine = comm_flags(peers.win[rank], n4);
   const int t = threadIdx.x;
@@ -73,18 +78,20 @@ __global__ void __launch_bounds__(256) lb_allreduce_kernel(const CommPeers peers
   // ---- phase 0 ----
   if (blockIdx.x == 0 && t < W) {
     __threadfence_system();
-    st_release_sys(&comm_flags(peers.win[t], n4)->ready[rank], epoch);
+    st_release_sys(&comm_flags(peers.win[t], n4)->ready[ch][rank], epoch);
   }
-  if (t < W && (mine->error || !wait_flag(&mine->ready[t], epoch, timeout_ns))) {
+  if (t < W && (mine->error || !wait_flag(&mine->ready[ch][t], epoch, timeout_ns))) {
     mine->error = 1; *host_error = 1u; s_fail = 1;
   }
   __syncthreads();
   if (s_fail) return;                    // nothing is summed and nothing is stored anywhere; Adam is predicated on the flag
 
   // ---- phase 1: reduce my slice, broadcast it ----
-  const int chunk = (n4 + W - 1) / W;
-  const int lo = rank * chunk, hi = min(n4, lo + chunk);
-  for (int i = lo + blockIdx.x * blockDim.x + t; i < hi; i += gridDim.x * blockDim.x) {
+  const int total = range.n4[0] + range.n4[1];
+  const int chunk = (total + W - 1) / W;
+  const int lo = rank * chunk, hi = min(total, lo + chunk);
+  for (int j = lo + blockIdx.x * blockDim.x + t; j < hi; j += gridDim.x * blockDim.x) {
+    const int i = j < range.n4[0] ? range.lo4[0] + j : range.lo4[1] + (j - range.n4[0]);     // position in the gradient vector
     float4 acc = ld_peer4(reinterpret_cast<const float4*>(peers.win[0]) + i);
 #pragma unroll
     for (int q = 1; q < W; ++q) {
@@ -98,28 +105,29 @@ __global__ void __launch_bounds__(256) lb_allreduce_kernel(const CommPeers peers
   // ---- phase 2 ----
   __threadfence_system();
   __syncthreads();
-  if (t == 0) s_last = atomicAdd(&mine->blocks_done, 1u) == gridDim.x - 1;
+  if (t == 0) s_last = atomicAdd(&mine->blocks_done[ch], 1u) == gridDim.x - 1;
   __syncthreads();
   if (s_last) {
-    if (t == 0) mine->blocks_done = 0;
+    if (t == 0) mine->blocks_done[ch] = 0;
     if (t < W) {
-      st_release_sys(&comm_flags(peers.win[t], n4)->done[rank], epoch);
-      if (!wait_flag(&mine->done[t], epoch, timeout_ns)) { mine->error = 1; *host_error = 1u; }
+      st_release_sys(&comm_flags(peers.win[t], n4)->done[ch][rank], epoch);
+      if (!wait_flag(&mine->done[ch][t], epoch, timeout_ns)) { mine->error = 1; *host_error = 1u; }
     }
   }
 }
 
 }  // namespace
 
-cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, unsigned epoch,
-                         unsigned long long timeout_ns, unsigned* host_error) {
-  const int chunk = (n4 + world - 1) / world;
+cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, const CommRange& range, int channel,
+                         unsigned epoch, unsigned long long timeout_ns, unsigned* host_error) {
+  if (channel < 0 || channel >= kCommChannels) return cudaErrorInvalidValue;
+  const int chunk = (range.n4[0] + range.n4[1] + world - 1) / world;
   int grid = (chunk + 255) / 256;
   grid = grid < 1 ? 1 : (grid > 96 ? 96 : grid);     // all blocks co-resident on any B200 (they poll each other's progress)
   switch (world) {
-    case 2: lb_allreduce_kernel<2><<<grid, 256, 0, st>>>(peers, rank, n4, epoch, timeout_ns, host_error); break;
-    case 4: lb_allreduce_kernel<4><<<grid, 256, 0, st>>>(peers, rank, n4, epoch, timeout_ns, host_error); break;
-    case 8: lb_allreduce_kernel<8><<<grid, 256, 0, st>>>(peers, rank, n4, epoch, timeout_ns, host_error); break;
+    case 2: lb_allreduce_kernel<2><<<grid, 256, 0, st>>>(peers, rank, n4, range, channel, epoch, timeout_ns, host_error); break;
+    case 4: lb_allreduce_kernel<4><<<grid, 256, 0, st>>>(peers, rank, n4, range, channel, epoch, timeout_ns, host_error); break;
+    case 8: lb_allreduce_kernel<8><<<grid, 256, 0, st>>>(peers, rank, n4, range, channel, epoch, timeout_ns, host_error); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

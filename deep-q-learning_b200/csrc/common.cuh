@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace dqn {
 
@@ -90,6 +91,16 @@ __host__ __device__ inline int packed_to_flat(int p, int D, int A) {
   return c == 0 ? offbv : offba + (c - 1);
 }
 __host__ __device__ inline int record_words(int D) { return (((2 * D + 4) * 4 + 31) / 32) * 8; }
+// Host side: the record stride a handle is created with.  DQN_B200_RECORD_BYTES (a multiple of 32, experiment knob) raises
+// the stride, e.g. to one 128-byte L2 line per record.
+inline int record_words_host(int D) {
+  int w = record_words(D);
+  if (const char* e = getenv("DQN_B200_RECORD_BYTES")) {
+    const int b = atoi(e);
+    if (b % 32 == 0 && b / 4 >= w && b <= 160) w = b / 4;
+  }
+  return w;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  Bit-exact twin of oracle/philox.py.

@@ -39,16 +39,19 @@ struct LbWorkspace {
 // ---- peer-memory gradient all-reduce (comm_p2p.cu) ----
 constexpr int kMaxWorld = 8;
 struct CommPeers { float* win[kMaxWorld]; };          // every rank's window, addressable from this GPU
+constexpr int kCommChannels = 2;                       // independent exchanges that may be in flight at once (one per stream)
 struct CommFlags {                                     // lives behind the n4 * 4 floats of a window
-  unsigned ready[kMaxWorld];                           // ready[q] = step number once rank q's gradient is complete
-  unsigned done[kMaxWorld];                            // done[q]  = step number once rank q has broadcast its slice
-  unsigned blocks_done, error;
+  unsigned ready[kCommChannels][kMaxWorld];            // ready[c][q] = epoch once rank q's part of channel c is complete
+  unsigned done[kCommChannels][kMaxWorld];             // done[c][q]  = epoch once rank q has broadcast its slice
+  unsigned blocks_done[kCommChannels], error;
 };
+// The part of the gradient vector one exchange covers: up to two ranges of float4 indices, treated as one index space.
+struct CommRange { int lo4[2], n4[2]; };
 __host__ __device__ inline CommFlags* comm_flags(float* win, int n4) { return reinterpret_cast<CommFlags*>(win + 4 * (size_t)n4); }
 inline size_t comm_window_bytes(int n4) { return (((size_t)n4 * 16 + sizeof(CommFlags)) + 255) / 256 * 256; }
 // host_error: a word of mapped pinned host memory that mirrors CommFlags.error (polled by the C ABI without a sync)
-cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, unsigned epoch,
-                         unsigned long long timeout_ns, unsigned* host_error);
+cudaError_t lb_allreduce(cudaStream_t st, const CommPeers& peers, int world, int rank, int n4, const CommRange& range, int channel,
+                         unsigned epoch, unsigned long long timeout_ns, unsigned* host_error);
 
 cudaError_t lb_gemm_ffma(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                          float* C, int ldc, const float* aux, int ldaux, int splitk);
@@ -57,8 +60,10 @@ cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const flo
 // dispatcher (gemm_mode: kGemmModeFFMA / kGemmModeTC3xTF32)
 cudaError_t lb_gemm(cudaStream_t st, int gemm_mode, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                     float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws);
+// after_dw2: nullptr, or an event recorded on `st` as soon as the W2 gradient (the 4 MB bulk of the vector) is final -- the
+// caller starts exchanging it on another stream while dh1 / dW1 are still being computed
 cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float gamma, float inv_global_batch,
-                                int gemm_mode, int loss_kind, const LbTaps& taps);
+                                int gemm_mode, int loss_kind, const LbTaps& taps, cudaEvent_t after_dw2 = nullptr);
 cudaError_t lb_polyak(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float tau);
 // comm_error: nullptr, or the window's CommFlags.error -- a non-zero value turns the update into a no-op
 cudaError_t lb_adam(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float b1, float b2, float c1, float c2,

@@ -486,7 +486,7 @@ lb_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int r
 
 // One forward/backward pass over the local batch already gathered into ws.s/a/r/s2/done.
 cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorkspace& ws, float gamma, float inv_global_batch,
-                                int gemm_mode, int loss_kind, const LbTaps& taps) {
+                                int gemm_mode, int loss_kind, const LbTaps& taps, cudaEvent_t after_dw2) {
   const int B = d.B, H1n = d.H1, H2n = d.H2, D = d.D, A = d.A;
   const int offb1 = D * H1n, offW2 = offb1 + H1n, offb2 = offW2 + H1n * H2n, offWv = offb2 + H2n;
   const int offbv = offWv + H2n, offba = offbv + 1 + H2n * A;
@@ -531,6 +531,7 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     const long long n = (long long)H1n * H2n;
     LBCHK(launch_reduce_partials(st, ws.gemmpart, ws.grads + offW2, n, splitk, n));
     LBCHK(cudaGetLastError());
+    if (after_dw2) LBCHK(cudaEventRecord(after_dw2, st));
   }
   if (gemm_mode == kGemmModeTC3xTF32) {
     // dh1 = relu'(h1) * (dh2 . W2^T): the tensor-core kernel's NT form (K-major B) runs at 126 TF against 151 TF for the NN

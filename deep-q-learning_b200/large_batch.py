@@ -140,13 +140,7 @@ class LargeBatchTrainer:
 
     # -- one train step ---------------------------------------------------------------------------------
     def forward_backward(self, indices=None, debug=False):
-        idx = None
-        if indices is not None:          # global index list of the step; this rank takes its contiguous slice
-            idx = np.ascontiguousarray(indices, dtype=np.int64)
-            if idx.shape == (self.batch_global,):
-                idx = np.ascontiguousarray(idx[self.rank * self.batch_local:(self.rank + 1) * self.batch_local])
-            elif idx.shape != (self.batch_local,):
-                raise ValueError("indices must have batch_global or batch_local entries")
+        idx = self._local_indices(indices)
         _lib.check(self.lib.dqn_lb_forward_backward(self.h, _lib.ptr(idx), 1 if debug else 0))
 
     def all_reduce(self):
@@ -159,10 +153,25 @@ class LargeBatchTrainer:
     def apply(self):
         _lib.check(self.lib.dqn_lb_apply(self.h))
 
+    def _local_indices(self, indices):
+        if indices is None:
+            return None
+        idx = np.ascontiguousarray(indices, dtype=np.int64)      # global index list of the step; this rank takes its contiguous slice
+        if idx.shape == (self.batch_global,):
+            idx = np.ascontiguousarray(idx[self.rank * self.batch_local:(self.rank + 1) * self.batch_local])
+        elif idx.shape != (self.batch_local,):
+            raise ValueError("indices must have batch_global or batch_local entries")
+        return idx
+
     def step(self, indices=None):
-        self.forward_backward(indices)
-        self.all_reduce()
-        self.apply()
+        """One train step.  With the library's own exchange (or a single rank) this is ONE C call that overlaps the exchange
+        of the W2 gradient with the rest of backward; with NCCL it is forward_backward -> all_reduce -> apply."""
+        if self.collective in ("p2p", "none"):
+            _lib.check(self.lib.dqn_lb_train_step(self.h, _lib.ptr(self._local_indices(indices)), 0))
+        else:
+            self.forward_backward(indices)
+            self.all_reduce()
+            self.apply()
 
     def sync_target(self):
         _lib.check(self.lib.dqn_lb_sync_target(self.h))

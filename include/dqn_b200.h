@@ -307,6 +307,11 @@ DQN_API int dqn_lb_comm_connect(dqn_lb_handle* h, const void* ipc_handles /* wor
 DQN_API int dqn_lb_allreduce(dqn_lb_handle* h);
 /* optimizer.update + apply_updates (q_learning_functions.py:24-25) with whatever is in the gradient buffer. */
 DQN_API int dqn_lb_apply(dqn_lb_handle* h);
+/* One whole step = dqn_lb_forward_backward + gradient exchange over the peer-memory windows + dqn_lb_apply, with the
+ * exchange of the W2 gradient (the bulk of the vector) issued on a second stream as soon as it is final, so that it
+ * overlaps the remaining backward GEMM (q_learning_functions.py:36 makes the shard gradients additive).
+ * world = 1: no exchange.  Replicas stay bit-identical (one reducer per element, fixed rank order). */
+DQN_API int dqn_lb_train_step(dqn_lb_handle* h, const int64_t* idx_or_null, int32_t debug);
 DQN_API int dqn_lb_sync_target(dqn_lb_handle* h);
 /* Extensions, as for the small-batch handle: soft target update and the L2 loss. */
 DQN_API int dqn_lb_polyak_target(dqn_lb_handle* h, float tau);

@@ -140,12 +140,15 @@ def test_real_layer_shapes_consecutive_steps(gemm_mode):
         what = f"{gemm_mode} H=1024 step {step}"
         assert np.array_equal(got["indices"], ref["indices"]), what
         assert np.array_equal(got["max_actions"], ref["max_actions"]), what
+        # step t starts from a device state that already carries t steps of round-off, and a batch-summed gradient
+        # amplifies a relative perturbation of theta by the cancellation in the sum: the per-step bar compounds
+        grow = step + 1
         for k in ("q", "next_q", "next_q_tm", "targets"):
-            assert_close(got[k], ref[k], atol_scale=atol, what=f"{what} {k}")
+            assert_close(got[k], ref[k], rtol=1e-5 * grow, atol_scale=atol * grow, what=f"{what} {k}")
         assert abs(got["loss"] - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"])), what
         for m in O.MODULES:
             for k in ("w", "b"):
-                assert_close(got["grads"][m][k], ref["grads"][m][k], atol_scale=atol, what=f"{what} grad {m}/{k}")
+                assert_close(got["grads"][m][k], ref["grads"][m][k], rtol=1e-5 * grow, atol_scale=atol * grow, what=f"{what} grad {m}/{k}")
         tr.apply()
         assert_params_close(tr.get_params(), ora, ill, what)
 
@@ -215,6 +218,38 @@ def test_peer_memory_allreduce_kernel(world):
             for m in O.MODULES:
                 assert np.array_equal(ps[0][m]["w"], p[m]["w"]) and np.array_equal(ps[0][m]["b"], p[m]["b"])
         assert_params_close(ps[0], ora, ill, f"p2p world {world} step {step}")
+
+
+def test_overlapped_step_equals_sequential_exchange():
+    """dqn_lb_train_step (W2 gradient exchanged on a second stream as soon as it is final, the rest behind dW1) gives the
+    same bits as forward_backward -> whole-vector all-reduce -> apply: one reducer per element, rank order, either way."""
+    import torch
+    def group(tag):
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        ranks = []
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                tr, _ = make(B=512, world=2, rank=r, collective="p2p", connect=False)
+            ranks.append(tr)
+        dqn_b200.LargeBatchTrainer.connect_in_process(ranks)
+        return ranks
+    a, b = group("overlap"), group("sequential")
+    for step in range(3):
+        for tr in a:
+            tr.step()
+        for tr in b:
+            tr.forward_backward()
+        for tr in b:
+            tr.all_reduce()
+        for tr in b:
+            tr.apply()
+        for tr in a + b:
+            tr.synchronize()
+        pa, pb = [tr.get_params() for tr in a], [tr.get_params() for tr in b]
+        for m in O.MODULES:
+            for k in ("w", "b"):
+                assert np.array_equal(pa[0][m][k], pa[1][m][k]) and np.array_equal(pa[0][m][k], pb[0][m][k]), f"step {step} {m}/{k}"
+        assert a[0].loss() == b[0].loss()
 
 
 def test_allreduce_timeout_skips_the_update_and_raises(monkeypatch):

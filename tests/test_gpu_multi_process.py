@@ -33,15 +33,18 @@ data = synthetic_transitions(rng, 2500, D, A, done_p=0.2)
 
 def run(collective):
     tr = dqn_b200.LargeBatchTrainer(D, A, HID, B, N, 0.99, dqn_b200.adamw(1e-3), rank=rank, world_size=world, seed=7, device=rank,
-                                    collective=collective)
+                                    collective="p2p" if collective == "p2p_seq" else collective)
     tr.set_params(params, 0); tr.set_params(params, 1)
     tr.store(*data)
     for _ in range(4):
-        tr.step()
+        if collective == "p2p_seq":          # the exchange as ONE whole-vector kernel behind backward (no overlap)
+            tr.forward_backward(); tr.all_reduce(); tr.apply()
+        else:                                # p2p: dqn_lb_train_step, W2 gradient exchanged on a second stream under dh1 / dW1
+            tr.step()
     flat = np.concatenate([np.ravel(tr.get_params()[m][k]) for m in O.MODULES for k in ("w", "b")])
     return flat, tr.loss()
 
-for coll in ("p2p", "nccl"):
+for coll in ("p2p", "p2p_seq", "nccl"):
     flat, loss = run(coll)
     t = torch.from_numpy(flat).cuda()
     every = [torch.empty_like(t) for _ in range(world)]
@@ -81,6 +84,8 @@ def test_two_processes_two_gpus(tmp_path):
     # ---- large-batch DP: replicas bit-identical; p2p ~ nccl ~ single rank ----
     p2p, nccl = np.load(tmp_path / "dp_p2p.npz"), np.load(tmp_path / "dp_nccl.npz")
     assert np.array_equal(p2p["params"][0], p2p["params"][1]) and np.array_equal(nccl["params"][0], nccl["params"][1])
+    seq = np.load(tmp_path / "dp_p2p_seq.npz")
+    assert np.array_equal(seq["params"], p2p["params"])          # overlapped exchange == whole-vector exchange, bit for bit
     HID, B, D, A, N = (256, 256), 512, 8, 4, 3000
     rng = np.random.default_rng(0)
     params = O.init_params(rng, D, A, hidden=HID, bias_std=0.05)
