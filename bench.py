@@ -912,6 +912,12 @@ def main():
                     help="train-step kernel of the single/population workloads: one CTA per agent, or one agent over a 4-CTA cluster "
                          "(auto = cluster while 4 * agents <= SMs)")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner, ...) are sent to stderr
+    # for the whole run; the line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    emit = lambda line: (real_stdout.write(json.dumps(line) + "\n"), real_stdout.flush())
     defaults = {"default": (200_000, 2_000), "single": (200_000, 2_000), "population": (256, 3), "dp": (20, 3), "per": (2000, 3),
                 "episodes": (1024, 3), "replay": (600, 3)}[args.workload]
     if args.steps is None:
@@ -923,7 +929,7 @@ def main():
     if args.impl == "reference":
         line = run_reference(args, ctx)
         if line is not None:
-            print(json.dumps(line))
+            emit(line)
         return
     if args.gpus != ctx.world and ctx.world == 1 and args.gpus > 1:
         # convenience: re-launch under torchrun, one rank per GPU
@@ -936,7 +942,7 @@ def main():
               "population": run_population, "dp": run_dp, "per": run_per, "episodes": run_episodes, "replay": run_replay}[args.workload]
         line = fn(args, ctx)
         if ctx.rank == 0 and line is not None:
-            print(json.dumps(line))
+            emit(line)
     finally:
         ctx.close()
 

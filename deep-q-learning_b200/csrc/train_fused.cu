@@ -2,8 +2,9 @@
 //
 // One CTA = one agent.  For K consecutive train steps it does everything Agent._step does
 // (General/QLearning/q_agent.py:146-169) without leaving the SM:
-//   sample_batch        replay_buffer.py:68-85        Philox (or supplied) indices, cp.async gather of
-//                                                      whole AoS records into shared memory, one step ahead
+//   sample_batch        replay_buffer.py:68-85        Philox (or supplied) indices; every sampled record is ONE bulk
+//                                                      async copy (cp.async.bulk global -> shared, the TMA engine's
+//                                                      non-tensor form) completing on an mbarrier, one step ahead
 //   preprocessing       q_learning_functions.py:76-85  done -> f32, action -> i32 while unpacking
 //   compute_q_targets   q_learning_functions.py:42-64  3 forwards, first-max argmax, F5-quirk TD target
 //   compute_loss        q_learning_functions.py:31-39  Huber(delta=1) summed over actions, mean over B
@@ -25,6 +26,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tile_ops.cuh"
+#include "tile16.cuh"
 
 namespace dqn {
 
@@ -41,9 +43,31 @@ constexpr int WS2 = kW2Stride;   // row stride of the [W2;b2] block (68: rows 4 
 constexpr int NPT = 13;
           // ceil(max smem-layout params / NT), D = 16: (17*32 + 33*64 + 65*8) = 3176
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// one whole record: global -> shared by the bulk-copy engine, bytes counted on the mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 struct Lay {   // offsets in floats
   int pW2, pWh, PS;
-  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oQB, oScr, oMeta, oDummy, oRed, oStage, total;
+  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oQB, oScr, oMeta, oDummy, oRed, oBar, oStage, total;
 };
 
 __host__ __device__ inline Lay make_layout(int D, int recw) {
@@ -68,6 +92,7 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
   L.oMeta = o; o += BT * 4;
   L.oDummy = o; o += 4;
   L.oRed = o; o += 32;
+  L.oBar = o; o += 4;               // mbarrier of the record gather
   L.oStage = o; o += BT * recw;
   L.total = o;
   return L;
@@ -139,6 +164,14 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   const int ntiles = (B + BT - 1) / BT;
   const float fB = (float)B;
   const int cpr = recw >> 2;
+  // Batches of 65..80 rows (the sweep draws up to 70, hyperparameter_optimization.py:121): 64 rows through the 64-row tile
+  // code, the rest through the 16-row tile code of tile16.cuh -- a second 64-row tile for six rows doubled the step and, in
+  // a one-wave launch (128 agents per GPU at 8 GPUs), the whole launch.  Its buffers alias X | H1 | H2, dead between tiles.
+  const bool tail16 = B > BT && B - BT <= t16::R;
+  const int nfull = tail16 ? 1 : ntiles;
+  t16::Bufs tb;
+  tb.W = W; tb.Wt = Wt; tb.G = G; tb.Red = Red; tb.pW2 = L.pW2; tb.pWh = L.pWh; tb.D = D;
+  tb.carve(sm + L.oX);
 
   // Record word -> smem destination of this thread's staged chunks (fixed for the whole launch):
   // thread t owns 16-byte chunks (t&3), (t&3)+4, (t&3)+8 of staged row t>>2.
@@ -154,22 +187,30 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
     udst[q] = o;
   }
 
-  // gather of (step kstep, tile) into the staging buffer; 4 lanes per row, 16-byte cp.async each
+  // gather of (step kstep, tile) into the staging buffer: one thread per row issues ONE bulk copy of the whole record
+  // (96 B for D <= 10); thread 0 posts the expected byte count of the tile on the mbarrier every thread waits on
+  const uint32_t bar = smem_addr(sm + L.oBar);
+  uint32_t bar_parity = 0;
+  if (t == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
   auto prefetch = [&](int kstep, int tile) {
-    const int i = tile * BT + urow;
-    float* dst = Stage + urow * recw;
-    if (i < B) {
-      long long slot;
-      if (args.idx) slot = args.idx[((size_t)sel * args.K + kstep) * B + i];
-      else slot = philox_index(args.seed, args.agent_id_base + agent, step0 + kstep, i, size);
-      const uint32_t* src = ring + slot * recw;
-      for (int c = ul4; c < cpr; c += 4) cp_async16(dst + 4 * c, src + 4 * c);
-      if (args.taps.enabled && ul4 == 0 && args.taps.indices) args.taps.indices[i] = slot;
-    } else {
-      for (int c = ul4; c < cpr; c += 4) st4(dst + 4 * c, 0.f, 0.f, 0.f, 0.f);
+    const int nvalid = B - tile * BT < BT ? B - tile * BT : BT;
+    if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * recw * 4));
+    if (ul4 == 0) {
+      const int i = tile * BT + urow;
+      float* dst = Stage + urow * recw;
+      if (i < B) {
+        long long slot;
+        if (args.idx) slot = args.idx[((size_t)sel * args.K + kstep) * B + i];
+        else slot = philox_index(args.seed, args.agent_id_base + agent, step0 + kstep, i, size);
+        bulk_load(smem_addr(dst), ring + slot * recw, (uint32_t)(recw * 4), bar);
+        if (args.taps.enabled && args.taps.indices) args.taps.indices[i] = slot;
+      } else {
+        for (int c = 0; c < cpr; ++c) st4(dst + 4 * c, 0.f, 0.f, 0.f, 0.f);
+      }
     }
-    cp_async_commit();
   };
+  auto gather_wait = [&]() { mbar_wait(bar, bar_parity); bar_parity ^= 1u; };
 
   double pb1 = ctl->pb1, pb2 = ctl->pb2;   // b1**count, b2**count carried across launches (thread 0 uses them)
 
@@ -186,9 +227,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
     }
     float loss_acc = 0.f;   // meaningful in warps 0,1
 
-    for (int tile = 0; tile < ntiles; ++tile) {
+    for (int tile = 0; tile < nfull; ++tile) {
       // ---- unpack staged records (k-major X, raw meta words): part of preprocessing (:76-85) ----
-      cp_async_wait_all();
+      gather_wait();
       __syncthreads();
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
@@ -510,6 +551,35 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
       }
       // the barrier at the top of the next tile / before Adam orders these G updates
     }  // tiles
+
+    if (tail16) {   // rows 64 .. B-1 (staged by the prefetch of "tile 1": rows >= B are zero-filled)
+      gather_wait();
+      __syncthreads();                       // also: every thread is done with tile 0 (its buffers are about to be reused)
+      if (t < 4 * t16::R) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const int c = ul4 + 4 * cc;
+          if (c < cpr) {
+            const float4 v = ld4(Stage + urow * recw + 4 * c);
+            const float w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int wd = 4 * c + j;
+              if (wd < D) tb.X[wd * t16::XS + urow] = w4[j];
+              else if (wd < 2 * D) tb.X[(wd - D) * t16::XS + t16::R + urow] = w4[j];
+              else if (wd < 2 * D + 4) tb.Meta[urow * 4 + (wd - 2 * D)] = w4[j];
+            }
+          }
+        }
+      }
+      for (int r = t; r < t16::HS; r += NT) { if (r < t16::XS) tb.X[D * t16::XS + r] = 1.f; tb.H2[kH2 * t16::HS + r] = 1.f; }
+      __syncthreads();
+      if (kstep + 1 < args.K) prefetch(kstep + 1, 0);
+      const float lp = t16::step<A>(tb, BT, B, fB, gamma, l2loss, args.taps);
+      if (t < t16::R) loss_acc += lp;        // warp 0 (its lane 0 publishes the sum below)
+      __syncthreads();
+      for (int r = t; r < RS2; r += NT) { X[D * RS2 + r] = 1.f; H2[kH2 * RS2 + r] = 1.f; }   // the 64-row layout's ones rows were overwritten
+    }
 
     if ((warp == 0 || warp == 1) && lane == 0) Red[warp] = loss_acc;
     __syncthreads();
