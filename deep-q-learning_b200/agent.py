@@ -162,9 +162,7 @@ class Agent:
         if indices is None:
             # the add()s staged since the last step (train_frequency of them, q_agent.py:182-187) ride in the
             # kernel's parameter buffer: one launch, no H2D copy (falls back to store + train for > 16)
-            n = rb._pending
-            _lib.check(self._lib.dqn_store_train_step(self._h, 0, n, *rb._ptrs, 1, None))
-            rb._pending = 0                                   # only once the library has taken the staged transitions
+            rb.step_staged()
         else:
             rb.flush()
             self._engine.train_steps(1, indices=indices, agent_begin=0, agent_end=1)

@@ -222,7 +222,7 @@ class DqnEngine:
         return out
 
     def last_loss(self, agent=0):
-        """Loss of the most recent train step (synchronises; the kernel writes it to mapped host memory)."""
+        """Loss of the most recent train step (waits for it; the kernel writes it to mapped host memory)."""
         _lib.check(self.lib.dqn_get_losses(self.h, agent, 1, self._loss1_ptr, None))
         return float(self._loss1[0])
 

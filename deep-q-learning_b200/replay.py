@@ -71,6 +71,14 @@ class ReplayBuffer:
         self._pa, self._pr, self._pd = np.zeros(self._cap, np.int64), np.zeros(self._cap, np.float32), np.zeros(self._cap, np.bool_)
         self._ptrs = tuple(_lib.ptr(x) for x in (self._ps, self._pa, self._pr, self._po, self._pd))
         self._stage = _hoststage.new(*self._ptrs, d, self._cap) if _hoststage is not None else None
+        self._bound = False
+        if self._stage is not None and hasattr(_hoststage, "bind"):
+            # the per-step C-ABI calls by address (no ctypes marshalling): dqn_store_train_step / dqn_get_losses of THIS handle
+            import ctypes as C
+            lib = _engine.lib
+            _hoststage.bind(self._stage, int(_engine.h.value), C.cast(lib.dqn_store_train_step, C.c_void_p).value,
+                            C.cast(lib.dqn_get_losses, C.c_void_p).value, int(_agent))
+            self._bound = True
         self._pending = 0
         self._counter = 0
         self._num_samples = 0
@@ -108,6 +116,28 @@ class ReplayBuffer:
         self._pr[i] = reward
         self._po[i] = observation
         self._pd[i] = done
+
+    def step_staged(self):
+        """``dqn_store_train_step(h, agent, n_staged, <staging arrays>, K=1, NULL)``: the staged add()s and ONE train step as one
+        command / launch.  Returns after enqueueing."""
+        n = self._pending
+        e = self._engine
+        if self._bound:
+            rc = _hoststage.step(self._stage, n)
+            if rc:
+                _lib.check(rc)
+        else:
+            _lib.check(e.lib.dqn_store_train_step(e.h, self._agent, n, *self._ptrs, 1, None))
+        self._pending = 0                                   # only once the library has taken the staged transitions
+
+    def last_loss(self):
+        """Loss of the most recent train step of this buffer's agent (waits for it)."""
+        if self._bound:
+            rc, loss = _hoststage.loss(self._stage)
+            if rc:
+                _lib.check(rc)
+            return loss
+        return self._engine.last_loss(self._agent)
 
     def flush(self):
         """Move staged add() transitions into the device ring (no-op when nothing is pending)."""
