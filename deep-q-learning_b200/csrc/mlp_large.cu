@@ -413,23 +413,19 @@ lb_head_grads_kernel(const float* __restrict__ red, float* __restrict__ grads, i
   grads[offb2 + j] = red[(size_t)(1 + kMaxA) * H2n + j];
 }
 
-// final reduction of the targets-kernel partials: loss -> grads[P] (extra slot), d head bias -> grads
-__global__ void lb_finish_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ grads, int P, int A, int offbv) {
-  const int c = threadIdx.x;
-  if (c >= 2 + kMaxA) return;
+// final reduction of the targets-kernel partials: loss -> grads[P] (extra slot), d(head bias) -> grads.  One warp per
+// column (0 = loss, 1 = d bv, 2.. = d ba): lane l sums blocks l, l + 32, ... in order, then a fixed shuffle tree.
+__global__ void __launch_bounds__(32 * (2 + kMaxA))
+lb_finish_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ grads, int P, int A, int offbv, int offba) {
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * 16 + c];
+  for (int b = lane; b < nblk; b += 32) s += partial[(size_t)b * 16 + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
   if (c == 0) grads[P] = s;                       // loss (local share of the global mean), extra slot after the P gradients
   else if (c == 1) grads[offbv] = s;              // d bv
-}
-
-// d ba lives after Wa: separate tiny kernel keeps the index arithmetic readable
-__global__ void lb_finish_ba_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ grads, int A, int offba) {
-  const int c = threadIdx.x;
-  if (c >= A) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * 16 + 2 + c];
-  grads[offba + c] = s;
+  else if (c - 2 < A) grads[offba + (c - 2)] = s; // d ba
 }
 
 // optax adam / adamw, exact fp32 (memory-bound: IEEE division and sqrt are free here)
@@ -510,8 +506,7 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
   const int nblk = (B + 255) / 256;
   lb_targets_kernel<<<nblk, 256, 0, st>>>(ws.Q, ws.a, ws.r, ws.done, ws.dhd, ws.partial, B, A, gamma, inv_global_batch, loss_kind, taps);
   LBCHK(cudaGetLastError());
-  lb_finish_kernel<<<1, 32, 0, st>>>(ws.partial, nblk, ws.grads, d.P, A, offbv);
-  lb_finish_ba_kernel<<<1, 32, 0, st>>>(ws.partial, nblk, ws.grads, A, offba);
+  lb_finish_kernel<<<1, 32 * (2 + kMaxA), 0, st>>>(ws.partial, nblk, ws.grads, d.P, A, offbv, offba);
   LBCHK(cudaGetLastError());
   // ---- backward ----
   const int nchunk = B / RC;
