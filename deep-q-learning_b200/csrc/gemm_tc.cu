@@ -21,6 +21,8 @@
 //   NN  h2 = h1 . W2        A K-major  (h1 [M][K]),   B MN-major (W2 [K][N])
 //   NT  dh1 = dh2 . W2^T    A K-major  (dh2 [M][K]),  B K-major  (W2 [N][K])
 //   TN  dW2 = h1^T . dh2    A MN-major (h1 [K][M]),   B MN-major (dh2 [K][N]), split-K over the batch
+#include <stdio.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "large.h"
@@ -400,6 +402,254 @@ gemm_tc_kernel(int M, int N, const float* __restrict__ A, int lda, const float* 
   }
 }
 
+// =====================================================================================================================
+// cta_group::2 form of the NN products (A K-major in tensor memory, B MN-major in shared memory): two CTAs of a cluster
+// -- an SM pair -- compute a 256 x 128 tile with ONE tcgen05.mma stream issued by the leader CTA (M = 256).  Each CTA
+// stages its own 128 rows of A into its own tensor memory and only HALF of the B tile (64 of the 128 columns) into its own
+// shared memory; the tensor cores of both SMs read both halves.  Per SM that halves the producers' B work (loads, hi / lo
+// split, shared-memory stores) and the shared-memory bytes each MMA reads -- the single-CTA kernel is bound by exactly
+// those (ncu: l1tex 55 %, tensor pipe 42 %, the MMA warp waiting for the producers).
+//   full[s]   (leader's)  one arrival per producer warp of BOTH CTAs (remote mbarrier.arrive for the peer's): count 8
+//   empty[s]  (both)      tcgen05.commit.cta_group::2 ... multicast::cluster -> the slot is free in both CTAs
+//   tfull[b]  (both)      same multicast commit: accumulator chunk b complete in both CTAs' tensor memory
+//   tempty[b] (leader's)  one arrival per epilogue warp of both CTAs: count 8
+// =====================================================================================================================
+constexpr int TN2 = TN / 2;                    // B columns staged per CTA
+constexpr int kSbo2 = (TN2 / 32) * kLboMN;     // stride between k atoms of a 64-column MN-major tile: 1024 B
+constexpr int kTileMN2 = (TK / 4) * kSbo2;     // 8192 B
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cta_addr, uint32_t rank) {   // arrive on CTA `rank`'s copy of the barrier
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar_cta_addr), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc),
+      "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc2(bool b_mn) {   // D = F32, A = B = TF32, M = 256, N = 128, A K-major
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// half B tile (32 k x 64 columns) of this CTA: G[k][mn] row-major; thread p: float4 column mq = p & 15, k = (p >> 4) + 8 i
+__device__ __forceinline__ void ld_b_half(const float* __restrict__ G, int ld, int n0, int k0, int p, float4 (&v)[4]) {
+  const int mq = p & 15, kb = p >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(G + (size_t)(k0 + kb + 8 * i) * ld + n0 + 4 * mq);
+}
+__device__ __forceinline__ void st_b_half(const float4 (&v)[4], uint8_t* s_hi, uint8_t* s_lo, int p) {
+  const int mq = p & 15, kb = p >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = kb + 8 * i, u = mq & 7;
+    const int off = (k >> 2) * kSbo2 + (mq >> 3) * kLboMN + (k & 3) * 128 + ((((u >> 1) ^ (k & 3)) << 5) | ((u & 1) << 4));
+    float4 hi, lo;
+    split_tf32(v[i], hi, lo);
+    *reinterpret_cast<float4*>(s_hi + off) = hi;
+    *reinterpret_cast<float4*>(s_lo + off) = lo;
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc2_kernel(int M, int N, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                const float* __restrict__ aux, int ldaux, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kStages = 4;
+  constexpr int kStageBytes = 2 * kTileMN2;            // b_hi | b_lo of this CTA's 64 columns
+  constexpr uint32_t kTmemCols = 512u;                 // 2 accumulators x 128 + 4 stages x (32 hi + 32 lo) columns of A
+  uint8_t* const tiles = smem;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* const full = bars, *const empty = bars + kStages, *const tfull = bars + 2 * kStages, *const tempty = bars + 2 * kStages + 2;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();             // 0 = leader (issues the MMAs)
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;   // grid.x runs over the row tiles: a cluster (2, 1, 1) is two consecutive row tiles
+  const int nb0 = n0 + (int)rank * TN2;                // this CTA's half of the B tile
+  const int nk = K / TK;
+  const int nchunks = nk / kStagesPerChunk;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), 8);                // 4 producer warps x 2 CTAs (only the leader's copy is used)
+      mbar_init(smem_u32(&empty[s]), 1);               // one multicast tcgen05.commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull[b]), 1);               // one multicast tcgen05.commit
+      mbar_init(smem_u32(&tempty[b]), 8);              // 4 epilogue warps x 2 CTAs (leader's copy)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {                                     // the same warp of both CTAs allocates collectively
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // both CTAs' barriers and TMEM exist
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers (both CTAs): own 128 rows of A -> TMEM, own 64 columns of B -> shared memory =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    float4 va0[8], va1[8], va2[8], vb0[4], vb1[4], vb2[4];
+    uint8_t* const xpose = reinterpret_cast<uint8_t*>(tmem_slot) + 64 + warp * 4096;
+    auto stage_out = [&](int kt, float4 (&va)[8], float4 (&vb)[4]) {
+      const int s = kt % kStages;
+      row_transpose(va, xpose, lane);
+      if (kt >= kStages) mbar_wait(smem_u32(&empty[s]), ((kt / kStages) - 1) & 1);
+      uint8_t* st = tiles + s * kStageBytes;
+      st_a_tmem(va, tmem_d + 256u + (uint32_t)(s * 64), tmem_d + 256u + (uint32_t)(s * 64 + 32), tid);
+      st_b_half(vb, st, st + kTileMN2, tid);
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&full[s]), 0u);
+    };
+    ld_tile<false>(A, lda, m0, 0, tid, va0); ld_b_half(B, ldb, nb0, 0, tid, vb0);
+    if (nk > 1) { ld_tile<false>(A, lda, m0, TK, tid, va1); ld_b_half(B, ldb, nb0, TK, tid, vb1); }
+    if (nk > 2) { ld_tile<false>(A, lda, m0, 2 * TK, tid, va2); ld_b_half(B, ldb, nb0, 2 * TK, tid, vb2); }
+    for (int kt = 0; kt < nk; kt += 3) {
+      stage_out(kt, va0, vb0);
+      if (kt + 3 < nk) { ld_tile<false>(A, lda, m0, (kt + 3) * TK, tid, va0); ld_b_half(B, ldb, nb0, (kt + 3) * TK, tid, vb0); }
+      if (kt + 1 < nk) {
+        stage_out(kt + 1, va1, vb1);
+        if (kt + 4 < nk) { ld_tile<false>(A, lda, m0, (kt + 4) * TK, tid, va1); ld_b_half(B, ldb, nb0, (kt + 4) * TK, tid, vb1); }
+      }
+      if (kt + 2 < nk) {
+        stage_out(kt + 2, va2, vb2);
+        if (kt + 5 < nk) { ld_tile<false>(A, lda, m0, (kt + 5) * TK, tid, va2); ld_b_half(B, ldb, nb0, (kt + 5) * TK, tid, vb2); }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== MMA issuer: one thread of the LEADER CTA =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (rank == 0 && warp == 8 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc2(true);
+      for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % kStages;
+        const int chunk = kt / kStagesPerChunk, b = chunk & 1;
+        const bool chunk_start = (kt % kStagesPerChunk) == 0;
+        if (chunk_start && chunk >= 2) {
+          mbar_wait(smem_u32(&tempty[b]), ((chunk >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(&full[s]), (kt / kStages) & 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_d + (uint32_t)(b * TN);
+        const uint32_t b_hi = smem_u32(tiles + s * kStageBytes), b_lo = b_hi + kTileMN2;
+        const uint32_t ta_hi = tmem_d + 256u + (uint32_t)(s * 64), ta_lo = ta_hi + 32u;
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint32_t boff = ks * 2 * kSbo2;          // two k atoms per k-step of 8
+          const uint64_t dbh = make_desc(b_hi + boff, kLboMN, kSbo2, 1), dbl = make_desc(b_lo + boff, kLboMN, kSbo2, 1);
+          const uint32_t first = (chunk_start && ks == 0) ? 0u : 1u;
+          umma2_tf32_ts(acc, ta_hi + 8u * ks, dbl, idesc, first);
+          umma2_tf32_ts(acc, ta_lo + 8u * ks, dbh, idesc, 1u);
+          umma2_tf32_ts(acc, ta_hi + 8u * ks, dbh, idesc, 1u);
+        }
+        umma2_commit(smem_u32(&empty[s]));
+        if ((kt % kStagesPerChunk) == kStagesPerChunk - 1) umma2_commit(smem_u32(&tfull[b]));
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): own 128 rows x 128 columns =====================
+    const int q = warp - 4;
+    const int m = m0 + 32 * q + lane;
+    float acc[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int b = chunk & 1;
+      mbar_wait(smem_u32(&tfull[b]), (chunk >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * TN);
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[b]), 0u);
+    }
+    float* crow = C + (size_t)m * ldc + n0;
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      if (EPI == kEpiBiasRelu) {
+        const float4 bb = *reinterpret_cast<const float4*>(aux + n0 + j);
+        v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f); v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
+      } else if (EPI == kEpiReluMask) {
+        const float4 h = *reinterpret_cast<const float4*>(aux + (size_t)m * ldaux + n0 + j);
+        v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(crow + j) = v;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // nobody frees TMEM / leaves while the pair still works
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <int EPI>
+cudaError_t launch_tc2(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       const float* aux, int ldaux) {
+  constexpr int smem = 4 * (2 * kTileMN2) + 256 + 4 * 4096;   // stages | barriers | transpose staging
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(M / TM, N / TN, 1);                      // cluster (2, 1, 1): CTAs (2j, y) and (2j + 1, y) are a pair
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (getenv("DQN_B200_GEMM_DEBUG")) {
+    int ncl = -1;
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&ncl, gemm_tc2_kernel<EPI>, &cfg);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, gemm_tc2_kernel<EPI>);
+    fprintf(stderr, "gemm_tc2: max active clusters %d (%s), regs %d, static smem %zu, max dyn smem %d, grid %u x %u\n", ncl, cudaGetErrorString(qe),
+            fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, cfg.gridDim.x, cfg.gridDim.y);
+  }
+  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, M, N, A, lda, B, ldb, C, ldc, aux, ldaux, K);
+}
+
 template <bool A_MN, bool B_MN, int EPI>
 cudaError_t launch_tc(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                       const float* aux, int ldaux, int splitk) {
@@ -422,6 +672,12 @@ cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const flo
                        float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws) {
   (void)ws;
   if (M % TM || N % TN || (K / splitk) % kChunkK) return cudaErrorInvalidValue;
+  // NN products on SM pairs (cta_group::2) when the row tiles pair up; DQN_B200_GEMM_CG=1 keeps the single-CTA kernel
+  static const bool pairs = [] { const char* e = getenv("DQN_B200_GEMM_CG"); return !(e && atoi(e) == 1); }();
+  if (pairs && (M / TM) % 2 == 0) {
+    if (kind == kGemmNN_BiasRelu) return launch_tc2<kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
+    if (kind == kGemmNN_ReluMask) return launch_tc2<kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
+  }
   switch (kind) {
     case kGemmNN_BiasRelu: return launch_tc<false, true, kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
     case kGemmNT_ReluMask: return launch_tc<false, false, kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
