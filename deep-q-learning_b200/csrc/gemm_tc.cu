@@ -21,6 +21,7 @@
 //   NN  h2 = h1 . W2        A K-major  (h1 [M][K]),   B MN-major (W2 [K][N])
 //   NT  dh1 = dh2 . W2^T    A K-major  (dh2 [M][K]),  B K-major  (W2 [N][K])
 //   TN  dW2 = h1^T . dh2    A MN-major (h1 [K][M]),   B MN-major (dh2 [K][N]), split-K over the batch
+#include <cuda.h>
 #include <stdio.h>
 
 #include "common.cuh"
@@ -650,6 +651,239 @@ cudaError_t launch_tc2(cudaStream_t st, int M, int N, int K, const float* A, int
   return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, M, N, A, lda, B, ldb, C, ldc, aux, ldaux, K);
 }
 
+// =====================================================================================================================
+// The same SM-pair kernel with the RAW fp32 tiles brought in by TMA (cp.async.bulk.tensor) into a deep shared-memory ring:
+//   warp 9      one thread per CTA issues, per k-stage, two tensor-map loads completing on raw_full[rs] (24 KB):
+//                 A  box {32 k, 128 rows} fp32, SWIZZLE_128B  -- lands in exactly the XOR-swizzled row layout from which a
+//                    thread reads "its" row conflict-free (what row_transpose() built with 8 stores + a warp barrier);
+//                 B  box {64 n, 32 k} fp32, no swizzle        -- row-major, read back as float4 (k, 4 columns);
+//   warps 0-3   "transformers": raw tile -> registers -> {hi, lo} tf32 split -> tensor memory (A) / UMMA shared layout (B).
+// With the loads off the producer threads' registers, six stages (144 KB per SM) are in flight instead of three register
+// sets (72 KB): on the step's real operands (537 MB of activations streamed from HBM, not L2-resident like the 64 MB of the
+// stand-alone check) the producers' wait for global loads was what the MMA warp waited for.
+// =====================================================================================================================
+constexpr int kRawStages = 6;
+constexpr int kRawA = TM * TK * 4;             // 16384 B
+constexpr int kRawB = TK * TN2 * 4;            // 8192 B
+constexpr int kRawBytes = kRawA + kRawB;       // 24576 B per stage
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, float* __restrict__ C, int ldc,
+                const float* __restrict__ aux, int ldaux, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kStages = 4;
+  constexpr int kStageBytes = 2 * kTileMN2;            // b_hi | b_lo of this CTA's 64 columns
+  constexpr uint32_t kTmemCols = 512u;
+  uint8_t* const raw = smem;                                                  // [kRawStages][A raw 16 KB | B raw 8 KB], 1 KB aligned
+  uint8_t* const tiles = smem + kRawStages * kRawBytes;                       // [kStages][b_hi | b_lo]
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(tiles + kStages * kStageBytes);
+  uint64_t* const full = bars, *const empty = bars + kStages, *const tfull = bars + 2 * kStages, *const tempty = bars + 2 * kStages + 2;
+  uint64_t* const raw_full = bars + 2 * kStages + 4, *const raw_empty = raw_full + kRawStages;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kRawStages);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  const int nb0 = n0 + (int)rank * TN2;
+  const int nk = K / TK;
+  const int nchunks = nk / kStagesPerChunk;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full[s]), 8); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), 8); }
+    for (int r = 0; r < kRawStages; ++r) { mbar_init(smem_u32(&raw_full[r]), 1); mbar_init(smem_u32(&raw_empty[r]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== transformers =====================
+    for (int kt = 0; kt < nk; ++kt) {
+      const int rs = kt % kRawStages, s = kt % kStages;
+      mbar_wait(smem_u32(&raw_full[rs]), (kt / kRawStages) & 1);
+      const uint8_t* ra = raw + rs * kRawBytes;
+      const uint8_t* rb = ra + kRawA;
+      float4 va[8], vb[4];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) va[q] = *reinterpret_cast<const float4*>(ra + tid * 128 + ((q ^ (tid & 7)) << 4));     // row tid, SWIZZLE_128B
+      {
+        const int mq = tid & 15, kb = tid >> 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vb[i] = *reinterpret_cast<const float4*>(rb + (kb + 8 * i) * (TN2 * 4) + mq * 16);
+      }
+      if (kt >= kStages) mbar_wait(smem_u32(&empty[s]), ((kt / kStages) - 1) & 1);      // UMMA slot drained by the MMAs
+      uint8_t* st = tiles + s * kStageBytes;
+      st_a_tmem(va, tmem_d + 256u + (uint32_t)(s * 64), tmem_d + 256u + (uint32_t)(s * 64 + 32), tid);
+      st_b_half(vb, st, st + kTileMN2, tid);
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&raw_empty[rs]));                 // this warp has read its part of the raw stage (values are consumed above)
+        mbar_arrive_cluster(smem_u32(&full[s]), 0u);
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer: one thread of the LEADER CTA =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc2(true);
+      for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % kStages;
+        const int chunk = kt / kStagesPerChunk, b = chunk & 1;
+        const bool chunk_start = (kt % kStagesPerChunk) == 0;
+        if (chunk_start && chunk >= 2) {
+          mbar_wait(smem_u32(&tempty[b]), ((chunk >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(&full[s]), (kt / kStages) & 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_d + (uint32_t)(b * TN);
+        const uint32_t b_hi = smem_u32(tiles + s * kStageBytes), b_lo = b_hi + kTileMN2;
+        const uint32_t ta_hi = tmem_d + 256u + (uint32_t)(s * 64), ta_lo = ta_hi + 32u;
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint32_t boff = ks * 2 * kSbo2;
+          const uint64_t dbh = make_desc(b_hi + boff, kLboMN, kSbo2, 1), dbl = make_desc(b_lo + boff, kLboMN, kSbo2, 1);
+          const uint32_t first = (chunk_start && ks == 0) ? 0u : 1u;
+          umma2_tf32_ts(acc, ta_hi + 8u * ks, dbl, idesc, first);
+          umma2_tf32_ts(acc, ta_lo + 8u * ks, dbh, idesc, 1u);
+          umma2_tf32_ts(acc, ta_hi + 8u * ks, dbh, idesc, 1u);
+        }
+        umma2_commit(smem_u32(&empty[s]));
+        if ((kt % kStagesPerChunk) == kStagesPerChunk - 1) umma2_commit(smem_u32(&tfull[b]));
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== TMA issuer: one thread of EACH CTA (own rows of A, own half of B) =====================
+    if (lane == 0) {
+      for (int kt = 0; kt < nk; ++kt) {
+        const int rs = kt % kRawStages;
+        if (kt >= kRawStages) mbar_wait(smem_u32(&raw_empty[rs]), ((kt / kRawStages) - 1) & 1);
+        const uint32_t bar = smem_u32(&raw_full[rs]);
+        const uint32_t dst = smem_u32(raw + rs * kRawBytes);
+        mbar_arrive_expect_tx(bar, (uint32_t)kRawBytes);
+        tma_load_2d(dst, &mapA, kt * TK, m0, bar);                 // {k, row}
+        tma_load_2d(dst + kRawA, &mapB, nb0, kt * TK, bar);        // {column, k}
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue (both CTAs): own 128 rows x 128 columns =====================
+    const int q = warp - 4;
+    const int m = m0 + 32 * q + lane;
+    float acc[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int b = chunk & 1;
+      mbar_wait(smem_u32(&tfull[b]), (chunk >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * TN);
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[b]), 0u);
+    }
+    float* crow = C + (size_t)m * ldc + n0;
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      if (EPI == kEpiBiasRelu) {
+        const float4 bb = *reinterpret_cast<const float4*>(aux + n0 + j);
+        v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f); v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
+      } else if (EPI == kEpiReluMask) {
+        const float4 h = *reinterpret_cast<const float4*>(aux + (size_t)m * ldaux + n0 + j);
+        v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(crow + j) = v;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// fp32 matrix [rows][cols] with row stride ld (floats): boxes of box_cols x box_rows
+bool make_map_2d(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_cols, int box_rows, bool swizzle128) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int EPI>
+cudaError_t launch_tc3(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       const float* aux, int ldaux) {
+  constexpr int smem = kRawStages * kRawBytes + 4 * (2 * kTileMN2) + 512;     // raw ring | UMMA B stages | barriers
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc3_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  CUtensorMap mapA, mapB;
+  if (!make_map_2d(&mapA, A, M, K, lda, TK, TM, true) || !make_map_2d(&mapB, B, K, N, ldb, TN2, TK, false)) return cudaErrorNotSupported;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(M / TM, N / TN, 1);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc3_kernel<EPI>, mapA, mapB, M, N, C, ldc, aux, ldaux, K);
+}
+
 template <bool A_MN, bool B_MN, int EPI>
 cudaError_t launch_tc(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                       const float* aux, int ldaux, int splitk) {
@@ -673,10 +907,14 @@ cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const flo
   (void)ws;
   if (M % TM || N % TN || (K / splitk) % kChunkK) return cudaErrorInvalidValue;
   // NN products on SM pairs (cta_group::2) when the row tiles pair up; DQN_B200_GEMM_CG=1 keeps the single-CTA kernel
-  static const bool pairs = [] { const char* e = getenv("DQN_B200_GEMM_CG"); return !(e && atoi(e) == 1); }();
-  if (pairs && (M / TM) % 2 == 0) {
-    if (kind == kGemmNN_BiasRelu) return launch_tc2<kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
-    if (kind == kGemmNN_ReluMask) return launch_tc2<kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
+  // DQN_B200_GEMM_CG (experiment knob): 1 = single-CTA kernel, 2 = SM pairs with thread-loaded operands, default 3 = SM pairs
+  // with the raw tiles brought in by TMA
+  static const int cg = [] { const char* e = getenv("DQN_B200_GEMM_CG"); return e ? atoi(e) : 3; }();
+  if (cg >= 2 && (M / TM) % 2 == 0 && (kind == kGemmNN_BiasRelu || kind == kGemmNN_ReluMask)) {
+    const bool tma_ok = cg >= 3 && lda % 4 == 0 && ldb % 4 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0 && encode_tiled_fn() != nullptr;
+    if (kind == kGemmNN_BiasRelu)
+      return tma_ok ? launch_tc3<kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux) : launch_tc2<kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
+    return tma_ok ? launch_tc3<kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux) : launch_tc2<kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
   }
   switch (kind) {
     case kGemmNN_BiasRelu: return launch_tc<false, true, kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
