@@ -680,6 +680,10 @@ template <int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, float* __restrict__ C, int ldc,
                 const float* __restrict__ aux, int ldaux, int K) {
+  // PERSISTENT: cluster c of NC walks the 256 x 128 tiles t = c, c + NC, ... with t = (row pair) * (N / 128) + (column tile), so
+  // the clusters running at the same time share rows of A (L2 hits) and the k-stage / accumulator-chunk counters simply
+  // run on across tiles: while the epilogue warps drain the last chunk of a tile and store C, the TMA thread, the
+  // transformers and the MMA thread are already two chunks into the next tile (the other accumulator buffer).
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kStages = 4;
   constexpr int kStageBytes = 2 * kTileMN2;            // b_hi | b_lo of this CTA's 64 columns
@@ -693,10 +697,13 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
-  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
-  const int nb0 = n0 + (int)rank * TN2;
   const int nk = K / TK;
-  const int nchunks = nk / kStagesPerChunk;
+  const int cpt = nk / kStagesPerChunk;                // accumulator chunks per tile
+  const int ntn = N / TN;
+  const int ntiles = (M / (2 * TM)) * ntn;
+  const int nclusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const int my_tiles = cluster_id < ntiles ? (ntiles - cluster_id + nclusters - 1) / nclusters : 0;
+  const int total_kt = my_tiles * nk;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full[s]), 8); mbar_init(smem_u32(&empty[s]), 1); }
@@ -716,9 +723,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   if (warp < 4) {
     // ===================== transformers =====================
-    for (int kt = 0; kt < nk; ++kt) {
-      const int rs = kt % kRawStages, s = kt % kStages;
-      mbar_wait(smem_u32(&raw_full[rs]), (kt / kRawStages) & 1);
+    for (int g = 0; g < total_kt; ++g) {
+      const int rs = g % kRawStages, s = g % kStages;
+      mbar_wait(smem_u32(&raw_full[rs]), (g / kRawStages) & 1);
       const uint8_t* ra = raw + rs * kRawBytes;
       const uint8_t* rb = ra + kRawA;
       float4 va[8], vb[4];
@@ -729,7 +736,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) vb[i] = *reinterpret_cast<const float4*>(rb + (kb + 8 * i) * (TN2 * 4) + mq * 16);
       }
-      if (kt >= kStages) mbar_wait(smem_u32(&empty[s]), ((kt / kStages) - 1) & 1);      // UMMA slot drained by the MMAs
+      if (g >= kStages) mbar_wait(smem_u32(&empty[s]), ((g / kStages) - 1) & 1);      // UMMA slot drained by the MMAs
       uint8_t* st = tiles + s * kStageBytes;
       st_a_tmem(va, tmem_d + 256u + (uint32_t)(s * 64), tmem_d + 256u + (uint32_t)(s * 64 + 32), tid);
       st_b_half(vb, st, st + kTileMN2, tid);
@@ -745,15 +752,15 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // ===================== MMA issuer: one thread of the LEADER CTA =====================
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = make_idesc2(true);
-      for (int kt = 0; kt < nk; ++kt) {
-        const int s = kt % kStages;
-        const int chunk = kt / kStagesPerChunk, b = chunk & 1;
-        const bool chunk_start = (kt % kStagesPerChunk) == 0;
+      for (int g = 0; g < total_kt; ++g) {
+        const int s = g % kStages;
+        const int chunk = g / kStagesPerChunk, b = chunk & 1;
+        const bool chunk_start = (g % kStagesPerChunk) == 0;
         if (chunk_start && chunk >= 2) {
           mbar_wait(smem_u32(&tempty[b]), ((chunk >> 1) - 1) & 1);
           tc_fence_after();
         }
-        mbar_wait(smem_u32(&full[s]), (kt / kStages) & 1);
+        mbar_wait(smem_u32(&full[s]), (g / kStages) & 1);
         tc_fence_after();
         const uint32_t acc = tmem_d + (uint32_t)(b * TN);
         const uint32_t b_hi = smem_u32(tiles + s * kStageBytes), b_lo = b_hi + kTileMN2;
@@ -768,58 +775,67 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           umma2_tf32_ts(acc, ta_hi + 8u * ks, dbh, idesc, 1u);
         }
         umma2_commit(smem_u32(&empty[s]));
-        if ((kt % kStagesPerChunk) == kStagesPerChunk - 1) umma2_commit(smem_u32(&tfull[b]));
+        if ((g % kStagesPerChunk) == kStagesPerChunk - 1) umma2_commit(smem_u32(&tfull[b]));
       }
     }
   } else if (warp == 9) {
     // ===================== TMA issuer: one thread of EACH CTA (own rows of A, own half of B) =====================
     if (lane == 0) {
-      for (int kt = 0; kt < nk; ++kt) {
-        const int rs = kt % kRawStages;
-        if (kt >= kRawStages) mbar_wait(smem_u32(&raw_empty[rs]), ((kt / kRawStages) - 1) & 1);
-        const uint32_t bar = smem_u32(&raw_full[rs]);
-        const uint32_t dst = smem_u32(raw + rs * kRawBytes);
-        mbar_arrive_expect_tx(bar, (uint32_t)kRawBytes);
-        tma_load_2d(dst, &mapA, kt * TK, m0, bar);                 // {k, row}
-        tma_load_2d(dst + kRawA, &mapB, nb0, kt * TK, bar);        // {column, k}
+      int g = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int t = cluster_id + i * nclusters;
+        const int m0 = ((t / ntn) * 2 + (int)rank) * TM, nb0 = (t % ntn) * TN + (int)rank * TN2;
+        for (int kt = 0; kt < nk; ++kt, ++g) {
+          const int rs = g % kRawStages;
+          if (g >= kRawStages) mbar_wait(smem_u32(&raw_empty[rs]), ((g / kRawStages) - 1) & 1);
+          const uint32_t bar = smem_u32(&raw_full[rs]);
+          const uint32_t dst = smem_u32(raw + rs * kRawBytes);
+          mbar_arrive_expect_tx(bar, (uint32_t)kRawBytes);
+          tma_load_2d(dst, &mapA, kt * TK, m0, bar);                 // {k, row}
+          tma_load_2d(dst + kRawA, &mapB, nb0, kt * TK, bar);        // {column, k}
+        }
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue (both CTAs): own 128 rows x 128 columns =====================
+    // ===================== epilogue (both CTAs): own 128 rows x 128 columns of every tile =====================
     const int q = warp - 4;
-    const int m = m0 + 32 * q + lane;
-    float acc[TN];
+    int chunk = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int t = cluster_id + i * nclusters;
+      const int m = ((t / ntn) * 2 + (int)rank) * TM + 32 * q + lane, n0 = (t % ntn) * TN;
+      float acc[TN];
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[j] = 0.f;
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-      const int b = chunk & 1;
-      mbar_wait(smem_u32(&tfull[b]), (chunk >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tbase = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * TN);
+      for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+      for (int cc = 0; cc < cpt; ++cc, ++chunk) {
+        const int b = chunk & 1;
+        mbar_wait(smem_u32(&tfull[b]), (chunk >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tbase = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * TN);
 #pragma unroll
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tbase + (uint32_t)c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[b]), 0u);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[b]), 0u);
-    }
-    float* crow = C + (size_t)m * ldc + n0;
+      float* crow = C + (size_t)m * ldc + n0;
 #pragma unroll
-    for (int j = 0; j < TN; j += 4) {
-      float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-      if (EPI == kEpiBiasRelu) {
-        const float4 bb = *reinterpret_cast<const float4*>(aux + n0 + j);
-        v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f); v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
-      } else if (EPI == kEpiReluMask) {
-        const float4 h = *reinterpret_cast<const float4*>(aux + (size_t)m * ldaux + n0 + j);
-        v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+      for (int j = 0; j < TN; j += 4) {
+        float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        if (EPI == kEpiBiasRelu) {
+          const float4 bb = *reinterpret_cast<const float4*>(aux + n0 + j);
+          v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f); v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
+        } else if (EPI == kEpiReluMask) {
+          const float4 h = *reinterpret_cast<const float4*>(aux + (size_t)m * ldaux + n0 + j);
+          v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(crow + j) = v;
       }
-      *reinterpret_cast<float4*>(crow + j) = v;
     }
   }
 
@@ -869,8 +885,16 @@ cudaError_t launch_tc3(cudaStream_t st, int M, int N, int K, const float* A, int
   }
   CUtensorMap mapA, mapB;
   if (!make_map_2d(&mapA, A, M, K, lda, TK, TM, true) || !make_map_2d(&mapB, B, K, N, ldb, TN2, TK, false)) return cudaErrorNotSupported;
+  static int sm_pairs = 0;
+  if (!sm_pairs) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sm_pairs = sms / 2 > 0 ? sms / 2 : 1;
+  }
+  const int ntiles = (M / (2 * TM)) * (N / TN);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(M / TM, N / TN, 1);
+  cfg.gridDim = dim3(2 * (ntiles < sm_pairs ? ntiles : sm_pairs), 1, 1);      // persistent: one cluster per SM pair
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
