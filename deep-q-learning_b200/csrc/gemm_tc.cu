@@ -908,6 +908,223 @@ cudaError_t launch_tc3(cudaStream_t st, int M, int N, int K, const float* A, int
   return cudaLaunchKernelEx(&cfg, gemm_tc3_kernel<EPI>, mapA, mapB, M, N, C, ldc, aux, ldaux, K);
 }
 
+// =====================================================================================================================
+// TN product (dW2 = h1^T . dh2: both operands MN-major, reduction over the batch rows, split-K) on SM pairs, persistent,
+// TMA-fed.  Work item = (256 x 128 tile, k-split); item w = cluster + i * clusters, split-major (w = z * tiles + t), so the
+// clusters running together cover all tiles of the same k rows and share them through L2.  A's own 128 columns of h1 and half
+// of dh2's 128 columns go raw into a 3-stage ring by TMA ({128 | 64 columns, 32 rows} boxes, row-major); the transformers
+// split them into the MN-major SWIZZLE_128B_BASE32B layouts (hi, lo); the leader issues SS-form tcgen05.mma.cta_group::2.
+// =====================================================================================================================
+constexpr int kRaw4Stages = 3, kUmma4Stages = 3;
+constexpr int kRaw4A = TK * TM * 4;                       // 16384 B: [32 k][128 m]
+constexpr int kRaw4Bytes = kRaw4A + kRawB;                 // + [32 k][64 n] = 24576 B
+constexpr int kStage4Bytes = 2 * kTileMN + 2 * kTileMN2;   // a_hi | a_lo | b_hi | b_lo = 49152 B
+
+__device__ __forceinline__ void umma2_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+      "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, float* __restrict__ C, int ldc,
+                int k_per_split, int splitk) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t kTmemCols = 256u;                 // two accumulators
+  uint8_t* const raw = smem;                                                  // [3][A raw 16 KB | B raw 8 KB]
+  uint8_t* const tiles = smem + kRaw4Stages * kRaw4Bytes;                     // [3][a_hi | a_lo | b_hi | b_lo]
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(tiles + kUmma4Stages * kStage4Bytes);
+  uint64_t* const full = bars, *const empty = bars + kUmma4Stages, *const tfull = bars + 2 * kUmma4Stages, *const tempty = tfull + 2;
+  uint64_t* const raw_full = tempty + 2, *const raw_empty = raw_full + kRaw4Stages;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kRaw4Stages);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nk = k_per_split / TK;
+  const int cpi = nk / kStagesPerChunk;                // accumulator chunks per work item
+  const int ntn = N / TN;
+  const int ntiles = (M / (2 * TM)) * ntn;
+  const int nitems = ntiles * splitk;
+  const int nclusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const int my_items = cluster_id < nitems ? (nitems - cluster_id + nclusters - 1) / nclusters : 0;
+  const int total_kt = my_items * nk;
+
+  if (tid == 0) {
+    for (int s = 0; s < kUmma4Stages; ++s) { mbar_init(smem_u32(&full[s]), 8); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), 8); }
+    for (int r = 0; r < kRaw4Stages; ++r) { mbar_init(smem_u32(&raw_full[r]), 1); mbar_init(smem_u32(&raw_empty[r]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== transformers =====================
+    for (int g = 0; g < total_kt; ++g) {
+      const int rs = g % kRaw4Stages, s = g % kUmma4Stages;
+      mbar_wait(smem_u32(&raw_full[rs]), (g / kRaw4Stages) & 1);
+      const uint8_t* ra = raw + rs * kRaw4Bytes;
+      const uint8_t* rb = ra + kRaw4A;
+      float4 va[8], vb[4];
+      {
+        const int mq = tid & 31, kb = tid >> 5;          // the (column, k) ownership st_tile<true> expects
+#pragma unroll
+        for (int i = 0; i < 8; ++i) va[i] = *reinterpret_cast<const float4*>(ra + (kb + 4 * i) * (TM * 4) + mq * 16);
+      }
+      {
+        const int mq = tid & 15, kb = tid >> 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vb[i] = *reinterpret_cast<const float4*>(rb + (kb + 8 * i) * (TN2 * 4) + mq * 16);
+      }
+      if (g >= kUmma4Stages) mbar_wait(smem_u32(&empty[s]), ((g / kUmma4Stages) - 1) & 1);
+      uint8_t* st = tiles + s * kStage4Bytes;
+      st_tile<true>(va, st, st + kTileMN, tid);
+      st_b_half(vb, st + 2 * kTileMN, st + 2 * kTileMN + kTileMN2, tid);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&raw_empty[rs]));
+        mbar_arrive_cluster(smem_u32(&full[s]), 0u);
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer: one thread of the LEADER CTA =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc2(true) | (1u << 15);      // A is MN-major too
+      for (int g = 0; g < total_kt; ++g) {
+        const int s = g % kUmma4Stages;
+        const int chunk = g / kStagesPerChunk, b = chunk & 1;
+        const bool chunk_start = (g % kStagesPerChunk) == 0;
+        if (chunk_start && chunk >= 2) {
+          mbar_wait(smem_u32(&tempty[b]), ((chunk >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(&full[s]), (g / kUmma4Stages) & 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_d + (uint32_t)(b * TN);
+        const uint32_t a_hi = smem_u32(tiles + s * kStage4Bytes), a_lo = a_hi + kTileMN;
+        const uint32_t b_hi = a_hi + 2 * kTileMN, b_lo = b_hi + kTileMN2;
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint32_t aoff = ks * 2 * kSboMN, boff = ks * 2 * kSbo2;
+          const uint64_t dah = make_desc(a_hi + aoff, kLboMN, kSboMN, 1), dal = make_desc(a_lo + aoff, kLboMN, kSboMN, 1);
+          const uint64_t dbh = make_desc(b_hi + boff, kLboMN, kSbo2, 1), dbl = make_desc(b_lo + boff, kLboMN, kSbo2, 1);
+          const uint32_t first = (chunk_start && ks == 0) ? 0u : 1u;
+          umma2_tf32_ss(acc, dah, dbl, idesc, first);
+          umma2_tf32_ss(acc, dal, dbh, idesc, 1u);
+          umma2_tf32_ss(acc, dah, dbh, idesc, 1u);
+        }
+        umma2_commit(smem_u32(&empty[s]));
+        if ((g % kStagesPerChunk) == kStagesPerChunk - 1) umma2_commit(smem_u32(&tfull[b]));
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== TMA issuer: one thread of each CTA =====================
+    if (lane == 0) {
+      int g = 0;
+      for (int i = 0; i < my_items; ++i) {
+        const int w = cluster_id + i * nclusters;
+        const int z = w / ntiles, t = w - z * ntiles;
+        const int m0 = ((t / ntn) * 2 + (int)rank) * TM, nb0 = (t % ntn) * TN + (int)rank * TN2;
+        const int kbeg = z * k_per_split;
+        for (int kt = 0; kt < nk; ++kt, ++g) {
+          const int rs = g % kRaw4Stages;
+          if (g >= kRaw4Stages) mbar_wait(smem_u32(&raw_empty[rs]), ((g / kRaw4Stages) - 1) & 1);
+          const uint32_t bar = smem_u32(&raw_full[rs]);
+          const uint32_t dst = smem_u32(raw + rs * kRaw4Bytes);
+          mbar_arrive_expect_tx(bar, (uint32_t)kRaw4Bytes);
+          tma_load_2d(dst, &mapA, m0, kbeg + kt * TK, bar);              // {column of h1, batch row}
+          tma_load_2d(dst + kRaw4A, &mapB, nb0, kbeg + kt * TK, bar);    // {column of dh2, batch row}
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: split-K partial of this CTA's 128 x 128 block =====================
+    const int q = warp - 4;
+    int chunk = 0;
+    for (int i = 0; i < my_items; ++i) {
+      const int w = cluster_id + i * nclusters;
+      const int z = w / ntiles, t = w - z * ntiles;
+      const int m = ((t / ntn) * 2 + (int)rank) * TM + 32 * q + lane, n0 = (t % ntn) * TN;
+      float acc[TN];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[j] = 0.f;
+      for (int cc = 0; cc < cpi; ++cc, ++chunk) {
+        const int b = chunk & 1;
+        mbar_wait(smem_u32(&tfull[b]), (chunk >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tbase = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * TN);
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[b]), 0u);
+      }
+      float* crow = C + (size_t)z * M * ldc + (size_t)m * ldc + n0;
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+cudaError_t launch_tc4(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int splitk) {
+  constexpr int smem = kRaw4Stages * kRaw4Bytes + kUmma4Stages * kStage4Bytes + 512;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  CUtensorMap mapA, mapB;     // A = h1 [K rows][M columns], B = dh2 [K rows][N columns]
+  if (!make_map_2d(&mapA, A, K, M, lda, TM, TK, false) || !make_map_2d(&mapB, B, K, N, ldb, TN2, TK, false)) return cudaErrorNotSupported;
+  static int sm_pairs = 0;
+  if (!sm_pairs) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sm_pairs = sms / 2 > 0 ? sms / 2 : 1;
+  }
+  const int nitems = (M / (2 * TM)) * (N / TN) * splitk;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (nitems < sm_pairs ? nitems : sm_pairs), 1, 1);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc4_kernel, mapA, mapB, M, N, C, ldc, K / splitk, splitk);
+}
+
 template <bool A_MN, bool B_MN, int EPI>
 cudaError_t launch_tc(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                       const float* aux, int ldaux, int splitk) {
@@ -940,6 +1157,9 @@ cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const flo
       return tma_ok ? launch_tc3<kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux) : launch_tc2<kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
     return tma_ok ? launch_tc3<kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux) : launch_tc2<kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
   }
+  if (cg >= 3 && kind == kGemmTN_SplitK && (M / TM) % 2 == 0 && lda % 4 == 0 && ldb % 4 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0 &&
+      encode_tiled_fn() != nullptr)
+    return launch_tc4(st, M, N, K, A, lda, B, ldb, C, ldc, splitk);
   switch (kind) {
     case kGemmNN_BiasRelu: return launch_tc<false, true, kEpiBiasRelu>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);
     case kGemmNT_ReluMask: return launch_tc<false, false, kEpiReluMask>(st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, 1);

@@ -521,7 +521,12 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
   }
   {   // dW2 = H1s^T . dH2  (reduction over the batch rows): split-K partials, fixed-order reduce
     int splitk = 1;
-    while (splitk < 16 && (H1n / BM) * (H2n / BN) * splitk < 296 && (B / (splitk * 2)) % BK == 0 && B / (splitk * 2) >= 256) splitk *= 2;
+    if (gemm_mode == kGemmModeTC3xTF32) {
+      // persistent SM-pair kernel: many (tile, split) work items per cluster keep the last round full; a split is >= 256 rows
+      while (splitk < 16 && (B / (splitk * 2)) % 128 == 0 && B / (splitk * 2) >= 256) splitk *= 2;
+    } else {
+      while (splitk < 16 && (H1n / BM) * (H2n / BN) * splitk < 296 && (B / (splitk * 2)) % BK == 0 && B / (splitk * 2) >= 256) splitk *= 2;
+    }
     LBCHK(lb_gemm(st, gemm_mode, kGemmTN_SplitK, H1n, H2n, B, ws.H1, H1n, ws.dH2, H2n, ws.gemmpart, H2n, nullptr, 0, splitk, ws));
     const long long n = (long long)H1n * H2n;
     LBCHK(launch_reduce_partials(st, ws.gemmpart, ws.grads + offW2, n, splitk, n));

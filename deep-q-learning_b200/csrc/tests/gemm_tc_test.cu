@@ -94,6 +94,9 @@ int main() {
   bad += run(kGemmNN_BiasRelu, 16384, 1024, 1024, 1, true);
   bad += run(kGemmNT_ReluMask, 16384, 1024, 1024, 1, true);
   bad += run(kGemmTN_SplitK, 1024, 1024, 16384, 4, true);
+  bad += run(kGemmTN_SplitK, 1024, 1024, 65536, 16, true);
+  bad += run(kGemmTN_SplitK, 1024, 1024, 8192, 16, true);
+  bad += run(kGemmNN_BiasRelu, 131072, 1024, 1024, 1, true);
   printf(bad ? "FAILED\n" : "ALL OK\n");
   return bad;
 }
