@@ -45,15 +45,28 @@ lb_layer1_kernel(const float* __restrict__ s, const float* __restrict__ s2, cons
   const int j4 = threadIdx.x;
   if (4 * j4 >= ncol) return;
   const float4 bias = reinterpret_cast<const float4*>(w1s)[D * 256 + j4];
-  for (int r = blockIdx.y; r < B; r += gridDim.y) {
-    float4 acc = bias;
+  // four rows per pass: every 16-byte weight load from shared memory feeds four rows (one row per pass made the kernel
+  // LSU-bound at 2.5 TB/s of what is a pure 805 MB write)
+  constexpr int RP = 4;
+  for (int r0 = blockIdx.y * RP; r0 < B; r0 += gridDim.y * RP) {
+    float4 acc[RP];
+#pragma unroll
+    for (int i = 0; i < RP; ++i) acc[i] = bias;
     for (int d = 0; d < D; ++d) {
-      const float xv = __ldg(x + (size_t)r * D + d);
       const float4 w = reinterpret_cast<const float4*>(w1s)[d * 256 + j4];
-      acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y); acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+#pragma unroll
+      for (int i = 0; i < RP; ++i) {
+        const float xv = r0 + i < B ? __ldg(x + (size_t)(r0 + i) * D + d) : 0.f;
+        acc[i].x = fmaf(xv, w.x, acc[i].x); acc[i].y = fmaf(xv, w.y, acc[i].y); acc[i].z = fmaf(xv, w.z, acc[i].z); acc[i].w = fmaf(xv, w.w, acc[i].w);
+      }
     }
-    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-    *reinterpret_cast<float4*>(H1 + ((size_t)pass * B + r) * H1n + col0 + 4 * j4) = acc;
+#pragma unroll
+    for (int i = 0; i < RP; ++i) {
+      if (r0 + i >= B) break;
+      float4 v = acc[i];
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      *reinterpret_cast<float4*>(H1 + ((size_t)pass * B + r0 + i) * H1n + col0 + 4 * j4) = v;
+    }
   }
 }
 
@@ -215,7 +228,7 @@ cudaError_t launch_reduce_partials(cudaStream_t st, const float* part, float* ou
 // ------------------------------------------------------------------------------------------------
 // head: Q = V + Adv - mean(Adv)  (dddqn.py:29-31).  One warp per row, rows [0,3B).
 // ------------------------------------------------------------------------------------------------
-constexpr int kHeadRows = 4;     // rows per warp: every head-weight load is reused for four activation rows
+constexpr int kHeadRows = 4;     // rows per warp: every head-weight load is reused for four activation rows (eight measured slower: 128 registers)
 
 __global__ void __launch_bounds__(256)
 lb_head_kernel(const float* __restrict__ H2, const float* __restrict__ theta, const float* __restrict__ theta_t,
