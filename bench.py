@@ -917,7 +917,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
                     help="dp workload: gradient all-reduce by the library's own peer-memory kernel (p2p) or by NCCL")
-    ap.add_argument("--step-kernel", default="auto", choices=["auto", "cta", "cluster"],
+    ap.add_argument("--step-kernel", default="auto", choices=["auto", "cta", "cluster", "cta_tc"],
                     help="train-step kernel of the single/population workloads: one CTA per agent, or one agent over a 4-CTA cluster "
                          "(auto = cluster while 4 * agents <= SMs)")
     args = ap.parse_args()

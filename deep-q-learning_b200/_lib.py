@@ -14,8 +14,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dqn_b200.h")
 DQN_OPT_ADAM, DQN_OPT_ADAMW = 0, 1
 DQN_PARAMS_ONLINE, DQN_PARAMS_TARGET = 0, 1
 LOSS_KINDS = {"huber": 0, "l2": 1, "mse": 1}     # "huber" = the reference (q_learning_functions.py:36); "l2"/"mse" = 0.5 e^2, an extension
-DQN_STEP_AUTO, DQN_STEP_CTA, DQN_STEP_CLUSTER = 0, 1, 2
-STEP_KERNELS = {"auto": DQN_STEP_AUTO, "cta": DQN_STEP_CTA, "cluster": DQN_STEP_CLUSTER}
+DQN_STEP_AUTO, DQN_STEP_CTA, DQN_STEP_CLUSTER, DQN_STEP_CTA_TC = 0, 1, 2, 3
+STEP_KERNELS = {"auto": DQN_STEP_AUTO, "cta": DQN_STEP_CTA, "cluster": DQN_STEP_CLUSTER, "cta_tc": DQN_STEP_CTA_TC}
 DQN_MAX_BATCH, DQN_MAX_OBS_DIM, DQN_MAX_ACTIONS = 1024, 16, 7
 LOSS_RING = 4096
 

@@ -369,7 +369,7 @@ DQN_API int dqn_set_counters(dqn_handle* h, int32_t agent, const dqn_counters* i
 DQN_API int dqn_set_step_kernel(dqn_handle* h, int32_t step_kernel) {
   if (!h) return fail(DQN_E_INVALID, "handle is NULL");
   if (h->session_active) if (int rc = session_stop(h)) return rc;
-  if (step_kernel < DQN_STEP_AUTO || step_kernel > DQN_STEP_CLUSTER) return fail(DQN_E_INVALID, "dqn_set_step_kernel: unknown kernel id");
+  if (step_kernel < DQN_STEP_AUTO || step_kernel > DQN_STEP_CTA_TC) return fail(DQN_E_INVALID, "dqn_set_step_kernel: unknown kernel id");
   h->step_kernel = step_kernel;
   return DQN_OK;
 }
@@ -553,7 +553,7 @@ int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, d
   const bool cluster = uses_cluster(h, n_sel);
   if (ist && !cluster) return fail(DQN_E_INVALID, "internal: inline store needs the cluster kernel");
   if (cluster) CU(launch_train_cluster(h->stream, ta, ist));
-  else CU(launch_train_fused(h->stream, ta));
+  else CU(launch_train_fused(h->stream, ta, h->step_kernel != DQN_STEP_CTA));   // AUTO / CTA_TC: tensor-core form
   if (ist) h->hctl[b].ring_counter += ist->n;
   for (int ag = b; ag < e; ++ag) {
     if (gate && !h->hep[ag].pending_train) continue;      // the device gate is closed for this agent: it does not step

@@ -65,9 +65,10 @@ cudaError_t launch_replay_gather(cudaStream_t st, const uint32_t* ring, const Di
                                  uint64_t seed, int agent, long long step, long long size, long long batch,
                                  float* s, long long* a, float* r, float* s2, uint8_t* done);
 
-size_t train_fused_smem_bytes(const Dims& d);
-cudaError_t train_fused_prepare(const Dims& d);   // cudaFuncSetAttribute for the instantiation
-cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args);
+// tc = the tensor-core form (tcgen05 3xTF32 for the layer-2 products), else fp32 FFMA throughout
+size_t train_fused_smem_bytes(const Dims& d, bool tc);
+cudaError_t train_fused_prepare(const Dims& d);   // cudaFuncSetAttribute for both instantiations
+cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args, bool tc);
 // the same step with one agent spread over a 4-CTA thread-block cluster (train_cluster.cu)
 size_t train_cluster_smem_bytes(const Dims& d);
 cudaError_t train_cluster_prepare(const Dims& d);

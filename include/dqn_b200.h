@@ -53,10 +53,11 @@ enum { DQN_PARAMS_ONLINE = 0, DQN_PARAMS_TARGET = 1 };
  * (q_learning_functions.py:36) and the default; L2 = optax.l2_loss = 0.5 e^2 in its place is an extension the reference
  * does not have: same reduction, gradient e / B instead of clip(e, -1, 1) / B. */
 enum { DQN_LOSS_HUBER = 0, DQN_LOSS_L2 = 1 };
-/* Train-step kernel: one CTA per agent (throughput form, used for populations), or one agent spread over a
- * 4-CTA thread-block cluster (latency form, used for a single agent).  AUTO = cluster while 4*agents <= SMs.
- * Both compute the same update; summation orders differ (results agree to fp32 round-off). */
-enum { DQN_STEP_AUTO = 0, DQN_STEP_CTA = 1, DQN_STEP_CLUSTER = 2 };
+/* Train-step kernel: one CTA per agent (throughput form, used for populations) -- CTA = fp32 FFMA throughout, CTA_TC = the
+ * layer-2 products (80 % of the flops) on the tensor cores as error-compensated 3xTF32 (tcgen05) -- or one agent spread
+ * over a 4-CTA thread-block cluster (latency form, used for a single agent).  AUTO = cluster while 4*agents <= SMs, else
+ * CTA_TC.  All compute the same update; summation orders differ (results agree to fp32 round-off). */
+enum { DQN_STEP_AUTO = 0, DQN_STEP_CTA = 1, DQN_STEP_CLUSTER = 2, DQN_STEP_CTA_TC = 3 };
 
 /* Construction-time configuration == the part of `Agent.__init__` (q_agent.py:61-118) that shapes
  * the hot path.  `network` becomes (obs_dim, hidden1, hidden2, num_actions) -- the dueling MLP of
@@ -79,7 +80,7 @@ typedef struct dqn_config {
   uint64_t seed;         /* Philox key for minibatch indices */
   int32_t agent_id_base; /* global id of local agent 0: the Philox counter uses (agent_id_base + agent), so a
                           *   sharded population draws the same indices as the unsharded one */
-  int32_t step_kernel;   /* DQN_STEP_AUTO / DQN_STEP_CTA / DQN_STEP_CLUSTER: which train-step kernel (see the enum) */
+  int32_t step_kernel;   /* DQN_STEP_AUTO / _CTA / _CLUSTER / _CTA_TC: which train-step kernel (see the enum) */
   void* stream;          /* cudaStream_t to enqueue on (NULL = default stream) */
   void* arena;           /* optional caller-allocated device memory (e.g. a torch tensor's  */
   uint64_t arena_bytes;  /*   data_ptr()); NULL => the library allocates dqn_arena_bytes() itself */

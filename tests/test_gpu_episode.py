@@ -16,7 +16,7 @@ from oracle.episode_oracle import EpisodeOracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["cta", "cluster"])
+@pytest.fixture(autouse=True, params=["cta", "cluster", "cta_tc"])
 def step_kernel(request, monkeypatch):
     monkeypatch.setenv("DQN_B200_STEP_KERNEL", request.param)
     return request.param

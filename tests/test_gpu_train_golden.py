@@ -21,7 +21,7 @@ CASES = ["lunar_lander", "sweep", "gamma0_terminal", "d8_b70"]
 NU_RTOL = 2e-5
 
 
-@pytest.fixture(autouse=True, params=["cta", "cluster"])
+@pytest.fixture(autouse=True, params=["cta", "cluster", "cta_tc"])
 def step_kernel(request, monkeypatch):
     monkeypatch.setenv("DQN_B200_STEP_KERNEL", request.param)
     return request.param

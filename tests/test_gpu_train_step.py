@@ -15,7 +15,7 @@ from oracle.replay_oracle import synthetic_transitions
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["cta", "cluster"])
+@pytest.fixture(autouse=True, params=["cta", "cluster", "cta_tc"])
 def step_kernel(request, monkeypatch):
     """Every test of this module runs against both train-step kernels: one CTA per agent (train_fused.cu) and
     one agent over a 4-CTA cluster (train_cluster.cu)."""
