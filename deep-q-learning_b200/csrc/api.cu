@@ -163,6 +163,7 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   // zero parameters / moments / rings / losses (ReplayBuffer.__init__ zero-fills, replay_buffer.py:26-30)
   e = cudaMemsetAsync(h->arena, 0, h->cv.stage, h->stream);
   if (e == cudaSuccess) e = train_fused_prepare(d);
+  if (e == cudaSuccess) e = train_tc_prepare(d);
   if (e == cudaSuccess) e = train_cluster_prepare(d);
   h->step_kernel = cfg->step_kernel;
   {
@@ -553,7 +554,8 @@ int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, d
   const bool cluster = uses_cluster(h, n_sel);
   if (ist && !cluster) return fail(DQN_E_INVALID, "internal: inline store needs the cluster kernel");
   if (cluster) CU(launch_train_cluster(h->stream, ta, ist));
-  else CU(launch_train_fused(h->stream, ta, h->step_kernel != DQN_STEP_CTA));   // AUTO / CTA_TC: tensor-core form
+  else if (h->step_kernel == DQN_STEP_CTA) CU(launch_train_fused(h->stream, ta));
+  else CU(launch_train_tc(h->stream, ta));                                     // AUTO / CTA_TC: tensor-core form
   if (ist) h->hctl[b].ring_counter += ist->n;
   for (int ag = b; ag < e; ++ag) {
     if (gate && !h->hep[ag].pending_train) continue;      // the device gate is closed for this agent: it does not step

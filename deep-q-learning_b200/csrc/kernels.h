@@ -65,10 +65,13 @@ cudaError_t launch_replay_gather(cudaStream_t st, const uint32_t* ring, const Di
                                  uint64_t seed, int agent, long long step, long long size, long long batch,
                                  float* s, long long* a, float* r, float* s2, uint8_t* done);
 
-// tc = the tensor-core form (tcgen05 3xTF32 for the layer-2 products), else fp32 FFMA throughout
-size_t train_fused_smem_bytes(const Dims& d, bool tc);
-cudaError_t train_fused_prepare(const Dims& d);   // cudaFuncSetAttribute for both instantiations
-cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args, bool tc);
+size_t train_fused_smem_bytes(const Dims& d);
+cudaError_t train_fused_prepare(const Dims& d);   // cudaFuncSetAttribute for the instantiation
+cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args);
+// the same one-CTA-per-agent step with the layer-2 products on the tensor cores (train_fused_tc.cu: tcgen05 3xTF32, 512 threads)
+size_t train_tc_smem_bytes(const Dims& d);
+cudaError_t train_tc_prepare(const Dims& d);
+cudaError_t launch_train_tc(cudaStream_t st, const TrainArgs& args);
 // the same step with one agent spread over a 4-CTA thread-block cluster (train_cluster.cu)
 size_t train_cluster_smem_bytes(const Dims& d);
 cudaError_t train_cluster_prepare(const Dims& d);

@@ -63,7 +63,15 @@ struct Bufs {
 // X and Meta hold the tile's rows (rows >= B zero-filled).  Every thread of the 256-thread CTA calls this; it starts and
 // ends without a barrier (the caller orders its own writes before, and reads of G after).  Returns, in threads 0..15, the
 // sum of the tile's per-sample losses (not yet divided by B).
-template <int A>
+// NB = 0: the CTA has exactly 256 threads (barrier 0).  NB = 256: the first 256 threads of a larger CTA call this and meet on named
+// barrier 1 (train_fused_tc.cu).
+template <int NB>
+__device__ __forceinline__ void tile_sync() {
+  if constexpr (NB == 0) __syncthreads();
+  else asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");
+}
+
+template <int A, int NB = 0>
 __device__ __forceinline__ float step(const Bufs& bf, int row_base, int B, float fB, float gamma, bool l2loss, const TapsDev& taps) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int D = bf.D;
@@ -92,14 +100,14 @@ __device__ __forceinline__ float step(const Bufs& bf, int row_base, int B, float
     op_tile4<2>(X + xcol, XS, Wsel + 2 * ct, kH1, D, acc);
     op_store_relu<2>(H1 + (2 * ct) * HS + 4 * rt, HS, acc);
   }
-  __syncthreads();
+  tile_sync<NB>();
   if (fwd) {   // layer 2: 4 rows x 4 units
     u64 acc[4][2];
     op_init<4>(Wsel + bf.pW2 + kH1 * WS2 + 4 * ct, acc);
     op_tile4<4>(H1 + 4 * rt, HS, Wsel + bf.pW2 + 4 * ct, WS2, kH1, acc);
     op_store_relu<4>(H2 + (4 * ct) * HS + 4 * rt, HS, acc);
   }
-  __syncthreads();
+  tile_sync<NB>();
   if (t < 4 * FR) {   // head: split-K over 4 thread groups, forward row fr = t % 48
     const int fr = t % FR, part = t / FR;
     const float* wh = (fr < 2 * R ? W : Wt) + bf.pWh;
@@ -122,7 +130,7 @@ __device__ __forceinline__ float step(const Bufs& bf, int row_base, int B, float
 #pragma unroll
     for (int c = 0; c <= A; ++c) Scr[(part * HC + c) * FR + fr] = acc[c];
   }
-  __syncthreads();
+  tile_sync<NB>();
   if (t < R) {   // targets / Huber / d(head) for this CTA's 16 samples (half of warp 0)
     const int i = t;
     float hd[3][1 + A];
@@ -199,7 +207,7 @@ __device__ __forceinline__ float step(const Bufs& bf, int row_base, int B, float
       if (taps.max_actions) taps.max_actions[grow] = astar;
     }
   }
-  __syncthreads();
+  tile_sync<NB>();
 
   // ---- backward ----
   {  // dh2 (16 rows x 64 units): thread = row r, 4 units
@@ -231,7 +239,7 @@ __device__ __forceinline__ float step(const Bufs& bf, int row_base, int B, float
       for (int jj = 0; jj < 4; ++jj) G[bf.pW2 + kH1 * WS2 + 4 * jt + jj] += o[jj];
     }
   }
-  __syncthreads();
+  tile_sync<NB>();
   {  // dW2: warp = 16 x 16 block, reduction over this CTA's 16 rows
     const int mi = lane & 7, ni = lane >> 3, k0 = 16 * (warp & 1) + mi, j0 = 16 * (warp >> 1) + ni;
     const float* ap[2] = {H1 + k0 * HS, H1 + (k0 + 8) * HS};
@@ -268,7 +276,7 @@ __device__ __forceinline__ float step(const Bufs& bf, int row_base, int B, float
     Dh1T[kk * RS + r] = H1[kk * HS + r] > 0.f ? acc[0][0] : 0.f;
     Dh1T[(kk + 16) * RS + r] = H1[(kk + 16) * HS + r] > 0.f ? acc[0][1] : 0.f;
   }
-  __syncthreads();
+  tile_sync<NB>();
   {  // [dW1; db1]
     const int hcol = t & 31, mt = t >> 5;
     const int d1 = mt + 8 <= D ? mt + 8 : D, d2 = mt + 16 <= D ? mt + 16 : D;

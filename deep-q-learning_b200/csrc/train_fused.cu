@@ -21,17 +21,6 @@
 //       bank groups.  Forward GEMMs run in outer-product form on these (both operands contiguous
 //       along the output tile), weight-gradient GEMMs in dot form (both operands contiguous along
 //       the reduction = batch row), so no explicit transposes are needed.
-//
-// TENSOR-CORE FORM (template flag TC, DQN_STEP_CTA_TC; what DQN_STEP_AUTO picks for populations): the four products that
-// hold 80 % of the step's flops run on tcgen05.mma (kind::tf32, M = 128) as error-compensated 3xTF32
-// (a = a_hi + a_lo: a_hi*b_lo + a_lo*b_hi + a_hi*b_hi, fp32 accumulation in tensor memory), two round trips per tile:
-//   forward   P2  h2(theta; s | s')  [128 x 64] = h1 [128 x 32] . W2       P1  h2(theta^-; s')  (rows in lanes 64..127)
-//   backward  P4  dh1 [64 r x 32]    = dh2 [r x 64 j] . W2^T               P3  dW2^T [64 j x 32 k] = dh2^T [j x 64 r] . h1
-// A operands never touch shared memory: "thread = TMEM lane = row" -- layer 1 is computed one batch row per thread and
-// its hi / lo halves go straight into tensor memory (tcgen05.st); dh2 is computed twice, once per row r (lanes 0..63)
-// and once per unit j (lanes 64..127), so P4 and P3 read ONE A tile whose two halves are dh2 and dh2^T.  B operands
-// (W2 in both orientations, h1 of the s rows) sit in shared memory in the K-major no-swizzle canonical layout (8 x 16 B
-// core matrices).  Everything else (layer 1, head, targets, dh2, dWh, dW1, Adam) stays fp32 FFMA on the CUDA cores.
 #include <math.h>
 
 #include "common.cuh"
@@ -76,80 +65,12 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// ---- tcgen05 pieces of the tensor-core form ----------------------------------------------------------------------------
-// Shared-memory B operands, K-major no-swizzle canonical layout (cute: ((8,n),(T,2)):((1T,SBO),(1,LBO)), T = 4 tf32):
-//   byte(mn, k) = (mn / 8) * SBO + (k / 4) * LBO + (mn % 8) * 16 + (k % 4) * 4        one k-step of 8 = two 16-byte chunks
-//   B2 / Bt2  W2 / W2^- as (mn = j 64, K = k 32): LBO 128, SBO 1024 (dense; written as 16-byte chunks)
-//   B4        W2 as (mn = k 32, K = j 64),  B3  h1 of the s rows as (mn = k 32, K = r 64): LBO 144, SBO 2304 -- the 16 spare
-//             bytes per chunk column put the 4-byte stores of 32 consecutive r (or the chunks of 8 consecutive k) on
-//             32 different banks
-constexpr int kLbo2 = 128, kSbo2 = 1024, kB2Bytes = 8 * kSbo2;          // 8192
-constexpr int kLbo4 = 144, kSbo4 = 16 * kLbo4, kB4Bytes = 4 * kSbo4;    // 2304, 9216
-// Tensor-memory columns (512 allocated; lane = row)
-constexpr uint32_t kA2Hi = 0, kA2Lo = 32, kA1Hi = 64, kA1Lo = 96, kD2 = 128, kD1 = 192, kAbHi = 256, kAbLo = 320, kD4 = 384, kD3 = 416;
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {   // version 1, no swizzle
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
-         (1ull << 46);
-}
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-// D[tmem] (+)= A[tmem] * B[smem]   (.ts form, one k-step of 8)
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 3xTF32 product over nks k-steps: small cross terms first, then hi * hi
-__device__ __forceinline__ void umma_3x(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t lbo, uint32_t sbo,
-                                        int nks, uint32_t idesc) {
-  for (int ks = 0; ks < nks; ++ks) {
-    const uint64_t dbh = make_desc(b_hi + 2u * lbo * ks, lbo, sbo), dbl = make_desc(b_lo + 2u * lbo * ks, lbo, sbo);
-    umma_ts(d, a_hi + 8u * ks, dbl, idesc, ks ? 1u : 0u);
-    umma_ts(d, a_lo + 8u * ks, dbh, idesc, 1u);
-    umma_ts(d, a_hi + 8u * ks, dbh, idesc, 1u);
-  }
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {   // 16 columns of this thread's lane
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// x = hi + lo with hi = tf32(x) (round to nearest) and lo = x - hi exactly (the tensor core drops lo's low mantissa bits)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-
 struct Lay {   // offsets in floats
   int pW2, pWh, PS;
-  int oW, oWt, oG, oX, oH1, oH2, oH2B, oDh2T, oDh2R, oDh1T, oDhdT, oDhdR, oQB, oScr, oMeta, oDummy, oRed, oBar, oStage;
-  int oB2, oBt2, oB4, oB3, total;
+  int oW, oWt, oG, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oQB, oScr, oMeta, oDummy, oRed, oBar, oStage, total;
 };
 
-__host__ __device__ inline Lay make_layout(int D, int recw, bool tc) {
+__host__ __device__ inline Lay make_layout(int D, int recw) {
   Lay L;
   L.pW2 = packed_w2(D);
   L.pWh = packed_head(D);
@@ -160,30 +81,24 @@ __host__ __device__ inline Lay make_layout(int D, int recw, bool tc) {
   L.oWt = o; o += PSa;
   L.oG = o; o += PSa;
   L.oX = o; o += (D + 1) * RS2;
-  L.oH1 = o; if (!tc) o += kH1 * RS2;
+  L.oH1 = o; o += kH1 * RS2;
   L.oH2 = o; o += (kH2 + 1) * RS2;
-  L.oH2B = o; if (tc) o += kH2 * RS1;            // tc: [64 j][68] h2(theta^-, s'); X | H2 | H2B also hold the 16-row tail tile
-  L.oDh2T = o; if (!tc) o += kH2 * RS1;
-  L.oDh2R = o; if (!tc) o += BT * RS1;
+  L.oDh2T = o; o += kH2 * RS1;
+  L.oDh2R = o; o += BT * RS1;
   L.oDh1T = o; o += kH1 * RS1;
   L.oDhdT = o; o += HC * RS1;
-  L.oDhdR = o; if (tc) o += BT * HC;             // tc: d(head) row-major [64 r][8]
-  L.oQB = o; if (!tc) o += BT * HC;
-  L.oScr = o; o += (tc ? 3 : 2) * 3 * BT * HC;
+  L.oQB = o; o += BT * HC;
+  L.oScr = o; o += 3 * BT * 2 * HC;
   L.oMeta = o; o += BT * 4;
   L.oDummy = o; o += 4;
-  L.oRed = o; o += 32 + (tc ? kH2 : 0);          // tc: [32..95] db2 partials of the upper row half
-  L.oBar = o; o += 8;               // [0,1] mbarrier of the record gather | tc: [2,3] mbarrier of the MMAs, [4] TMEM base address
+  L.oRed = o; o += 32;
+  L.oBar = o; o += 4;               // mbarrier of the record gather
   L.oStage = o; o += BT * recw;
-  L.oB2 = o; if (tc) o += 2 * kB2Bytes / 4;      // hi | lo
-  L.oBt2 = o; if (tc) o += 2 * kB2Bytes / 4;
-  L.oB4 = o; if (tc) o += 2 * kB4Bytes / 4;
-  L.oB3 = o; if (tc) o += 2 * kB4Bytes / 4;
   L.total = o;
   return L;
 }
 
-template <int A, bool TC>
+template <int A>
 __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs args) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x;
@@ -196,7 +111,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   const int D = args.dims.D;
   const int recw = args.dims.recw;
   const int PK = args.dims.PK;
-  const Lay L = make_layout(D, recw, TC);
+  const Lay L = make_layout(D, recw);
   if (args.gate && !args.gate[agent].train_flag) return;   // episode gate closed (q_agent.py:186): uniform over the CTA / cluster
 
   float* const W = sm + L.oW;       // theta      (smem layout)
@@ -214,15 +129,6 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   float* const Meta = sm + L.oMeta; // [64][4]  raw action lo, action hi, reward, done
   float* const Red = sm + L.oRed;   // [0..1] loss partials, [8..11] Adam bias corrections, [16..31] head-bias partials
   float* const Stage = sm + L.oStage;
-  // tensor-core form only
-  float* const H2B = sm + L.oH2B;   // [64 j][68]  h2(theta^-, s')
-  float* const DhdR = sm + L.oDhdR; // [64 r][8]
-  const int wq = warp & 3, wc = warp >> 2;          // a warp reaches TMEM lanes 32 wq .. 32 wq + 31; wc = which half of the columns
-  const int row2 = 32 * wq + lane;                  // forward row of batch A: < 64 = s row, else s' row (row2 - 64)
-  const uint32_t tlane = (uint32_t)(32 * wq) << 16;
-  const uint32_t sB2 = smem_addr(sm + L.oB2), sBt2 = smem_addr(sm + L.oBt2), sB4 = smem_addr(sm + L.oB4), sB3 = smem_addr(sm + L.oB3);
-  const uint32_t mbar = smem_addr(sm + L.oBar + 2);
-  uint32_t mma_parity = 0, tmem = 0;
 
   float* const gW = args.params + (size_t)agent * 4 * PK;
   float* const gWt = gW + PK;
@@ -285,30 +191,8 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
   // (96 B for D <= 10); thread 0 posts the expected byte count of the tile on the mbarrier every thread waits on
   const uint32_t bar = smem_addr(sm + L.oBar);
   uint32_t bar_parity = 0;
-  if (t == 0) { mbar_init(bar, 1); if (TC) mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  if constexpr (TC) {
-    if (warp == 0) {          // all 512 columns of the SM's tensor memory (one CTA per SM)
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(sm + L.oBar + 4)), "r"(512u) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-  }
+  if (t == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  if constexpr (TC) {
-    tc_fence_after();
-    tmem = *reinterpret_cast<const uint32_t*>(sm + L.oBar + 4);
-    // theta^- does not change inside a launch: its W2 operand (mn = j, K = k) is laid out once.  16-byte chunk (j, kc) at
-    // (j / 8) * SBO + kc * LBO + (j % 8) * 16: a quarter-warp writes 128 contiguous bytes
-    for (int ci = t; ci < 512; ci += NT) {
-      const int j = ci & 63, kc = ci >> 6;
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) split_tf32(Wt[L.pW2 + (4 * kc + e) * WS2 + j], hi[e], lo[e]);
-      uint8_t* dst = reinterpret_cast<uint8_t*>(sm + L.oBt2) + (j >> 3) * kSbo2 + kc * kLbo2 + (j & 7) * 16;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(dst + kB2Bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-  }
   auto prefetch = [&](int kstep, int tile) {
     const int nvalid = B - tile * BT < BT ? B - tile * BT : BT;
     if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * recw * 4));
@@ -355,36 +239,9 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
           sm[udst[4 * cc + 0]] = v.x; sm[udst[4 * cc + 1]] = v.y; sm[udst[4 * cc + 2]] = v.z; sm[udst[4 * cc + 3]] = v.w;
         }
       }
-      if constexpr (TC) {
-        if (tile == 0) {   // this step's W2 as tensor-core operands (hi | lo): B2 (mn = j, K = k) and B4 (mn = k, K = j), 16-byte chunks
-          for (int ci = t; ci < 512; ci += NT) {
-            {
-              const int j = ci & 63, kc = ci >> 6;
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) split_tf32(W[L.pW2 + (4 * kc + e) * WS2 + j], hi[e], lo[e]);
-              uint8_t* dst = reinterpret_cast<uint8_t*>(sm + L.oB2) + (j >> 3) * kSbo2 + kc * kLbo2 + (j & 7) * 16;
-              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(dst + kB2Bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            {
-              const int k = (ci & 7) + 8 * (ci >> 7), jc = (ci >> 3) & 15;
-              const float4 w = ld4(W + L.pW2 + k * WS2 + 4 * jc);
-              uint32_t hi[4], lo[4];
-              split_tf32(w.x, hi[0], lo[0]); split_tf32(w.y, hi[1], lo[1]); split_tf32(w.z, hi[2], lo[2]); split_tf32(w.w, hi[3], lo[3]);
-              uint8_t* dst = reinterpret_cast<uint8_t*>(sm + L.oB4) + (k >> 3) * kSbo4 + jc * kLbo4 + (k & 7) * 16;
-              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(dst + kB4Bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-        }
-      }
       __syncthreads();
       if (tile + 1 < ntiles) prefetch(kstep, tile + 1);
       else if (kstep + 1 < args.K) prefetch(kstep + 1, 0);
-      uint32_t mask1 = 0, mask2 = 0;   // tc: relu' of this thread's 16 h1 / 32 h2 entries (kept from the forward for the backward)
-      float db2_part = 0.f;
-      if constexpr (!TC) {
 
       // ================= batch B: Q(theta^-, s')  (q_learning_functions.py:54) ==============
       {  // layer 1: rows = s' (X cols 64..127) -> H1 cols 0..63
@@ -666,305 +523,6 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
           }
         }
       }
-      } else {
-      // =====================================================================================================
-      // tensor-core form
-      // =====================================================================================================
-      {  // ---- layer 1, one batch row per thread: theta on (s | s') = 128 rows; theta^- on s' (warps with lanes 64..127) ----
-        u64 acc[8], acct[8];
-        const float* w1 = W + 16 * wc;
-        const float* w1t = Wt + 16 * wc;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i] = ld64(w1 + D * kH1 + 2 * i); acct[i] = ld64(w1t + D * kH1 + 2 * i); }
-        for (int d = 0; d < D; ++d) {
-          const float x = X[d * RS2 + row2];
-          const u64 xx = pack2(x, x);
-          const u64x2 a0 = ld2x64(w1 + d * kH1), a1 = ld2x64(w1 + d * kH1 + 4), a2 = ld2x64(w1 + d * kH1 + 8), a3 = ld2x64(w1 + d * kH1 + 12);
-          ffma2(acc[0], xx, a0.lo); ffma2(acc[1], xx, a0.hi); ffma2(acc[2], xx, a1.lo); ffma2(acc[3], xx, a1.hi);
-          ffma2(acc[4], xx, a2.lo); ffma2(acc[5], xx, a2.hi); ffma2(acc[6], xx, a3.lo); ffma2(acc[7], xx, a3.hi);
-          if (wq >= 2) {
-            const u64x2 b0 = ld2x64(w1t + d * kH1), b1v = ld2x64(w1t + d * kH1 + 4), b2v = ld2x64(w1t + d * kH1 + 8), b3 = ld2x64(w1t + d * kH1 + 12);
-            ffma2(acct[0], xx, b0.lo); ffma2(acct[1], xx, b0.hi); ffma2(acct[2], xx, b1v.lo); ffma2(acct[3], xx, b1v.hi);
-            ffma2(acct[4], xx, b2v.lo); ffma2(acct[5], xx, b2v.hi); ffma2(acct[6], xx, b3.lo); ffma2(acct[7], xx, b3.hi);
-          }
-        }
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float a, b;
-          unpack2(acc[i], a, b);
-          a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
-          mask1 |= (a > 0.f ? 1u : 0u) << (2 * i) | (b > 0.f ? 1u : 0u) << (2 * i + 1);
-          split_tf32(a, hi[2 * i], lo[2 * i]); split_tf32(b, hi[2 * i + 1], lo[2 * i + 1]);
-        }
-        tmem_st16(tmem + tlane + kA2Hi + 16u * wc, hi);
-        tmem_st16(tmem + tlane + kA2Lo + 16u * wc, lo);
-        if (wq < 2) {   // h1 of the s rows is also the B operand of P3 (mn = k, K = r): 4-byte stores, conflict-free (LBO = 144)
-          uint8_t* b3 = reinterpret_cast<uint8_t*>(sm + L.oB3) + (row2 >> 2) * kLbo4 + (row2 & 3) * 4;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = 16 * wc + i;
-            *reinterpret_cast<uint32_t*>(b3 + (k >> 3) * kSbo4 + (k & 7) * 16) = hi[i];
-            *reinterpret_cast<uint32_t*>(b3 + (k >> 3) * kSbo4 + (k & 7) * 16 + kB4Bytes) = lo[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float a, b;
-            unpack2(acct[i], a, b);
-            split_tf32(fmaxf(a, 0.f), hi[2 * i], lo[2 * i]); split_tf32(fmaxf(b, 0.f), hi[2 * i + 1], lo[2 * i + 1]);
-          }
-          tmem_st16(tmem + tlane + kA1Hi + 16u * wc, hi);
-          tmem_st16(tmem + tlane + kA1Lo + 16u * wc, lo);
-        }
-        tmem_wait_st();
-        fence_async_smem();     // the operand stores of this thread (B3 here, B2 / B4 in the unpack phase) -> async proxy
-        tc_fence_before();
-      }
-      __syncthreads();
-      if (t == 0) {   // ---- forward products: h2 pre-activations of all 192 forward rows ----
-        tc_fence_after();
-        umma_3x(tmem + kD2, tmem + kA2Hi, tmem + kA2Lo, sB2, sB2 + kB2Bytes, kLbo2, kSbo2, kH1 / 8, make_idesc(kH2));
-        umma_3x(tmem + kD1, tmem + kA1Hi, tmem + kA1Lo, sBt2, sBt2 + kB2Bytes, kLbo2, kSbo2, kH1 / 8, make_idesc(kH2));
-        umma_commit(mbar);
-      }
-      mbar_wait(mbar, mma_parity); mma_parity ^= 1u;
-      tc_fence_after();
-      {  // ---- epilogue: + b2, relu -> H2 [j][row] (k-major, for the head / dWh); lanes 64..127 also own h2(theta^-, s') -> H2B ----
-        uint32_t r0[16], r1[16];
-        tmem_ld16(tmem + tlane + kD2 + 32u * wc, r0);
-        tmem_ld16(tmem + tlane + kD2 + 32u * wc + 16u, r1);
-        tmem_wait_ld();
-        const float* bias = W + L.pW2 + kH1 * WS2 + 32 * wc;
-        float* h2 = H2 + (32 * wc) * RS2 + row2;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float v0 = fmaxf(__uint_as_float(r0[i]) + bias[i], 0.f), v1 = fmaxf(__uint_as_float(r1[i]) + bias[16 + i], 0.f);
-          h2[i * RS2] = v0; h2[(16 + i) * RS2] = v1;
-          mask2 |= (v0 > 0.f ? 1u : 0u) << i | (v1 > 0.f ? 1u : 0u) << (16 + i);
-        }
-        if (wq >= 2) {
-          tmem_ld16(tmem + tlane + kD1 + 32u * wc, r0);
-          tmem_ld16(tmem + tlane + kD1 + 32u * wc + 16u, r1);
-          tmem_wait_ld();
-          const float* biast = Wt + L.pW2 + kH1 * WS2 + 32 * wc;
-          float* h2b = H2B + (32 * wc) * RS1 + (row2 - BT);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            h2b[i * RS1] = fmaxf(__uint_as_float(r0[i]) + biast[i], 0.f);
-            h2b[(16 + i) * RS1] = fmaxf(__uint_as_float(r1[i]) + biast[16 + i], 0.f);
-          }
-        }
-        tc_fence_before();
-      }
-      __syncthreads();
-      {  // ---- dueling head of the three forwards of row i (split-K over 4 thread groups), targets / loss / d(head) on part 0 ----
-        const int i = t & 63, part = t >> 6;
-        constexpr int NP = (A + 2) / 2;
-        u64 as2[NP], an2[NP], ab2[NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-          as2[q] = an2[q] = part == 0 ? ld64(W + L.pWh + kH2 * HC + 2 * q) : 0ull;
-          ab2[q] = part == 0 ? ld64(Wt + L.pWh + kH2 * HC + 2 * q) : 0ull;
-        }
-        const float* wh = W + L.pWh;
-        const float* wht = Wt + L.pWh;
-#pragma unroll 4
-        for (int k = 16 * part; k < 16 * part + 16; ++k) {
-          const float hs = H2[k * RS2 + i], hn = H2[k * RS2 + BT + i], hb = H2B[k * RS1 + i];
-          const u64 hs2 = pack2(hs, hs), hn2 = pack2(hn, hn), hb2 = pack2(hb, hb);
-          const u64x2 w0 = ld2x64(wh + k * HC), v0 = ld2x64(wht + k * HC);
-          ffma2(as2[0], hs2, w0.lo); ffma2(an2[0], hn2, w0.lo); ffma2(ab2[0], hb2, v0.lo);
-          if constexpr (NP > 1) { ffma2(as2[1], hs2, w0.hi); ffma2(an2[1], hn2, w0.hi); ffma2(ab2[1], hb2, v0.hi); }
-          if constexpr (NP > 2) {
-            const u64x2 w1 = ld2x64(wh + k * HC + 4), v1 = ld2x64(wht + k * HC + 4);
-            ffma2(as2[2], hs2, w1.lo); ffma2(an2[2], hn2, w1.lo); ffma2(ab2[2], hb2, v1.lo);
-            if constexpr (NP > 3) { ffma2(as2[3], hs2, w1.hi); ffma2(an2[3], hn2, w1.hi); ffma2(ab2[3], hb2, v1.hi); }
-          }
-        }
-        float as[2 * NP], an[2 * NP], ab[2 * NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-          unpack2(as2[q], as[2 * q], as[2 * q + 1]); unpack2(an2[q], an[2 * q], an[2 * q + 1]); unpack2(ab2[q], ab[2 * q], ab[2 * q + 1]);
-        }
-        if (part > 0) {
-#pragma unroll
-          for (int c = 0; c <= A; ++c) {
-            Scr[(((part - 1) * 3 + 0) * HC + c) * BT + i] = as[c];
-            Scr[(((part - 1) * 3 + 1) * HC + c) * BT + i] = an[c];
-            Scr[(((part - 1) * 3 + 2) * HC + c) * BT + i] = ab[c];
-          }
-        }
-        __syncthreads();
-        if (part == 0) {
-#pragma unroll
-          for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int c = 0; c <= A; ++c) {
-              as[c] += Scr[((p * 3 + 0) * HC + c) * BT + i]; an[c] += Scr[((p * 3 + 1) * HC + c) * BT + i]; ab[c] += Scr[((p * 3 + 2) * HC + c) * BT + i];
-            }
-          float ms = 0.f, mn = 0.f, mb = 0.f;
-#pragma unroll
-          for (int j = 1; j <= A; ++j) { ms += as[j]; mn += an[j]; mb += ab[j]; }
-          ms = ms / (float)A; mn = mn / (float)A; mb = mb / (float)A;
-          float q[A], nq[A], qb[A];
-#pragma unroll
-          for (int j = 0; j < A; ++j) { q[j] = as[0] + as[1 + j] - ms; nq[j] = an[0] + an[1 + j] - mn; qb[j] = ab[0] + ab[1 + j] - mb; }   // dddqn.py:31
-          // ---- compute_q_targets (q_learning_functions.py:55-59) ----
-          int astar = 0; float best = nq[0];
-#pragma unroll
-          for (int j = 1; j < A; ++j) if (nq[j] > best) { best = nq[j]; astar = j; }   // first max wins
-          const float4 meta = ld4(Meta + 4 * i);
-          int a = __float_as_int(meta.x);
-          a = a < 0 ? 0 : (a >= A ? A - 1 : a);                 // jax clamps out-of-range gather indices
-          const float rew = meta.z;
-          const float done = __float_as_uint(meta.w) ? 1.f : 0.f;   // dones.astype(float32), :84
-          float qa = q[0], nqt = qb[0];
-#pragma unroll
-          for (int j = 1; j < A; ++j) { if (j == a) qa = q[j]; if (j == astar) nqt = qb[j]; }
-          const float tv = rew + (1.0f - done) * (gamma * nqt - qa);              // :58 (F5 quirk kept)
-          const float tgt = qa + tv;                                            // :59
-          // ---- compute_loss (:35-36) with pred == q ----
-          const float e = qa - tgt;
-          const float ae = fabsf(e);
-          const float quad = fminf(ae, 1.0f);
-          const bool valid = tile * BT + i < B;
-          const float l = valid ? (l2loss ? 0.5f * e * e : 0.5f * quad * quad + (ae - quad)) : 0.f;
-          const float gi = valid ? (l2loss ? e : fminf(fmaxf(e, -1.0f), 1.0f)) / fB : 0.f;     // d mean_i sum_j loss / d pred[i,a]
-          // ---- backward through the dueling head: dV = sum_j dQ_j, dAdv = dQ - dV/A ----
-          const float dval = gi;
-          float dsum[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) dsum[c] = 0.f;
-          dsum[0] = dval;
-          DhdT[0 * RS1 + i] = dval;
-#pragma unroll
-          for (int j = 0; j < A; ++j) {
-            const float dadv = (j == a ? gi : 0.f) - dval / (float)A;
-            DhdT[(1 + j) * RS1 + i] = dadv;
-            dsum[1 + j] = dadv;
-          }
-          st4(DhdR + HC * i, dsum[0], dsum[1], dsum[2], dsum[3]);
-          st4(DhdR + HC * i + 4, dsum[4], dsum[5], dsum[6], dsum[7]);
-#pragma unroll
-          for (int c = 0; c <= A; ++c) {
-            const float s = warp_sum(dsum[c]);
-            if (lane == 0) Red[16 + warp * 8 + c] = s;
-          }
-          loss_acc += warp_sum(l);
-          if (args.taps.enabled && valid) {
-            const int gi_row = tile * BT + i;
-#pragma unroll
-            for (int j = 0; j < A; ++j) {
-              if (args.taps.q) args.taps.q[gi_row * A + j] = q[j];
-              if (args.taps.next_q) args.taps.next_q[gi_row * A + j] = nq[j];
-              if (args.taps.next_q_tm) args.taps.next_q_tm[gi_row * A + j] = qb[j];
-              if (args.taps.targets) args.taps.targets[gi_row * A + j] = (j == a) ? tgt : q[j];
-            }
-            if (args.taps.max_actions) args.taps.max_actions[gi_row] = astar;
-          }
-        }
-      }
-      __syncthreads();
-      {  // ---- dh2 = relu'(h2) * (d(head) . Wh^T), computed per row r (lanes 0..63) AND per unit j (lanes 64..127): the two halves of
-         //      the backward A tile; the reduction index runs over this warp's 32 columns ----
-        if (t <= A) G[L.pWh + kH2 * HC + t] += Red[16 + t] + Red[24 + t];     // d(head bias), fixed order
-        if (wq < 2) {          // lane = batch row r; columns = units j of [32 wc, 32 wc + 32)
-          float dh[1 + A];
-#pragma unroll
-          for (int c = 0; c <= A; ++c) dh[c] = DhdT[c * RS1 + row2];
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int j = 32 * wc + 16 * half + i;
-              const float4 w0 = ld4(W + L.pWh + j * HC), w1 = ld4(W + L.pWh + j * HC + 4);
-              const float whj[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-              float v = 0.f;
-#pragma unroll
-              for (int c = 0; c <= A; ++c) v = fmaf(dh[c], whj[c], v);
-              v = (mask2 >> (16 * half + i)) & 1u ? v : 0.f;
-              split_tf32(v, hi[i], lo[i]);
-            }
-            tmem_st16(tmem + tlane + kAbHi + 32u * wc + 16u * half, hi);
-            tmem_st16(tmem + tlane + kAbLo + 32u * wc + 16u * half, lo);
-          }
-        } else {               // lane = unit j; columns = batch rows r of [32 wc, 32 wc + 32)
-          const int j = row2 - BT;
-          const float4 w0 = ld4(W + L.pWh + j * HC), w1 = ld4(W + L.pWh + j * HC + 4);
-          const float whj[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const int r0 = 32 * wc + 16 * half + 4 * i4;
-              const float4 h = ld4(H2 + j * RS2 + r0);
-              const float hv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float4 d0 = ld4(DhdR + HC * (r0 + e)), d1 = ld4(DhdR + HC * (r0 + e) + 4);
-                const float dr[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-                float v = 0.f;
-#pragma unroll
-                for (int c = 0; c <= A; ++c) v = fmaf(dr[c], whj[c], v);
-                v = hv[e] > 0.f ? v : 0.f;
-                db2_part += v;
-                split_tf32(v, hi[4 * i4 + e], lo[4 * i4 + e]);
-              }
-            }
-            tmem_st16(tmem + tlane + kAbHi + 32u * wc + 16u * half, hi);
-            tmem_st16(tmem + tlane + kAbLo + 32u * wc + 16u * half, lo);
-          }
-          if (wc == 1) Red[32 + j] = db2_part;
-        }
-        tmem_wait_st();
-        tc_fence_before();
-      }
-      __syncthreads();
-      if (t == 0) {   // ---- backward products: dh1 (lanes 0..63) and dW2^T (lanes 64..127) from the one A tile ----
-        tc_fence_after();
-        umma_3x(tmem + kD4, tmem + kAbHi, tmem + kAbLo, sB4, sB4 + kB4Bytes, kLbo4, kSbo4, kH2 / 8, make_idesc(kH1));
-        umma_3x(tmem + kD3, tmem + kAbHi, tmem + kAbLo, sB3, sB3 + kB4Bytes, kLbo4, kSbo4, BT / 8, make_idesc(kH1));
-        umma_commit(mbar);
-      }
-      {  // dWh[j][c] += sum_r h2[r][j] * dhd[r][c] on the CUDA cores while the tensor core works
-        const int j = warp * 8 + (lane & 7), part = lane >> 3;
-        const float* ap[1] = {H2 + j * RS2 + 16 * part};
-        const float* bp[1 + A];
-#pragma unroll
-        for (int c = 0; c <= A; ++c) bp[c] = DhdT + c * RS1 + 16 * part;
-        float acc[1][1 + A];
-        dot_tile<1, 1 + A, 4>(ap, bp, acc);
-#pragma unroll
-        for (int c = 0; c <= A; ++c) {
-          float v = acc[0][c];
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (part == 0) G[L.pWh + j * HC + c] += v;
-        }
-      }
-      mbar_wait(mbar, mma_parity); mma_parity ^= 1u;
-      tc_fence_after();
-      {
-        uint32_t r0[16];
-        if (wq < 2) {          // dh1[r][k] = relu'(h1) * (dh2 . W2^T)  -> Dh1T (k-major, for dW1)
-          tmem_ld16(tmem + tlane + kD4 + 16u * wc, r0);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) Dh1T[(16 * wc + i) * RS1 + row2] = (mask1 >> i) & 1u ? __uint_as_float(r0[i]) : 0.f;
-        } else {               // dW2[k][j] += (dh2^T . h1)[j][k];  db2[j] += sum_r dh2[r][j]
-          const int j = row2 - BT;
-          tmem_ld16(tmem + tlane + kD3 + 16u * wc, r0);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) G[L.pW2 + (16 * wc + i) * WS2 + j] += __uint_as_float(r0[i]);
-          if (wc == 0) G[L.pW2 + kH1 * WS2 + j] += db2_part + Red[32 + j];
-        }
-        tc_fence_before();
-      }
-      }   // TC
       __syncthreads();
       {  // (d) [dW1;db1][d][h] += sum_r x[r][d] * dh1[r][h]   (row D of X is ones -> db1)
         const int hcol = t & 31, mt = t >> 5;
@@ -1074,49 +632,35 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_fused_kernel(const TrainArgs 
     ctl->adam_count = c > 0x7fffffffLL ? 0x7fffffff : (int)c;
     ctl->pb1 = pb1; ctl->pb2 = pb2;
   }
-  if constexpr (TC) {
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-      tc_fence_after();
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-    }
-  }
 }
 
 typedef void (*TrainKernel)(const TrainArgs);
-template <bool TC>
-TrainKernel pick_kernel_t(int A) {
+TrainKernel pick_kernel(int A) {
   switch (A) {
-    case 2: return dqn_train_fused_kernel<2, TC>;
-    case 3: return dqn_train_fused_kernel<3, TC>;
-    case 4: return dqn_train_fused_kernel<4, TC>;
-    case 5: return dqn_train_fused_kernel<5, TC>;
-    case 6: return dqn_train_fused_kernel<6, TC>;
-    case 7: return dqn_train_fused_kernel<7, TC>;
+    case 2: return dqn_train_fused_kernel<2>;
+    case 3: return dqn_train_fused_kernel<3>;
+    case 4: return dqn_train_fused_kernel<4>;
+    case 5: return dqn_train_fused_kernel<5>;
+    case 6: return dqn_train_fused_kernel<6>;
+    case 7: return dqn_train_fused_kernel<7>;
     default: return nullptr;
   }
 }
-TrainKernel pick_kernel(int A, bool tc) { return tc ? pick_kernel_t<true>(A) : pick_kernel_t<false>(A); }
 
 }  // namespace
 
-size_t train_fused_smem_bytes(const Dims& d, bool tc) { return (size_t)make_layout(d.D, d.recw, tc).total * sizeof(float); }
+size_t train_fused_smem_bytes(const Dims& d) { return (size_t)make_layout(d.D, d.recw).total * sizeof(float); }
 
 cudaError_t train_fused_prepare(const Dims& d) {
-  for (int tc = 0; tc < 2; ++tc) {
-    TrainKernel k = pick_kernel(d.A, tc != 0);
-    if (!k) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_fused_smem_bytes(d, tc != 0));
-    if (e != cudaSuccess) return e;
-  }
-  return cudaSuccess;
+  TrainKernel k = pick_kernel(d.A);
+  if (!k) return cudaErrorInvalidValue;
+  return cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_fused_smem_bytes(d));
 }
 
-cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args, bool tc) {
-  TrainKernel k = pick_kernel(args.dims.A, tc);
+cudaError_t launch_train_fused(cudaStream_t st, const TrainArgs& args) {
+  TrainKernel k = pick_kernel(args.dims.A);
   if (!k) return cudaErrorInvalidValue;
-  k<<<args.n_sel, NT, train_fused_smem_bytes(args.dims, tc), st>>>(args);
+  k<<<args.n_sel, NT, train_fused_smem_bytes(args.dims), st>>>(args);
   return cudaGetLastError();
 }
 
