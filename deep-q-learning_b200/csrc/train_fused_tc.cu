@@ -46,6 +46,9 @@ constexpr int kLbo2 = 128, kSbo2 = 1024, kB2Bytes = 8 * kSbo2;          // 8192
 constexpr int kLbo4 = 144, kSbo4 = 16 * kLbo4, kB4Bytes = 4 * kSbo4;    // 2304, 9216
 // Tensor-memory columns (512 allocated; lane = row)
 constexpr uint32_t kA2Hi = 0, kA2Lo = 32, kA1Hi = 64, kA1Lo = 96, kD2 = 128, kD1 = 192, kAbHi = 256, kAbLo = 320, kD4 = 384, kD3 = 416;
+// B4 and B3 are adjacent (hi: B4 | B3, then lo: B4 | B3), so ONE operand of mn = 64 (SBO groups 0..3 = W2, 4..7 = h1) feeds a single
+// N = 64 product whose accumulator columns are [D4 | D3]: lanes 0..63 of D4 and lanes 64..127 of D3 are the useful halves
+constexpr int kBbHalf = 2 * kB4Bytes;   // bytes from a hi buffer to its lo twin
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -138,7 +141,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 
 struct Lay {   // offsets in floats
   int pW2, pWh, PS;
-  int oW, oWt, oG, oX, oH2, oDh1T, oDhdT, oDhdR, oHP, oMeta, oDummy, oRed, oBar, oStage, oB2, oBt2, oB4, oB3, total;
+  int oW, oWt, oG, oX, oH2, oDh1T, oDhdT, oDhdR, oHP, oWhT, oMeta, oDummy, oRed, oBar, oStage, oB2, oBt2, oB4, oB3, total;
 };
 
 __host__ __device__ inline Lay make_layout(int D, int recw) {
@@ -157,6 +160,7 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
   L.oDhdT = o; o += HC * RS1;         // [8 c][68]
   L.oDhdR = o; o += BT * HC;          // [64 r][8]
   L.oHP = o; o += 3 * 4 * HC * BT;    // head partials [forward set][column quarter][c][row]
+  L.oWhT = o; o += HC * kH2;          // [8 c][64 j]  head weights of theta, transposed (rebuilt every step)
   L.oMeta = o; o += BT * 4;
   L.oDummy = o; o += 4;
   L.oRed = o; o += 32 + 4 * kH2;      // [0..1] loss, [8..11] Adam bias corrections, [16..31] head-bias partials, [32..] db2 partials [quarter][j]
@@ -164,8 +168,8 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
   L.oStage = o; o += BT * recw;
   L.oB2 = o; o += 2 * kB2Bytes / 4;   // hi | lo
   L.oBt2 = o; o += 2 * kB2Bytes / 4;
-  L.oB4 = o; o += 2 * kB4Bytes / 4;
-  L.oB3 = o; o += 2 * kB4Bytes / 4;
+  L.oB4 = o; o += kB4Bytes / 4;       // hi: B4 | B3, lo: B4 | B3
+  L.oB3 = o; o += kB4Bytes / 4 + 2 * kB4Bytes / 4;
   L.total = o;
   return L;
 }
@@ -192,13 +196,16 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
   float* const DhdT = sm + L.oDhdT;
   float* const DhdR = sm + L.oDhdR;
   float* const HP = sm + L.oHP;
+  float* const WhT = sm + L.oWhT;
+  float* const Qs = Dh1T;                                   // [3 forward sets][8][64 rows] Q-values (Dh1T is dead until the backward epilogue)
+  float* const DW1P = sm + L.oB3;                           // [4 row quarters][(D+1) * 32] partial dW1 (the h1 operand is dead after the backward product)
   float* const Meta = sm + L.oMeta; // [64][4]  raw action lo, action hi, reward, done
   float* const Red = sm + L.oRed;
   float* const Stage = sm + L.oStage;
   const int wq = warp & 3, wc = warp >> 2;          // TMEM quadrant (lanes 32 wq ..), column quarter
   const int row2 = 32 * wq + lane;                  // forward row of batch A: < 64 = s row, else s' row (row2 - 64); backward: r | 64 + j
   const uint32_t tlane = (uint32_t)(32 * wq) << 16;
-  const uint32_t sB2 = smem_addr(sm + L.oB2), sBt2 = smem_addr(sm + L.oBt2), sB4 = smem_addr(sm + L.oB4), sB3 = smem_addr(sm + L.oB3);
+  const uint32_t sB2 = smem_addr(sm + L.oB2), sBt2 = smem_addr(sm + L.oBt2), sB4 = smem_addr(sm + L.oB4);
   const uint32_t bar = smem_addr(sm + L.oBar), mbar = smem_addr(sm + L.oBar + 2);
 
   float* const gW = args.params + (size_t)agent * 4 * PK;
@@ -325,7 +332,11 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
           sm[udst[4 * cc + 0]] = v.x; sm[udst[4 * cc + 1]] = v.y; sm[udst[4 * cc + 2]] = v.z; sm[udst[4 * cc + 3]] = v.w;
         }
       }
-      if (tile == 0) {   // this step's W2 as tensor-core operands: B2 (mn = j, K = k) and B4 (mn = k, K = j)
+      if (tile > 0) {    // fold the previous tile's partial dW1 (Adam folds the last tile's)
+        for (int p = t; p < (D + 1) * kH1; p += NT) G[p] += ((DW1P[p] + DW1P[17 * kH1 + p]) + DW1P[2 * 17 * kH1 + p]) + DW1P[3 * 17 * kH1 + p];
+      }
+      if (tile == 0) {   // this step's W2 as tensor-core operands: B2 (mn = j, K = k) and B4 (mn = k, K = j); head weights transposed
+        WhT[t] = W[L.pWh + (t & 63) * HC + (t >> 6)];
         lay_b2(W + L.pW2, sm + L.oB2);
         {
           const int k = (t & 7) + 8 * (t >> 7), jc = (t >> 3) & 15;
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
           split_tf32(w.x, hi[0], lo[0]); split_tf32(w.y, hi[1], lo[1]); split_tf32(w.z, hi[2], lo[2]); split_tf32(w.w, hi[3], lo[3]);
           uint8_t* dst = reinterpret_cast<uint8_t*>(sm + L.oB4) + (k >> 3) * kSbo4 + jc * kLbo4 + (k & 7) * 16;
           *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(dst + kB4Bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(dst + kBbHalf) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       __syncthreads();
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             *reinterpret_cast<uint32_t*>(b3 + i * 16) = hi[i];
-            *reinterpret_cast<uint32_t*>(b3 + i * 16 + kB4Bytes) = lo[i];
+            *reinterpret_cast<uint32_t*>(b3 + i * 16 + kBbHalf) = lo[i];
           }
         } else {
 #pragma unroll
@@ -471,27 +482,31 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
         tc_fence_before();
       }
       __syncthreads();
-      if (t < BT) {   // ---- dueling head, targets / loss / d(head) of batch row i ----
-        const int i = t;
-        float hd[3][1 + A];
-#pragma unroll
-        for (int g = 0; g < 3; ++g)
+      if (warp < 8) {   // ---- dueling head: thread (row i, forward set g) sums the four column quarters; dddqn.py:31 ----
+        const int i = t & 63, g = t >> 6;
+        if (g < 3) {
+          float hd[1 + A];
 #pragma unroll
           for (int c = 0; c <= A; ++c) {
             float v = (g < 2 ? W : Wt)[L.pWh + kH2 * HC + c];
 #pragma unroll
             for (int p = 0; p < 4; ++p) v += HP[((g * 4 + p) * HC + c) * BT + i];
-            hd[g][c] = v;
+            hd[c] = v;
           }
-        float q[A], nq[A], qb[A];
-        {
-          float ms = 0.f, mn = 0.f, mb = 0.f;
+          float ms = 0.f;
 #pragma unroll
-          for (int j = 1; j <= A; ++j) { ms += hd[0][j]; mn += hd[1][j]; mb += hd[2][j]; }
-          ms = ms / (float)A; mn = mn / (float)A; mb = mb / (float)A;
+          for (int j = 1; j <= A; ++j) ms += hd[j];
+          ms = ms / (float)A;
 #pragma unroll
-          for (int j = 0; j < A; ++j) { q[j] = hd[0][0] + hd[0][1 + j] - ms; nq[j] = hd[1][0] + hd[1][1 + j] - mn; qb[j] = hd[2][0] + hd[2][1 + j] - mb; }   // dddqn.py:31
+          for (int j = 0; j < A; ++j) Qs[(g * HC + j) * BT + i] = hd[0] + hd[1 + j] - ms;
         }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+      if (t < BT) {   // ---- targets / loss / d(head) of batch row i ----
+        const int i = t;
+        float q[A], nq[A], qb[A];
+#pragma unroll
+        for (int j = 0; j < A; ++j) { q[j] = Qs[(0 * HC + j) * BT + i]; nq[j] = Qs[(1 * HC + j) * BT + i]; qb[j] = Qs[(2 * HC + j) * BT + i]; }
         // ---- compute_q_targets (q_learning_functions.py:55-59) ----
         int astar = 0; float best = nq[0];
 #pragma unroll
@@ -553,41 +568,49 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
          //      the backward A tile; the reduction index runs over this warp's 16 columns ----
         if (t <= A) G[L.pWh + kH2 * HC + t] += Red[16 + t] + Red[24 + t];     // d(head bias), fixed order
         uint32_t hi[16], lo[16];
-        if (wq < 2) {          // lane = batch row r; columns = units j of [16 wc, 16 wc + 16)
-          float dh[1 + A];
+        u64 v2[8];
 #pragma unroll
-          for (int c = 0; c <= A; ++c) dh[c] = DhdT[c * RS1 + row2];
+        for (int q = 0; q < 8; ++q) v2[q] = 0ull;
+        if (wq < 2) {          // lane = batch row r; columns = units j of [16 wc, 16 wc + 16): v[j] = sum_c dhd[r][c] * Wh[j][c]
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int j = 16 * wc + i;
-            const float4 w0 = ld4(W + L.pWh + j * HC), w1 = ld4(W + L.pWh + j * HC + 4);
-            const float whj[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            float v = 0.f;
+          for (int c = 0; c <= A; ++c) {
+            const float dv = DhdT[c * RS1 + row2];
+            const u64 dd = pack2(dv, dv);
 #pragma unroll
-            for (int c = 0; c <= A; ++c) v = fmaf(dh[c], whj[c], v);
-            v = (mask2 >> i) & 1u ? v : 0.f;
-            split_tf32(v, hi[i], lo[i]);
-          }
-        } else {               // lane = unit j; columns = batch rows r of [16 wc, 16 wc + 16)
-          const int j = row2 - BT;
-          const float4 w0 = ld4(W + L.pWh + j * HC), w1 = ld4(W + L.pWh + j * HC + 4);
-          const float whj[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const int r0 = 16 * wc + 4 * i4;
-            const float4 h = ld4(H2 + j * RS1 + r0);
-            const float hv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 d0 = ld4(DhdR + HC * (r0 + e)), d1 = ld4(DhdR + HC * (r0 + e) + 4);
-              const float dr[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-              float v = 0.f;
-#pragma unroll
-              for (int c = 0; c <= A; ++c) v = fmaf(dr[c], whj[c], v);
-              v = hv[e] > 0.f ? v : 0.f;
-              db2_part += v;
-              split_tf32(v, hi[4 * i4 + e], lo[4 * i4 + e]);
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const u64x2 w = ld2x64(WhT + c * kH2 + 16 * wc + 4 * q4);
+              ffma2(v2[2 * q4], dd, w.lo); ffma2(v2[2 * q4 + 1], dd, w.hi);
             }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float a, b;
+            unpack2(v2[q], a, b);
+            a = (mask2 >> (2 * q)) & 1u ? a : 0.f;
+            b = (mask2 >> (2 * q + 1)) & 1u ? b : 0.f;
+            split_tf32(a, hi[2 * q], lo[2 * q]); split_tf32(b, hi[2 * q + 1], lo[2 * q + 1]);
+          }
+        } else {               // lane = unit j; columns = batch rows r of [16 wc, 16 wc + 16): the same products in the same order
+          const int j = row2 - BT;
+#pragma unroll
+          for (int c = 0; c <= A; ++c) {
+            const float wv = WhT[c * kH2 + j];
+            const u64 ww = pack2(wv, wv);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const u64x2 d = ld2x64(DhdT + c * RS1 + 16 * wc + 4 * q4);
+              ffma2(v2[2 * q4], d.lo, ww); ffma2(v2[2 * q4 + 1], d.hi, ww);
+            }
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 h = ld4(H2 + j * RS1 + 16 * wc + 4 * q4);
+            float a, b, c2, d2;
+            unpack2(v2[2 * q4], a, b); unpack2(v2[2 * q4 + 1], c2, d2);
+            a = h.x > 0.f ? a : 0.f; b = h.y > 0.f ? b : 0.f; c2 = h.z > 0.f ? c2 : 0.f; d2 = h.w > 0.f ? d2 : 0.f;
+            db2_part += (a + b) + (c2 + d2);
+            split_tf32(a, hi[4 * q4], lo[4 * q4]); split_tf32(b, hi[4 * q4 + 1], lo[4 * q4 + 1]);
+            split_tf32(c2, hi[4 * q4 + 2], lo[4 * q4 + 2]); split_tf32(d2, hi[4 * q4 + 3], lo[4 * q4 + 3]);
           }
           if (wc > 0) Red[32 + wc * kH2 + j] = db2_part;
         }
@@ -599,8 +622,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
       __syncthreads();
       if (t == 0) {   // ---- backward products: dh1 (lanes 0..63) and dW2^T (lanes 64..127) from the one A tile ----
         tc_fence_after();
-        umma_3x<kH2 / 8>(tmem + kD4, tmem + kAbHi, tmem + kAbLo, sB4, sB4 + kB4Bytes, kLbo4, kSbo4, make_idesc(kH1));
-        umma_3x<BT / 8>(tmem + kD3, tmem + kAbHi, tmem + kAbLo, sB3, sB3 + kB4Bytes, kLbo4, kSbo4, make_idesc(kH1));
+        umma_3x<BT / 8>(tmem + kD4, tmem + kAbHi, tmem + kAbLo, sB4, sB4 + kBbHalf, kLbo4, kSbo4, make_idesc(2 * kH1));
         umma_commit(mbar);
       }
       if (warp >= NW / 2) {  // dWh[j][c] += sum_r h2[r][j] * dhd[r][c] on the CUDA cores (warps 8..15) while the tensor core works
@@ -639,19 +661,18 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
         tc_fence_before();
       }
       __syncthreads();
-      {  // [dW1;db1][d][h] += sum_r x[r][d] * dh1[r][h]   (row D of X is ones -> db1): warp = input row d, lane = unit h
-        const float* bp[1] = {Dh1T + lane * RS1};
-        if (warp <= D) {
-          const float* ap[1] = {X + warp * RS2};
-          float acc[1][1];
-          dot_tile<1, 1, 16>(ap, bp, acc);
-          G[warp * kH1 + lane] += acc[0][0];
-        }
-        if (warp == 0 && D == NW) {      // D = 16: row 16 (the ones row)
-          const float* ap[1] = {X + NW * RS2};
-          float acc[1][1];
-          dot_tile<1, 1, 16>(ap, bp, acc);
-          G[NW * kH1 + lane] += acc[0][0];
+      {  // [dW1;db1][d][h] = sum_r x[r][d] * dh1[r][h]  (row D of X is ones -> db1): lane = unit h, warp = (row quarter, four
+         // input rows d); the four quarters' partial sums are folded into G by the next tile's unpack phase or by Adam
+        const int rq = warp & 3;
+        const float* bp[1] = {Dh1T + lane * RS1 + 16 * rq};
+        for (int d0 = 4 * (warp >> 2); d0 <= D; d0 += 16) {
+          const float* ap[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ap[i] = X + (d0 + i <= D ? d0 + i : D) * RS2 + 16 * rq;
+          float acc[4][1];
+          dot_tile<4, 1, 4>(ap, bp, acc);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (d0 + i <= D) DW1P[rq * 17 * kH1 + (d0 + i) * kH1 + lane] = acc[i][0];
         }
       }
       // the barrier at the top of the next tile / before Adam orders these G updates
@@ -693,25 +714,35 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
     __syncthreads();
 
     if (args.taps.enabled && args.taps.grads) {
-      for (int p = t; p < L.PS; p += NT) args.taps.grads[p] = G[p];
+      for (int p = t; p < L.PS; p += NT)
+        args.taps.grads[p] = G[p] + (p < (D + 1) * kH1 ? ((DW1P[p] + DW1P[17 * kH1 + p]) + DW1P[2 * 17 * kH1 + p]) + DW1P[3 * 17 * kH1 + p] : 0.f);
     }
     // ================= optimiser: optax adam / adamw (q_learning_functions.py:24-25) ==========
     {
       const float c1 = Red[8 + 2 * (kstep & 1)], c2 = Red[9 + 2 * (kstep & 1)];
       const float rc1 = 1.0f / c1, rc2 = 1.0f / c2;
       const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+      // branch-free body (indices clamped, stores guarded) so that the seven sqrt / reciprocal chains of a thread overlap
+      float gv[NPT], th[NPT];
+      const int nW1 = (D + 1) * kH1;
+#pragma unroll
+      for (int i = 0; i < NPT; ++i) {
+        const int p = t + i * NT, pc = p < L.PS ? p : L.PS - 1;
+        gv[i] = G[pc]; th[i] = W[pc];
+        if (i == 0 && t < nW1) gv[0] += ((DW1P[t] + DW1P[17 * kH1 + t]) + DW1P[2 * 17 * kH1 + t]) + DW1P[3 * 17 * kH1 + t];   // nW1 <= 544: i = 0 and, below, i = 1
+        if (i == 1 && p < nW1) gv[1] += ((DW1P[p] + DW1P[17 * kH1 + p]) + DW1P[2 * 17 * kH1 + p]) + DW1P[3 * 17 * kH1 + p];
+      }
 #pragma unroll
       for (int i = 0; i < NPT; ++i) {
         const int p = t + i * NT;
+        const float g = p < L.PS ? gv[i] : 0.f;
+        const float m = b1 * mreg[i] + omb1 * g;
+        const float v = b2 * vreg[i] + omb2 * (g * g);
+        mreg[i] = m; vreg[i] = v;
+        const float u = (m * rc1) * fast_rcp(fast_sqrt(v * rc2 + eps_root) + eps);
         if (p < L.PS) {
-          const float g = G[p];
           G[p] = 0.f;
-          const float m = b1 * mreg[i] + omb1 * g;
-          const float v = b2 * vreg[i] + omb2 * (g * g);
-          mreg[i] = m; vreg[i] = v;
-          const float u = (m * rc1) * fast_rcp(fast_sqrt(v * rc2 + eps_root) + eps);
-          const float th = W[p];
-          W[p] = th - lr * (u + wd * th);        // add_decayed_weights (wd = 0 for adam); scale(-lr); apply_updates
+          W[p] = th[i] - lr * (u + wd * th[i]);  // add_decayed_weights (wd = 0 for adam); scale(-lr); apply_updates
         }
       }
     }
