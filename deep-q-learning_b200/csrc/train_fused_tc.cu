@@ -133,15 +133,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// x = hi + lo with hi = tf32(x) (round to nearest) and lo = x - hi exactly (the tensor core drops lo's low mantissa bits)
+// x = hi + lo with hi = tf32(x) (round to nearest, ties away: what cvt.rna.tf32.f32 computes for finite x, without its
+// Inf / NaN guard) and lo = x - hi exactly (the tensor core drops lo's low mantissa bits)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
+__device__ __forceinline__ uint32_t pos_bit(float v) { return min(__float_as_uint(v), 1u); }   // v >= +0: 1 iff v > 0
 
 struct Lay {   // offsets in floats
   int pW2, pWh, PS;
-  int oW, oWt, oG, oX, oH2, oDh1T, oDhdT, oDhdR, oHP, oWhT, oMeta, oDummy, oRed, oBar, oStage, oB2, oBt2, oB4, oB3, total;
+  int oW, oWt, oG, oX, oH2, oDh1T, oDhdT, oHP, oWhT, oMeta, oDummy, oRed, oBar, oStage, oB2, oBt2, oB4, oB3, total;
 };
 
 __host__ __device__ inline Lay make_layout(int D, int recw) {
@@ -158,7 +160,6 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
   L.oH2 = o; o += kH2 * RS1;          // [64 j][68]   h2(theta, s): dWh, relu' of the per-unit dh2 pass
   L.oDh1T = o; o += kH1 * RS1;        // [32 k][68]
   L.oDhdT = o; o += HC * RS1;         // [8 c][68]
-  L.oDhdR = o; o += BT * HC;          // [64 r][8]
   L.oHP = o; o += 3 * 4 * HC * BT;    // head partials [forward set][column quarter][c][row]
   L.oWhT = o; o += HC * kH2;          // [8 c][64 j]  head weights of theta, transposed (rebuilt every step)
   L.oMeta = o; o += BT * 4;
@@ -194,7 +195,6 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
   float* const H2 = sm + L.oH2;
   float* const Dh1T = sm + L.oDh1T;
   float* const DhdT = sm + L.oDhdT;
-  float* const DhdR = sm + L.oDhdR;
   float* const HP = sm + L.oHP;
   float* const WhT = sm + L.oWhT;
   float* const Qs = Dh1T;                                   // [3 forward sets][8][64 rows] Q-values (Dh1T is dead until the backward epilogue)
@@ -357,14 +357,22 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
         const float* w1t = Wt + 8 * wc;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { acc[i] = ld64(w1 + D * kH1 + 2 * i); acct[i] = ld64(w1t + D * kH1 + 2 * i); }
-#pragma unroll 2
-        for (int d = 0; d < D; ++d) {
-          const float x = X[d * RS2 + row2];
-          const u64 xx = pack2(x, x);
-          const u64x2 a0 = ld2x64(w1 + d * kH1), a1 = ld2x64(w1 + d * kH1 + 4);
-          ffma2(acc[0], xx, a0.lo); ffma2(acc[1], xx, a0.hi); ffma2(acc[2], xx, a1.lo); ffma2(acc[3], xx, a1.hi);
-          if (wq >= 2) {
+        if (wq < 2) {
+#pragma unroll 4
+          for (int d = 0; d < D; ++d) {
+            const float x = X[d * RS2 + row2];
+            const u64 xx = pack2(x, x);
+            const u64x2 a0 = ld2x64(w1 + d * kH1), a1 = ld2x64(w1 + d * kH1 + 4);
+            ffma2(acc[0], xx, a0.lo); ffma2(acc[1], xx, a0.hi); ffma2(acc[2], xx, a1.lo); ffma2(acc[3], xx, a1.hi);
+          }
+        } else {
+#pragma unroll 4
+          for (int d = 0; d < D; ++d) {
+            const float x = X[d * RS2 + row2];
+            const u64 xx = pack2(x, x);
+            const u64x2 a0 = ld2x64(w1 + d * kH1), a1 = ld2x64(w1 + d * kH1 + 4);
             const u64x2 c0 = ld2x64(w1t + d * kH1), c1 = ld2x64(w1t + d * kH1 + 4);
+            ffma2(acc[0], xx, a0.lo); ffma2(acc[1], xx, a0.hi); ffma2(acc[2], xx, a1.lo); ffma2(acc[3], xx, a1.hi);
             ffma2(acct[0], xx, c0.lo); ffma2(acct[1], xx, c0.hi); ffma2(acct[2], xx, c1.lo); ffma2(acct[3], xx, c1.hi);
           }
         }
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
           float a, b;
           unpack2(acc[i], a, b);
           a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
-          mask1 |= (a > 0.f ? 1u : 0u) << (2 * i) | (b > 0.f ? 1u : 0u) << (2 * i + 1);
+          mask1 |= pos_bit(a) << (2 * i) | pos_bit(b) << (2 * i + 1);
           split_tf32(a, hi[2 * i], lo[2 * i]); split_tf32(b, hi[2 * i + 1], lo[2 * i + 1]);
         }
         tmem_st8(tmem + tlane + kA2Hi + 8u * wc, hi);
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
           for (int e = 0; e < 4; ++e) {
             const int i = 4 * i4 + e;
             const float v = fmaxf(__uint_as_float(r0[i]) + bb[e], 0.f);
-            mask2 |= (v > 0.f ? 1u : 0u) << i;
+            mask2 |= pos_bit(v) << i;
             if (wq < 2) H2[(16 * wc + i) * RS1 + row2] = v;
             const u64 vv = pack2(v, v);
             const u64x2 w0 = ld2x64(wh + i * HC);
@@ -530,26 +538,11 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
         const float l = valid ? (l2loss ? 0.5f * e * e : 0.5f * quad * quad + (ae - quad)) : 0.f;
         const float gi = valid ? (l2loss ? e : fminf(fmaxf(e, -1.0f), 1.0f)) / fB : 0.f;     // d mean_i sum_j loss / d pred[i,a]
         // ---- backward through the dueling head: dV = sum_j dQ_j, dAdv = dQ - dV/A ----
-        float dsum[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) dsum[c] = 0.f;
-        dsum[0] = gi;
         DhdT[0 * RS1 + i] = gi;
+        const float gia = gi / (float)A;
 #pragma unroll
-        for (int j = 0; j < A; ++j) {
-          const float dadv = (j == a ? gi : 0.f) - gi / (float)A;
-          DhdT[(1 + j) * RS1 + i] = dadv;
-          dsum[1 + j] = dadv;
-        }
-        st4(DhdR + HC * i, dsum[0], dsum[1], dsum[2], dsum[3]);
-        st4(DhdR + HC * i + 4, dsum[4], dsum[5], dsum[6], dsum[7]);
-        // head-bias gradient = column sums of d(head): warp shuffle, then a fixed-order add of the two warps' sums
-#pragma unroll
-        for (int c = 0; c <= A; ++c) {
-          const float s = warp_sum(dsum[c]);
-          if (lane == 0) Red[16 + warp * 8 + c] = s;
-        }
-        loss_acc += warp_sum(l);
+        for (int j = 0; j < A; ++j) DhdT[(1 + j) * RS1 + i] = (j == a ? gi : 0.f) - gia;
+        Red[32 + i] = l;   // summed (like the head-bias gradient = column sums of d(head)) by idle warps under the backward product
         if (args.taps.enabled && valid) {
           const int gi_row = tile * BT + i;
 #pragma unroll
@@ -566,7 +559,6 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
       float db2_part = 0.f;
       {  // ---- dh2 = relu'(h2) * (d(head) . Wh^T), per row r (lanes 0..63) AND per unit j (lanes 64..127): the two halves of
          //      the backward A tile; the reduction index runs over this warp's 16 columns ----
-        if (t <= A) G[L.pWh + kH2 * HC + t] += Red[16 + t] + Red[24 + t];     // d(head bias), fixed order
         uint32_t hi[16], lo[16];
         u64 v2[8];
 #pragma unroll
@@ -624,6 +616,17 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
         tc_fence_after();
         umma_3x<BT / 8>(tmem + kD4, tmem + kAbHi, tmem + kAbLo, sB4, sB4 + kBbHalf, kLbo4, kSbo4, make_idesc(2 * kH1));
         umma_commit(mbar);
+      }
+      if (warp == 0) {       // sum of the tile's per-sample losses (fixed order)
+        loss_acc += warp_sum(Red[32 + lane] + Red[32 + 32 + lane]);
+      } else if (warp == 1) {   // d(head bias)[c] = sum_r dhd[r][c]
+        const int c = lane & 7, part = lane >> 3;
+        const float4 d0 = ld4(DhdT + c * RS1 + 16 * part), d1 = ld4(DhdT + c * RS1 + 16 * part + 4), d2 = ld4(DhdT + c * RS1 + 16 * part + 8),
+                     d3 = ld4(DhdT + c * RS1 + 16 * part + 12);
+        float v = (((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w))) + (((d2.x + d2.y) + (d2.z + d2.w)) + ((d3.x + d3.y) + (d3.z + d3.w)));
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (part == 0 && c <= A) G[L.pWh + kH2 * HC + c] += v;
       }
       if (warp >= NW / 2) {  // dWh[j][c] += sum_r h2[r][j] * dhd[r][c] on the CUDA cores (warps 8..15) while the tensor core works
         const int j = (warp - NW / 2) * 8 + (lane & 7), part = lane >> 3;
@@ -710,7 +713,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_tc_kernel(const TrainArgs arg
       for (int r = t; r < RS2; r += NT) X[D * RS2 + r] = 1.f;   // the 64-row layout's ones row was overwritten
     }
 
-    if ((warp == 0 || warp == 1) && lane == 0) Red[warp] = loss_acc;
+    if ((warp == 0 || warp == 1) && lane == 0) Red[warp] = loss_acc;   // (warp 1 contributes 0)
     __syncthreads();
 
     if (args.taps.enabled && args.taps.grads) {
