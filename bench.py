@@ -355,16 +355,17 @@ def run_single(args, ctx, with_extras=True):
 
     def e2e_loop(n, off=0):
         # Software-pipelined the way the reference's loop allows: _step() only ENQUEUES step i (a command to the resident
-        # kernel), so the host stages the train_frequency add()s of step i+1 while the device works, and reads step i's
-        # loss right before it issues step i+1.  Every step's loss is read back, one read per step, inside the timed region.
+        # kernel, which holds two command slots), so the host stages the train_frequency add()s of step i+1 while the device
+        # works, publishes step i+1 and THEN reads step i's loss (dqn_get_loss_lagged).  Every step's loss is read back, one
+        # read per step, one step behind, inside the timed region; the device never waits for the host between two steps.
         last = 0.0
         for i in range(n):
             for j in range(TRAIN_FREQUENCY):                      # q_agent.py:182  one add() per env transition
                 k = off + i * TRAIN_FREQUENCY + j
                 rb.add(s[k], a_py[k], r_py[k], s2[k], d_py[k])
-            if i:
-                last = rb.last_loss()                              # device -> host read of the previous step's loss
             agent._step()                                          # q_agent.py:187
+            if i:
+                last = rb.last_loss(1)                             # device -> host read of the previous step's loss
         return rb.last_loss()
 
     e2e_loop(8)
@@ -433,7 +434,9 @@ def run_single(args, ctx, with_extras=True):
                    "timed_region_s": timed_s, "min_timed_region_s": MIN_TIMED_S},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": TRAIN_FREQUENCY * REC_BYTES_ALGO,
                 "d2h_bytes_per_step": 4, "steps": e2e_steps, "timed_region_s": e2e_secs,
-                "api": "ReplayBuffer.add x4 (host numpy) + Agent._step() + loss readback per step (the adds of step i+1 are staged while step i runs)"
+                "loss_read_lag_steps": 1,
+                "api": "ReplayBuffer.add x4 (host numpy) + Agent._step() + loss readback per step, one step behind (step i+1 is staged and "
+                       "published while step i runs, then step i's loss is read: dqn_get_loss_lagged)"
                        + ("" if args.no_session else "; Agent(session=True): commands served by the resident train-step kernel")},
         "gpu_launches": reps * launches_per_rep, "replay_samples_per_sec": value * B,
         "roofline": roofline, "cpu_baseline": cpu, "extras": extras,

@@ -111,6 +111,7 @@ PROTOTYPES = {
     "dqn_store_train_step": (C.c_int, [_H, _i32, _i64, _P, _P, _P, _P, _P, _i32, _P]),
     "dqn_train_step_device_idx": (C.c_int, [_H, _i32, _i32, _i32, _P]),
     "dqn_get_losses": (C.c_int, [_H, _i32, _i32, _P, C.POINTER(_i64)]),
+    "dqn_get_loss_lagged": (C.c_int, [_H, _i32, _i32, _P]),
     "dqn_sync_target": (C.c_int, [_H, _i32, _i32]),
     "dqn_polyak_target": (C.c_int, [_H, _i32, _i32, C.c_float]),
     "dqn_set_loss_kind": (C.c_int, [_H, _i32, _i32, _i32]),

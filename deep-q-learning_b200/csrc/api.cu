@@ -156,7 +156,9 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   if (e != cudaSuccess) { cudaFreeHost(h->pinned); if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaHostAlloc(mapped) failed"); }
   memset((void*)h->mailbox, 0, sizeof(unsigned long long) * cfg->n_agents);
   h->sess = nullptr; h->sess_dev = nullptr;
-  h->session_enabled = h->session_active = h->session_outstanding = h->session_no_lease = h->session_launch_blocked = false;
+  h->session_enabled = h->session_active = h->session_no_lease = h->session_launch_blocked = false;
+  h->session_inflight = 0; h->session_op[0] = h->session_op[1] = 0; h->session_loss[0] = h->session_loss[1] = 0.f;
+  h->session_step_no[0] = h->session_step_no[1] = h->session_loss_step[0] = h->session_loss_step[1] = -1;
   h->session_seq = 0; h->session_last_loss = 0.f; h->session_last_cmd = 0.0;
   h->slot_next = 0;
   for (int i = 0; i < kSlots; ++i) cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming);
@@ -626,14 +628,14 @@ DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const 
   int srv = DQN_OK;
   if (h->session_enabled && K == 1 && n <= kInlineMax) {
     if (size_of(h, agent) + n == 0) return fail(DQN_E_INVALID, "dqn_train_step: replay ring of an agent is empty");
-    srv = session_prepare(h);                                // previous command answered (the slot is free), kernel alive
+    srv = session_prepare(h, 1);                             // at most ONE earlier command still in flight (this one's slot is free), kernel alive
     if (srv < 0) return srv;
   }
   if (h->session_enabled && K == 1 && n <= kInlineMax && srv == DQN_OK) {
     // served by the resident kernel: records into the mapped slot, ring the doorbell; no launch, no copy
     const int D = h->dims.D, recw = h->dims.recw;
     const unsigned long long stamp = ((h->session_seq + 1) & 0xffffffffull) << 32;     // the command's sequence number
-    volatile unsigned long long* slot = h->sess->stamped;
+    volatile unsigned long long* slot = h->sess->stamped[(h->session_seq + 1) & 1];
     for (int i = 0; i < (int)n; ++i) {
       uint32_t rec[kInlineWords];
       memset(rec, 0, sizeof rec);
@@ -644,15 +646,14 @@ DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const 
       rec[2 * D + 3] = done[i] ? 1u : 0u;
       for (int w = 0; w < recw; ++w) slot[(size_t)i * recw + w] = stamp | rec[w];
     }
-    session_publish(h, kOpStep, (int)n);
     AgentCtl& c = h->hctl[agent];
+    h->session_step_no[(h->session_seq + 1) & 1] = c.train_steps + 1;
+    session_publish(h, kOpStep, (int)n);
     c.ring_counter += n;
     c.train_steps += 1;
     if (c.adam_count < 0x7fffffff) c.adam_count += 1;
     if (loss_out) {
-      uint32_t bits = 0;
-      if (int rc = session_collect(h, &bits)) return rc;
-      memcpy(&h->session_last_loss, &bits, 4);
+      if (int rc = session_collect(h, nullptr)) return rc;
       *loss_out = h->session_last_loss;
     }
     return DQN_OK;
@@ -717,12 +718,7 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
     if (train_steps_out) *train_steps_out = h->hctl[agent].train_steps;
     if (n == 0) return DQN_OK;
     if (!loss_out || h->hctl[agent].train_steps < 1) return fail(DQN_E_INVALID, "dqn_get_losses: n must be <= min(train steps so far, 4096)");
-    if (h->session_outstanding) {
-      const bool was_step = ((h->sess->doorbell >> 8) & 0xff) == kOpStep;
-      uint32_t bits = 0;
-      if (int rc = session_collect(h, &bits)) return rc;
-      if (was_step) memcpy(&h->session_last_loss, &bits, 4);
-    }
+    if (int rc = session_collect(h, nullptr)) return rc;      // (train-step answers land in session_last_loss)
     if ((uint32_t)(h->mailbox[agent] >> 32) == (uint32_t)h->hctl[agent].train_steps) {   // also covers steps of earlier launches
       const uint32_t bits = (uint32_t)h->mailbox[agent];
       memcpy(loss_out, &bits, 4);
@@ -747,6 +743,27 @@ DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_
   if (n1 < (size_t)n) CU(cudaMemcpyAsync(dst + n1, src, ((size_t)n - n1) * 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   if (dst != loss_out) memcpy(loss_out, dst, (size_t)n * 4);
+  return DQN_OK;
+}
+
+DQN_API int dqn_get_loss_lagged(dqn_handle* h, int32_t agent, int32_t lag, float* loss_out) {
+  if (int rc = check_agent_raw(h, agent)) return rc;
+  if (!loss_out || lag < 0 || lag > 1) return fail(DQN_E_INVALID, "dqn_get_loss_lagged: lag must be 0 or 1, loss_out not NULL");
+  if (lag == 0) return dqn_get_losses(h, agent, 1, loss_out, nullptr);
+  const long long T = h->hctl[agent].train_steps - 1;         // the step whose loss is wanted
+  if (T < 1) return fail(DQN_E_INVALID, "dqn_get_loss_lagged: needs two train steps");
+  if (h->session_active) {
+    // the newest command stays in flight when it is the train step after T; every older answer is collected
+    const int newest = (int)(h->session_seq & 1);
+    const int keep = h->session_inflight > 0 && h->session_op[newest] == kOpStep && h->session_step_no[newest] == T + 1 ? 1 : 0;
+    if (int rc = session_collect(h, nullptr, keep)) return rc;
+    if (h->session_loss_step[T & 1] == T) { *loss_out = h->session_loss[T & 1]; return DQN_OK; }
+  }
+  if (int rc = check_agent(h, agent)) return rc;               // (ends a session) the step ran in an earlier launch: the loss ring has it
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(h->bounce, h->loss_ring + (size_t)agent * kLossCap + (size_t)((T - 1) % kLossCap), 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  memcpy(loss_out, h->bounce, 4);
   return DQN_OK;
 }
 
@@ -826,7 +843,7 @@ DQN_API int dqn_act(dqn_handle* h, int32_t agent, const float* state, int32_t* a
     for (int k = 0; k < h->dims.D; ++k) {
       uint32_t bits;
       memcpy(&bits, state + k, 4);
-      h->sess->stamped[k] = stamp | bits;
+      h->sess->stamped[(h->session_seq + 1) & 1][k] = stamp | bits;
     }
     session_publish(h, kOpAct, 0);
     uint32_t act = 0;

@@ -38,25 +38,33 @@ int session_launch(dqn_handle* h, unsigned long long first_seq) {
 }  // namespace
 
 namespace dqn {
-// wait for the answer to the command in flight (if any); a command that a timed-out kernel never saw is re-sent to a
-// fresh launch
-int session_collect(dqn_handle* h, uint32_t* payload_out) {
-  if (!h->session_outstanding) return DQN_OK;
-  const uint32_t want = (uint32_t)h->session_seq;
+// Wait for the answer to the OLDEST command in flight; a command that a timed-out kernel never saw is served by a fresh
+// launch (the kernel starts at that sequence number; a younger command published meanwhile sits in the other slot).
+static int session_collect_oldest(dqn_handle* h, uint32_t* payload_out) {
+  const unsigned long long seq = h->session_seq - (unsigned long long)h->session_inflight + 1;
+  const int slot = (int)(seq & 1);
+  const uint32_t want = (uint32_t)seq;
   for (unsigned long spin = 1;; ++spin) {
-    const unsigned long long v = h->sess->response;
+    const unsigned long long v = h->sess->response[slot];
     if ((uint32_t)(v >> 32) == want) {
+      if (h->session_op[slot] == kOpStep) {
+        const uint32_t bits = (uint32_t)v;
+        const long long T = h->session_step_no[slot];
+        memcpy(&h->session_loss[T & 1], &bits, 4);
+        h->session_loss_step[T & 1] = T;
+        h->session_last_loss = h->session_loss[T & 1];
+      }
       if (payload_out) *payload_out = (uint32_t)v;
-      h->session_outstanding = false;
+      h->session_inflight -= 1;
       return DQN_OK;
     }
     if ((spin & 0x3fff) == 0) {
       const cudaError_t e = cudaStreamQuery(h->stream);
       if (e == cudaSuccess) {                       // the kernel has left (idle time-out) ...
-        if ((uint32_t)(h->sess->response >> 32) == want) continue;      // ... after answering
-        if (int rc = session_launch(h, h->session_seq)) return rc;      // ... without seeing the command: a fresh launch serves it
+        if ((uint32_t)(h->sess->response[slot] >> 32) == want) continue;   // ... after answering
+        if (int rc = session_launch(h, seq)) return rc;                    // ... without seeing the command: a fresh launch serves it
       } else if (e != cudaErrorNotReady) {
-        h->session_active = false; h->session_outstanding = false;
+        h->session_active = false; h->session_inflight = 0;
         return fail(DQN_E_CUDA, std::string("session kernel failed: ") + cudaGetErrorString(e));
       }
     }
@@ -64,10 +72,17 @@ int session_collect(dqn_handle* h, uint32_t* payload_out) {
   }
 }
 
-// Make the session ready for the next command: the previous one answered, a live kernel.  The caller then writes the
-// payload stamped with session_seq + 1 and publishes.
-int session_prepare(dqn_handle* h) {
-  if (int rc = session_collect(h, nullptr)) return rc;       // at most one command in flight
+// wait until at most `keep` commands are in flight; payload_out = the answer of the last one collected
+int session_collect(dqn_handle* h, uint32_t* payload_out, int keep) {
+  while (h->session_inflight > keep)
+    if (int rc = session_collect_oldest(h, payload_out)) return rc;
+  return DQN_OK;
+}
+
+// Make the session ready for the next command: at most `keep` (0 or 1) earlier commands still in flight -- the slot of
+// session_seq + 1 is free -- and a live kernel.  The caller then writes the payload stamped with session_seq + 1 and publishes.
+int session_prepare(dqn_handle* h, int keep) {
+  if (int rc = session_collect(h, nullptr, keep)) return rc;
   if (h->session_active && !h->session_no_lease && host_now() - h->session_last_cmd > 0.010) {
     // the kernel leaves by itself after ~30 ms of silence; past 10 ms do not race it: retire it and start a fresh one
     if (int rc = session_stop(h)) return rc;
@@ -85,22 +100,21 @@ int session_prepare(dqn_handle* h) {
 }
 void session_publish(dqn_handle* h, int op, int n) {
   h->session_seq += 1;
+  const int slot = (int)(h->session_seq & 1);
+  h->session_op[slot] = op;
   __sync_synchronize();                                      // payload before the doorbell
-  h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)op << 8) | (unsigned long long)n;
-  h->session_outstanding = true;
+  h->sess->doorbell[slot] = (h->session_seq << 16) | ((unsigned long long)op << 8) | (unsigned long long)n;
+  h->session_inflight += 1;
   h->session_last_cmd = host_now();
 }
 
 int session_stop(dqn_handle* h) {
   if (!h->session_active) return DQN_OK;
   CU(cudaSetDevice(h->cfg.device));
-  uint32_t payload = 0;
-  const bool was_step = h->session_outstanding && ((h->sess->doorbell >> 8) & 0xff) == kOpStep;
-  if (int rc = session_collect(h, &payload)) return rc;
-  if (was_step) memcpy(&h->session_last_loss, &payload, 4);
+  if (int rc = session_collect(h, nullptr, 0)) return rc;    // (train-step answers land in session_last_loss)
   h->session_seq += 1;
   __sync_synchronize();
-  h->sess->doorbell = (h->session_seq << 16) | ((unsigned long long)kOpExit << 8);
+  h->sess->doorbell[h->session_seq & 1] = (h->session_seq << 16) | ((unsigned long long)kOpExit << 8);
   h->session_active = false;                                 // (a kernel that already timed out never reads the EXIT; harmless)
   CU(cudaStreamSynchronize(h->stream));
   return DQN_OK;

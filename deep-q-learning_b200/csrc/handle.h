@@ -76,7 +76,12 @@ struct dqn_handle {
   // session mode (dqn_set_session): a resident cluster kernel serves STEP / ACT / SYNC commands from mapped host memory
   dqn::SessionCtl* sess;             // mapped pinned host memory (nullptr until enabled)
   dqn::SessionCtl* sess_dev;         // device alias
-  bool session_enabled, session_active, session_outstanding;
+  bool session_enabled, session_active;
+  int session_inflight;         // commands published and not yet collected (0..2): seq - inflight + 1 .. seq, slot = seq % 2
+  int session_op[2];            // op of the command last published in each slot
+  long long session_step_no[2]; // train-step number (1-based) of the STEP command last published in each slot
+  float session_loss[2];        // loss of train step T, kept at [T % 2] once its answer has been collected ...
+  long long session_loss_step[2];   // ... together with T
   bool session_launch_blocked;  // the last session launch call returned only after the kernel had left (profiler)
   bool session_no_lease;        // diagnostics (dqn_set_session(h, 2)): never retire the kernel early, rely on the re-send path
   unsigned long long session_seq;       // sequence number of the last command published
@@ -90,11 +95,11 @@ struct dqn_handle {
 namespace dqn {
 
 // session mode (api_session.cu)
-int session_stop(dqn_handle* h);                                  // answer in flight collected, EXIT, stream drained
+int session_stop(dqn_handle* h);                                  // answers in flight collected, EXIT, stream drained
 constexpr int kSessionUnavailable = 1;                            // session_prepare: launches are synchronous here, session mode switched off
-int session_prepare(dqn_handle* h);                               // previous command answered, a live kernel
-void session_publish(dqn_handle* h, int op, int n);               // payload already written with stamp session_seq + 1
-int session_collect(dqn_handle* h, uint32_t* payload_out);        // wait for the answer of the command in flight
+int session_prepare(dqn_handle* h, int keep = 0);                 // at most `keep` (0 / 1) commands still in flight, a live kernel
+void session_publish(dqn_handle* h, int op, int n);               // payload already written (slot (session_seq + 1) % 2) with stamp session_seq + 1
+int session_collect(dqn_handle* h, uint32_t* payload_out, int keep = 0);   // wait until at most `keep` commands are in flight
 // the train-step launch shared by dqn_train_step*, dqn_store_train_step and dqn_train_flagged (api.cu)
 int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, dqn_debug_taps* taps, const InlineStore* ist = nullptr,
                  const EpisodeCtl* gate = nullptr);

@@ -9,9 +9,10 @@
  *   hoststage.put(stage, i, state, action, reward, observation, done)     # row i of the five staging arrays
  *
  * It can also make the two C-ABI calls of the reference's per-step sequence without going through ctypes (~1.2 us of
- * argument marshalling each): after hoststage.bind(stage, handle, &dqn_store_train_step, &dqn_get_losses, agent),
+ * argument marshalling each): after hoststage.bind(stage, handle, &dqn_store_train_step, &dqn_get_losses, &dqn_get_loss_lagged, agent),
  *   hoststage.step(stage, n)     == dqn_store_train_step(handle, agent, n, <the staging arrays>, 1, NULL)   -> status
  *   hoststage.loss(stage)        == dqn_get_losses(handle, agent, 1, &loss, NULL)                             -> (status, loss)
+ *   hoststage.loss(stage, 1)     == dqn_get_loss_lagged(handle, agent, 1, &loss)                              -> (status, loss)
  * The functions are the library's own entry points (include/dqn_b200.h), called by address.
  */
 #define PY_SSIZE_T_CLEAN
@@ -30,6 +31,7 @@ typedef struct {
   void* handle;
   int (*store_train_step)(void*, int32_t, int64_t, const float*, const int64_t*, const float*, const float*, const uint8_t*, int32_t, float*);
   int (*get_losses)(void*, int32_t, int32_t, float*, int64_t*);
+  int (*get_loss_lagged)(void*, int32_t, int32_t, float*);
   int32_t agent;
 } Stage;
 
@@ -43,7 +45,7 @@ static PyObject* hs_new(PyObject* self, PyObject* args) {
   if (!st) return PyErr_NoMemory();
   st->s = (float*)(uintptr_t)as; st->a = (int64_t*)(uintptr_t)aa; st->r = (float*)(uintptr_t)ar;
   st->o = (float*)(uintptr_t)ao; st->d = (uint8_t*)(uintptr_t)ad; st->D = D; st->cap = cap;
-  st->handle = NULL; st->store_train_step = NULL; st->get_losses = NULL; st->agent = 0;
+  st->handle = NULL; st->store_train_step = NULL; st->get_losses = NULL; st->get_loss_lagged = NULL; st->agent = 0;
   return PyCapsule_New(st, "dqn_b200.hoststage", stage_free);
 }
 
@@ -83,14 +85,15 @@ static PyObject* hs_put(PyObject* self, PyObject* const* args, Py_ssize_t nargs)
 
 static PyObject* hs_bind(PyObject* self, PyObject* args) {
   PyObject* cap;
-  unsigned long long handle, f_step, f_loss;
+  unsigned long long handle, f_step, f_loss, f_lagged;
   int agent;
-  if (!PyArg_ParseTuple(args, "OKKKi", &cap, &handle, &f_step, &f_loss, &agent)) return NULL;
+  if (!PyArg_ParseTuple(args, "OKKKKi", &cap, &handle, &f_step, &f_loss, &f_lagged, &agent)) return NULL;
   Stage* st = (Stage*)PyCapsule_GetPointer(cap, "dqn_b200.hoststage");
   if (!st) return NULL;
   st->handle = (void*)(uintptr_t)handle;
   *(void**)(&st->store_train_step) = (void*)(uintptr_t)f_step;
   *(void**)(&st->get_losses) = (void*)(uintptr_t)f_loss;
+  *(void**)(&st->get_loss_lagged) = (void*)(uintptr_t)f_lagged;
   st->agent = (int32_t)agent;
   Py_RETURN_NONE;
 }
@@ -106,21 +109,23 @@ static PyObject* hs_step(PyObject* self, PyObject* const* args, Py_ssize_t nargs
 }
 
 static PyObject* hs_loss(PyObject* self, PyObject* const* args, Py_ssize_t nargs) {
-  if (nargs != 1) { PyErr_SetString(PyExc_TypeError, "loss(stage)"); return NULL; }
+  if (nargs != 1 && nargs != 2) { PyErr_SetString(PyExc_TypeError, "loss(stage[, lag])"); return NULL; }
   Stage* st = (Stage*)PyCapsule_GetPointer(args[0], "dqn_b200.hoststage");
   if (!st) return NULL;
   if (!st->get_losses) { PyErr_SetString(PyExc_RuntimeError, "hoststage.loss: bind() has not been called"); return NULL; }
+  long lag = 0;
+  if (nargs == 2) { lag = PyLong_AsLong(args[1]); if (lag == -1 && PyErr_Occurred()) return NULL; }
   float loss = 0.f;
-  const int rc = st->get_losses(st->handle, st->agent, 1, &loss, NULL);
+  const int rc = lag ? st->get_loss_lagged(st->handle, st->agent, (int32_t)lag, &loss) : st->get_losses(st->handle, st->agent, 1, &loss, NULL);
   return Py_BuildValue("(id)", rc, (double)loss);
 }
 
 static PyMethodDef methods[] = {
     {"new", hs_new, METH_VARARGS, "new(addr_s, addr_a, addr_r, addr_o, addr_d, D, capacity) -> stage"},
     {"put", (PyCFunction)(void (*)(void))hs_put, METH_FASTCALL, "put(stage, i, state, action, reward, observation, done)"},
-    {"bind", hs_bind, METH_VARARGS, "bind(stage, handle, addr_dqn_store_train_step, addr_dqn_get_losses, agent)"},
+    {"bind", hs_bind, METH_VARARGS, "bind(stage, handle, addr_dqn_store_train_step, addr_dqn_get_losses, addr_dqn_get_loss_lagged, agent)"},
     {"step", (PyCFunction)(void (*)(void))hs_step, METH_FASTCALL, "step(stage, n) -> status of dqn_store_train_step(handle, agent, n, staged arrays, 1, NULL)"},
-    {"loss", (PyCFunction)(void (*)(void))hs_loss, METH_FASTCALL, "loss(stage) -> (status, loss of the last train step)"},
+    {"loss", (PyCFunction)(void (*)(void))hs_loss, METH_FASTCALL, "loss(stage[, lag]) -> (status, loss of the last train step / of the one before it)"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_hoststage", "host-side staging of ReplayBuffer.add", -1, methods};

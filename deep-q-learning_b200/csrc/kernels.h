@@ -21,17 +21,19 @@ struct TapsDev {
 };
 
 // Session mode of the cluster train-step kernel: a block of MAPPED PINNED host memory through which a resident kernel
-// takes commands (no launch, no copy per command).  The host writes state / rec and then the doorbell; the kernel
-// answers in `response`.  At most one command is in flight.
+// takes commands (no launch, no copy per command).  The host writes the payload and then the doorbell of slot seq % 2;
+// the kernel answers in that slot's `response`.  Commands are served in sequence order; at most TWO are in flight (one per
+// slot), so the host can publish train step i + 1 while the kernel runs step i and read step i's loss afterwards.
 enum { kOpStep = 1, kOpAct = 2, kOpSync = 3, kOpExit = 4 };
+constexpr int kSessionSlotUnits = 16 * 40;
 struct SessionCtl {
-  volatile unsigned long long doorbell;   // host -> device: (seq << 16) | (op << 8) | n
-  volatile unsigned long long response;   // device -> host: (seq << 32) | payload (loss bits / action)
-  volatile unsigned long long closed;     // device -> host: written once when the kernel leaves (next seq it would have served)
-  unsigned long long pad[5];
+  volatile unsigned long long doorbell[2];   // host -> device: (seq << 16) | (op << 8) | n
+  volatile unsigned long long response[2];   // device -> host: (seq << 32) | payload (loss bits / action)
+  volatile unsigned long long closed;        // device -> host: written once when the kernel leaves (next seq it would have served)
+  unsigned long long pad[3];
   // payload, one 8-byte unit per 32-bit word: (low 32 bits of seq) << 32 | word.  STEP: n records in the ring's AoS
   // layout, stride dims.recw words; ACT: the D floats of the state.  A unit is valid when its stamp is the command's.
-  volatile unsigned long long stamped[16 * 40];
+  volatile unsigned long long stamped[2][kSessionSlotUnits];
 };
 
 struct TrainArgs {

@@ -289,9 +289,13 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   // Rank 0 polls the doorbell in mapped host memory and forwards each command word to the four CTAs' shared memory, so
   // the whole cluster takes the same decision (including the idle time-out).  Commands: STEP = n ReplayBuffer.add +
   // one Agent._step (records read from the host slot), ACT = greedy action for one state (rank 0), SYNC = theta^- :=
-  // theta, EXIT.  The host has at most one command in flight.
+  // theta, EXIT.  Command seq lives in slot seq % 2 (doorbell, payload, response); the host has at most two in flight.
   unsigned long long next_seq = args.sess_first_seq;
   bool wt_dirty = false;
+  // The host may have published the NEXT command (other slot) while this one runs: rank 0's polling warp issues the loads of
+  // its doorbell and first 128 payload units at the tail of a step, under the all-gather, and looks at them first.
+  unsigned long long pre_w = 0ull, pre_u[4] = {0ull, 0ull, 0ull, 0ull};
+  bool have_pre = false;
   volatile unsigned long long* CmdWordR[CS];
 #pragma unroll
   for (int c = 0; c < CS; ++c) CmdWordR[c] = cluster.map_shared_rank(const_cast<unsigned long long*>(CmdWord), c);
@@ -309,13 +313,22 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
           if (warp == 0) {
             unsigned long long w = 0ull, u[4];
             const long long c0 = clock64();
+            volatile unsigned long long* const door = &sess->doorbell[next_seq & 1];      // the command's slot: seq % 2
+            volatile unsigned long long* const units = sess->stamped[next_seq & 1];
             for (;;) {
-              if (lane == 0) {
-                w = ld_sys_u64(&sess->doorbell);
-                if ((w >> 16) != next_seq && clock64() - c0 > kIdleCycles) w = (next_seq << 16) | ((unsigned long long)kOpExit << 8);
-              }
+              if (have_pre) {
+                w = pre_w;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) u[q] = ld_sys_u64(&sess->stamped[lane + 32 * q]);
+                for (int q = 0; q < 4; ++q) u[q] = pre_u[q];
+                have_pre = false;
+              } else {
+                if (lane == 0) {
+                  w = ld_sys_u64(door);
+                  if ((w >> 16) != next_seq && clock64() - c0 > kIdleCycles) w = (next_seq << 16) | ((unsigned long long)kOpExit << 8);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) u[q] = ld_sys_u64(&units[lane + 32 * q]);
+              }
               w = __shfl_sync(0xffffffffu, w, 0);
               if ((w >> 16) == next_seq) break;
             }
@@ -326,8 +339,8 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
               for (int q = 0; q < 4; ++q) {
                 const int idx = base + lane + 32 * q;
                 if (idx < need) {
-                  unsigned long long x = base == 0 ? u[q] : ld_sys_u64(&sess->stamped[idx]);
-                  while ((uint32_t)(x >> 32) != (uint32_t)next_seq) x = ld_sys_u64(&sess->stamped[idx]);
+                  unsigned long long x = base == 0 ? u[q] : ld_sys_u64(&units[idx]);
+                  while ((uint32_t)(x >> 32) != (uint32_t)next_seq) x = ld_sys_u64(&units[idx]);
                   if (wop == kOpStep) {            // ReplayBuffer.add x n (replay_buffer.py:58-65)
                     const int i = idx / recw, c = idx - i * recw;
                     ring[(size_t)((rc + i) % args.dims.N) * recw + c] = (uint32_t)x;
@@ -361,7 +374,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         if (op == kOpAct) {              // compute_action (q_learning_functions.py:67-73) from the resident weights
           if (rank == 0 && warp == 0) {          // the state is already in Stage (stamped payload)
             const int best = warp_greedy_action(W, D, A, Stage, nullptr);
-            if (lane == 0) st_sys_u64(&sess->response, (next_seq << 32) | (unsigned long long)(uint32_t)best);
+            if (lane == 0) st_sys_u64(&sess->response[next_seq & 1], (next_seq << 32) | (unsigned long long)(uint32_t)best);
           }
           __syncthreads();
           ++next_seq;
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
           for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) { const float4 w4 = ld4(W + 4 * p4); st4(Wt + 4 * p4, w4.x, w4.y, w4.z, w4.w); }
           wt_dirty = true;
           cluster_barrier_after_local_stores();     // every CTA has taken the command before rank 0 can forward the next one
-          if (rank == 0 && t == 0) st_sys_u64(&sess->response, next_seq << 32);
+          if (rank == 0 && t == 0) st_sys_u64(&sess->response[next_seq & 1], next_seq << 32);
           ++next_seq;
         } else {
           break;
@@ -444,7 +457,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         args.loss_ring[(size_t)agent * kLossCap + (size_t)((step0 + kstep) % kLossCap)] = loss;
         if (serve || kstep == args.K - 1)
           args.loss_mailbox[agent] = ((unsigned long long)(uint32_t)(step0 + kstep + 1) << 32) | __float_as_uint(loss);
-        if (serve) st_sys_u64(&sess->response, (next_seq << 32) | __float_as_uint(loss));
+        if (serve) st_sys_u64(&sess->response[next_seq & 1], (next_seq << 32) | __float_as_uint(loss));
         if (args.taps.enabled && args.taps.loss) args.taps.loss[0] = loss;
       }
       const float th[4] = {th4.x, th4.y, th4.z, th4.w};
@@ -460,7 +473,15 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       st4(W + pown, nw[0], nw[1], nw[2], nw[3]);
       if (args.taps.enabled && args.taps.grads) st4(args.taps.grads + pown, g[0], g[1], g[2], g[3]);
     }
-    if (serve) ++next_seq;
+    if (serve) {
+      ++next_seq;
+      if (rank == 0 && warp == 0) {          // loads in flight under the all-gather; consumed by the poll at the top of the loop
+        if (lane == 0) pre_w = ld_sys_u64(&sess->doorbell[next_seq & 1]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pre_u[q] = ld_sys_u64(&sess->stamped[next_seq & 1][lane + 32 * q]);
+        have_pre = true;
+      }
+    }
     if (gather_after) {
       // ---- all-gather (push): my new slice -> the three peers' replicas; wait for theirs ----
       fence_proxy_async();

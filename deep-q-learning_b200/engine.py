@@ -226,6 +226,12 @@ class DqnEngine:
         _lib.check(self.lib.dqn_get_losses(self.h, agent, 1, self._loss1_ptr, None))
         return float(self._loss1[0])
 
+    def lagged_loss(self, agent=0, lag=1):
+        """Loss of the train step ``lag`` steps before the most recent one; waits for that step only (in session mode the
+        most recent step may still be in flight)."""
+        _lib.check(self.lib.dqn_get_loss_lagged(self.h, agent, int(lag), self._loss1_ptr))
+        return float(self._loss1[0])
+
     def train_step_count(self, agent=0):
         ts = C.c_int64(0)
         _lib.check(self.lib.dqn_get_losses(self.h, agent, 0, None, C.byref(ts)))

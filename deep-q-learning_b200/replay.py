@@ -77,7 +77,7 @@ class ReplayBuffer:
             import ctypes as C
             lib = _engine.lib
             _hoststage.bind(self._stage, int(_engine.h.value), C.cast(lib.dqn_store_train_step, C.c_void_p).value,
-                            C.cast(lib.dqn_get_losses, C.c_void_p).value, int(_agent))
+                            C.cast(lib.dqn_get_losses, C.c_void_p).value, C.cast(lib.dqn_get_loss_lagged, C.c_void_p).value, int(_agent))
             self._bound = True
         self._pending = 0
         self._counter = 0
@@ -130,14 +130,16 @@ class ReplayBuffer:
             _lib.check(e.lib.dqn_store_train_step(e.h, self._agent, n, *self._ptrs, 1, None))
         self._pending = 0                                   # only once the library has taken the staged transitions
 
-    def last_loss(self):
-        """Loss of the most recent train step of this buffer's agent (waits for it)."""
+    def last_loss(self, lag=0):
+        """Loss of the most recent train step of this buffer's agent (waits for it).  ``lag=1``: the loss of the step BEFORE the
+        most recent one, waiting for that step only -- with ``Agent(session=True)`` the most recent step may still be in flight,
+        so a loop that calls ``_step()`` and then ``last_loss(1)`` reads every loss, one step behind, without stalling the device."""
         if self._bound:
-            rc, loss = _hoststage.loss(self._stage)
+            rc, loss = _hoststage.loss(self._stage, lag)
             if rc:
                 _lib.check(rc)
             return loss
-        return self._engine.last_loss(self._agent)
+        return self._engine.lagged_loss(self._agent, lag) if lag else self._engine.last_loss(self._agent)
 
     def flush(self):
         """Move staged add() transitions into the device ring (no-op when nothing is pending)."""

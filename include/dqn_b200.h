@@ -191,7 +191,8 @@ DQN_API int dqn_store_train_step(dqn_handle* h, int32_t agent, int64_t n, const 
                                  const float* s2, const uint8_t* done, int32_t K, float* loss_out);
 /* Session mode (single-agent handles): ONE resident launch of the cluster kernel keeps theta / theta^- / Adam state in
  * shared memory and serves the agent's per-env-step calls from commands in mapped host memory -- no launch and no copy
- * per call: dqn_store_train_step (n <= 16, K = 1), dqn_act, dqn_sync_target(h, 0, 1), dqn_get_losses(n <= 1).  This is
+ * per call: dqn_store_train_step (n <= 16, K = 1), dqn_act, dqn_sync_target(h, 0, 1), dqn_get_losses(n <= 1),
+ * dqn_get_loss_lagged.  This is
  * the reference's env loop (q_agent.py:174-189: _policy -> add -> _step) without a kernel launch on its path.  The
  * kernel is started on demand, leaves by itself after ~30 ms without a command (state written back), and any other
  * entry point ends the session first.  While it is resident the handle's stream is occupied. */
@@ -202,6 +203,11 @@ DQN_API int dqn_train_step_device_idx(dqn_handle* h, int32_t agent_begin, int32_
                               const int64_t* idx_dev);
 /* Loss of the most recent `n` train steps of `agent` (oldest first), host pointer. */
 DQN_API int dqn_get_losses(dqn_handle* h, int32_t agent, int32_t n, float* loss_out, int64_t* train_steps_out);
+/* Loss of the train step `lag` (0 or 1) steps before the most recent one; lag 0 == dqn_get_losses(h, agent, 1, ...).
+ * Waits for THAT step only: in session mode the most recent step may still be in flight (the resident kernel takes two
+ * commands, one per slot), so an env loop (q_agent.py:174-189) can publish step i + 1 and then read step i's loss --
+ * every loss is read, one step behind -- and the device never waits for the host between two steps. */
+DQN_API int dqn_get_loss_lagged(dqn_handle* h, int32_t agent, int32_t lag, float* loss_out);
 
 /* Agent._update_target_model (q_agent.py:143-144): theta^- := theta for agents in the range. */
 DQN_API int dqn_sync_target(dqn_handle* h, int32_t agent_begin, int32_t agent_end);

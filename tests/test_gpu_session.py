@@ -98,6 +98,46 @@ def test_session_survives_idle_timeouts_and_unserved_calls():
         dqn_b200.DqnEngine(9, 4, 100, 8, 0.9, dqn_b200.adam(1e-3), n_agents=2, session=True)   # single-agent handles only
 
 
+def test_two_commands_in_flight_lagged_loss():
+    """The pipelined env loop: publish step i + 1 while step i may still run, then read step i's loss
+    (dqn_get_loss_lagged).  Losses, parameters, moments and ring must equal the launch-per-call engine bit for bit; idle
+    time-outs with two commands pending and unserved calls in between must not lose a command or a loss."""
+    ref, ses = pair(seed=31)
+    rng = np.random.default_rng(7)
+    ref_losses, ses_losses = [], []
+    l0 = np.zeros(1, np.float32)
+    for it in range(200):
+        n = int(rng.integers(1, 7))
+        data = synthetic_transitions(rng, n, 9, 4, done_p=0.2)
+        store_step(ref, data, l0)
+        ref_losses.append(float(l0[0]))
+        store_step(ses, data, None)                                   # published; step it - 1 may still be running
+        if it:
+            ses_losses.append(ses.lagged_loss(0, 1))                  # loss of step it - 1
+        if it % 37 == 36:
+            time.sleep(0.08)                                          # resident kernel leaves with a command answered but not collected
+        if it == 90:
+            st = rng.standard_normal(9).astype(np.float32)
+            assert ref.act(st) == ses.act(st)                         # a command that drains both slots
+        if it == 120:
+            ref.sync_target(); ses.sync_target()
+        if it == 150:
+            ses.train_steps(2); ref.train_steps(2)                    # not served by the session: ends it, lagged loss falls back to the ring
+            ref_losses.append(None); ref_losses.append(float(ref.last_loss()))
+            ses_losses.append(None); ses_losses.append(ses.lagged_loss(0, 1))
+            ses_losses.append(float(ses.last_loss()))
+    ses_losses.append(float(ses.last_loss()))
+    # drop the two bookkeeping entries around the K = 2 launch (its first step's loss is only in the ring)
+    ref_seq = [x for x in ref_losses if x is not None]
+    ses_seq = [x for x in ses_losses if x is not None]
+    assert ref.lagged_loss(0, 1) == ses.lagged_loss(0, 1)
+    assert ref.train_step_count() == ses.train_step_count() == 202
+    same_state(ref, ses)
+    assert len(ref_seq) >= 200
+    assert ses_seq[:150] == ref_seq[:150]
+    assert ses_seq[-40:] == ref_seq[-40:]
+
+
 def test_session_large_payloads():
     """D = 16 (160-byte records) and up to 16 adds per step: 640 payload units, i.e. several read rounds beyond the 128
     units that ride along with the doorbell poll; A = 7, B = 130 (three tiles) for good measure."""
