@@ -50,7 +50,7 @@ constexpr int NPC = 4;            // slice parameters per thread: one 16-byte ch
 
 struct CLay {
   int pW2, pWh, PS, SL;
-  int oW, oWt, oG, oGin, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oScr, oMeta, oDummy, oRed, oCmd, oBar, oStage, total;
+  int oW, oWt, oG, oGin, oX, oH1, oH2, oDh2T, oDh2R, oDh1T, oDhdT, oScr, oMeta, oDummy, oRed, oCmd, oBar, oStage, oAct, total;
 };
 
 __host__ __device__ inline CLay make_clayout(int D, int recw) {
@@ -79,6 +79,7 @@ __host__ __device__ inline CLay make_clayout(int D, int recw) {
   L.oCmd = o; o += 8;
   L.oBar = o; o += 4;                     // two mbarriers: [0] peers' gradient slices have landed, [1] peers' weight slices have landed
   L.oStage = o; o += R * recw;
+  L.oAct = o; o += kMaxD;                 // session: the state of an ACT command (the record staging buffer may hold a speculative gather)
   L.total = o;
   return L;
 }
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   volatile unsigned long long* const CmdWord = reinterpret_cast<volatile unsigned long long*>(sm + L.oCmd);   // session: (seq << 16 | op << 8 | n), written by rank 0
   volatile int* const Cmd = reinterpret_cast<volatile int*>(sm + L.oCmd + 2);                                // session: op, n for the whole CTA
   float* const Stage = sm + L.oStage;
+  float* const ActS = sm + L.oAct;
   t16::Bufs tb;                         // the 16-row tile code (tile16.cuh) works on these buffers
   tb.W = W; tb.Wt = Wt; tb.G = G; tb.X = X; tb.H1 = H1; tb.H2 = H2; tb.Dh2T = Dh2T; tb.Dh2R = Dh2R; tb.Dh1T = Dh1T; tb.DhdT = DhdT;
   tb.Scr = Scr; tb.Meta = Meta; tb.Red = Red; tb.pW2 = L.pW2; tb.pWh = L.pWh; tb.D = D;
@@ -260,14 +262,17 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     udst[q] = o;
   }
 
+  long long my_slot = -1;        // ring slot of the row this thread gathered last (threads 0..63)
   auto prefetch = [&](int kstep, int tile) {
     if (t < 4 * R) {
       const int i = tile * BT + rank * R + urow;
       float* dst = Stage + urow * recw;
+      my_slot = -1;
       if (i < B) {
         long long slot;
         if (args.idx) slot = args.idx[((size_t)sel * args.K + kstep) * B + i];
         else slot = philox_index(args.seed, args.agent_id_base + agent, step0 + kstep, i, size);
+        my_slot = slot;
         const uint32_t* src = ring + slot * recw;
         for (int c = ul4; c < cpr; c += 4) cp_async16(dst + 4 * c, src + 4 * c);
         if (args.taps.enabled && ul4 == 0 && args.taps.indices) args.taps.indices[i] = slot;
@@ -296,6 +301,37 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
   // its doorbell and first 128 payload units at the tail of a step, under the all-gather, and looks at them first.
   unsigned long long pre_w = 0ull, pre_u[4] = {0ull, 0ull, 0ull, 0ull};
   bool have_pre = false;
+  // Speculative gather: once the ring is full its size no longer depends on the next command, so the NEXT step's minibatch
+  // indices are known before that command arrives.  The rows are gathered at the tail of a step, under the all-gather and
+  // the command intake; when the command is there, a row whose slot its add()s overwrote is gathered again.
+  bool spec = false;
+  // payload of command `w` (polling warp of rank 0): STEP = its n records into the ring (ReplayBuffer.add x n,
+  // replay_buffer.py:58-65), ACT = the state into shared memory; units whose stamp is not the command's are read again
+  auto intake = [&](unsigned long long w, const unsigned long long (&u)[4], unsigned long long seq) {
+    volatile unsigned long long* const units = sess->stamped[seq & 1];
+    const int wop = (int)((w >> 8) & 0xff), wn = (int)(w & 0xff);
+    const int need = wop == kOpStep ? wn * recw : (wop == kOpAct ? D : 0);
+    for (int base = 0; base < need; base += 128) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = base + lane + 32 * q;
+        if (idx < need) {
+          unsigned long long x = base == 0 ? u[q] : ld_sys_u64(&units[idx]);
+          while ((uint32_t)(x >> 32) != (uint32_t)seq) x = ld_sys_u64(&units[idx]);
+          if (wop == kOpStep) {
+            const int i = idx / recw, c = idx - i * recw;
+            ring[(size_t)((rc + i) % args.dims.N) * recw + c] = (uint32_t)x;
+          } else {
+            ActS[idx] = __uint_as_float((uint32_t)x);
+          }
+        }
+      }
+    }
+    __threadfence();                       // the records are in the ring before any CTA is told about the step
+    __syncwarp();
+  };
+  unsigned long long early_w = 0ull;       // a STEP command whose records went into the ring under the previous step's all-gather
+  bool early_done = false;
   volatile unsigned long long* CmdWordR[CS];
 #pragma unroll
   for (int c = 0; c < CS; ++c) CmdWordR[c] = cluster.map_shared_rank(const_cast<unsigned long long*>(CmdWord), c);
@@ -311,10 +347,11 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
           // doorbell shows the command its payload -- up to 128 words: 5 records at D <= 10, or the state of an ACT --
           // has arrived in the same PCIe round trip; a unit whose stamp is not the command's is re-read.
           if (warp == 0) {
-            unsigned long long w = 0ull, u[4];
+            unsigned long long w = early_w, u[4];
             const long long c0 = clock64();
             volatile unsigned long long* const door = &sess->doorbell[next_seq & 1];      // the command's slot: seq % 2
             volatile unsigned long long* const units = sess->stamped[next_seq & 1];
+            if (!early_done) {
             for (;;) {
               if (have_pre) {
                 w = pre_w;
@@ -332,26 +369,10 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
               w = __shfl_sync(0xffffffffu, w, 0);
               if ((w >> 16) == next_seq) break;
             }
-            const int wop = (int)((w >> 8) & 0xff), wn = (int)(w & 0xff);
-            const int need = wop == kOpStep ? wn * recw : (wop == kOpAct ? D : 0);
-            for (int base = 0; base < need; base += 128) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int idx = base + lane + 32 * q;
-                if (idx < need) {
-                  unsigned long long x = base == 0 ? u[q] : ld_sys_u64(&units[idx]);
-                  while ((uint32_t)(x >> 32) != (uint32_t)next_seq) x = ld_sys_u64(&units[idx]);
-                  if (wop == kOpStep) {            // ReplayBuffer.add x n (replay_buffer.py:58-65)
-                    const int i = idx / recw, c = idx - i * recw;
-                    ring[(size_t)((rc + i) % args.dims.N) * recw + c] = (uint32_t)x;
-                  } else {
-                    Stage[idx] = __uint_as_float((uint32_t)x);
-                  }
-                }
-              }
+            intake(w, u, next_seq);
             }
-            __threadfence();                       // the records are in the ring before any CTA is told about the step
-            __syncwarp();
+            early_done = false;
+            const int wop = (int)((w >> 8) & 0xff), wn = (int)(w & 0xff);
             if (lane == 0) {
 #pragma unroll
               for (int c = 0; c < CS; ++c) *CmdWordR[c] = w;
@@ -372,8 +393,8 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         next_seq += (unsigned long long)Cmd[2];
         __syncthreads();
         if (op == kOpAct) {              // compute_action (q_learning_functions.py:67-73) from the resident weights
-          if (rank == 0 && warp == 0) {          // the state is already in Stage (stamped payload)
-            const int best = warp_greedy_action(W, D, A, Stage, nullptr);
+          if (rank == 0 && warp == 0) {          // the state is already in shared memory (stamped payload)
+            const int best = warp_greedy_action(W, D, A, ActS, nullptr);
             if (lane == 0) st_sys_u64(&sess->response[next_seq & 1], (next_seq << 32) | (unsigned long long)(uint32_t)best);
           }
           __syncthreads();
@@ -389,9 +410,25 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         }
       }
       if (op != kOpStep) break;          // EXIT (or the idle time-out)
+      const long long rc_old = rc;
       rc += n;                           // rank 0 has put the n records into the ring (above)
       size = rc < args.dims.N ? rc : args.dims.N;
-      prefetch(kstep, 0);
+      if (spec) {                        // rows gathered ahead: only those in the window [rc_old, rc_old + n) (mod N) are stale
+        spec = false;
+        if (t < 4 * R && my_slot >= 0) {
+          long long dlt = my_slot - rc_old % args.dims.N;
+          if (dlt < 0) dlt += args.dims.N;
+          if (dlt < n) {
+            cp_async_wait_all();         // the stale copy has landed before the fresh one is issued
+            const uint32_t* src = ring + my_slot * recw;
+            float* dst = Stage + urow * recw;
+            for (int c = ul4; c < cpr; c += 4) cp_async16(dst + 4 * c, src + 4 * c);
+          }
+        }
+        cp_async_commit();
+      } else {
+        prefetch(kstep, 0);
+      }
     }
     const bool gather_after = serve || kstep + 1 < args.K;      // the last step of a K-step launch needs no all-gather
     if (t == 0) {
@@ -436,6 +473,13 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     // ---- reduce-scatter (push): slice c of this CTA's partial gradient -> slot of CTA c ----
     if (t < CS && t != rank)
       bulk_push(map_to_rank(smem_addr(Gin + (rank - (rank > t ? 1 : 0)) * L.SL), t), smem_addr(G + t * L.SL), slice_bytes(t), map_to_rank(bar_g, t));
+    if (serve && rank == 0 && warp == 0) {   // the NEXT command's doorbell and first payload units: loads in flight under the exchange and Adam
+      const unsigned long long ns = next_seq + 1;
+      if (lane == 0) pre_w = ld_sys_u64(&sess->doorbell[ns & 1]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pre_u[q] = ld_sys_u64(&sess->stamped[ns & 1][lane + 32 * q]);
+      have_pre = true;
+    }
     mbar_wait(bar_g, par_g);                 // the three peers' slices of MY slice have landed
     par_g ^= 1u;
     if (kstep == args.K - 1) PHASE_CLOCK(5);
@@ -475,12 +519,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     }
     if (serve) {
       ++next_seq;
-      if (rank == 0 && warp == 0) {          // loads in flight under the all-gather; consumed by the poll at the top of the loop
-        if (lane == 0) pre_w = ld_sys_u64(&sess->doorbell[next_seq & 1]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) pre_u[q] = ld_sys_u64(&sess->stamped[next_seq & 1][lane + 32 * q]);
-        have_pre = true;
-      }
+      if (rc >= args.dims.N && !args.idx) { prefetch(kstep + 1, 0); spec = true; }   // (the staging buffer was unpacked long ago)
     }
     if (gather_after) {
       // ---- all-gather (push): my new slice -> the three peers' replicas; wait for theirs ----
@@ -488,6 +527,15 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
       __syncthreads();                       // the whole slice is written
       if (t < CS && t != rank)
         bulk_push(map_to_rank(smem_addr(W + rank * L.SL), t), smem_addr(W + rank * L.SL), slice_bytes(rank), map_to_rank(bar_w, t));
+      if (serve && rank == 0 && warp == 0 && have_pre) {
+        // If the next command is already there and is a train step, its records go into the ring now, while the weight slices
+        // travel (this step's gather finished long ago; a speculatively gathered row they overwrite is gathered again).
+        const unsigned long long w = __shfl_sync(0xffffffffu, pre_w, 0);
+        if ((w >> 16) == next_seq && ((w >> 8) & 0xff) == kOpStep) {
+          intake(w, pre_u, next_seq);
+          early_w = w; early_done = true; have_pre = false;
+        }
+      }
       mbar_wait(bar_w, par_w);
       par_w ^= 1u;
       // Only now may the partial gradient be cleared: a bulk copy signals completion at its DESTINATION, so the sender
@@ -497,6 +545,7 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     }
   }  // steps
   PHASE_CLOCK(6);
+  cp_async_wait_all();                     // (a speculative gather that no command consumed)
   // No CTA may leave while a bulk copy still reads its shared memory or a peer may still push into it: every push of
   // the last step has completed once all four CTAs are past their last mbarrier wait.
   cluster.sync();
