@@ -617,6 +617,7 @@ def run_population(args, ctx):
     del pop, eng
     if ctx.rank != 0:
         return None
+    pop_kernel = "dqn_train_fused_kernel<4>" if args.step_kernel == "cta" else "dqn_train_tc_kernel<4>"
     mean_b = float(np.mean([h["batch_size"] for h in hp_all]))
     two_tile = float(np.mean([h["batch_size"] > 64 for h in hp_all]))
     value = n_global * steps / rep_s
@@ -633,14 +634,15 @@ def run_population(args, ctx):
         "config": {"workload": "configs[2]: population of %d independent sweep agents, one CTA per agent, sharded over ranks, no collective" % n_global,
                    "obs_dim": D, "num_actions": A, "hidden": [32, 64], "ring_slots_per_agent": ring, "mean_batch": mean_b,
                    "agents_with_batch_over_64": two_tile, "agents_per_rank": n_local, "tiles_on_busiest_rank": max_tiles,
-                   "optimizer": "adam(1e-4)", "steps_per_launch": kpl, "l2": "rings total %.1f GB per rank >> L2; flushed before every rep" % (n_local * ring * 96 / 1e9)},
+                   "optimizer": "adam(1e-4)", "steps_per_launch": kpl,
+                   "step_kernel": "cta (fp32 FFMA)" if args.step_kernel == "cta" else "cta_tc (layer-2 products on tcgen05 3xTF32, 512 threads)", "l2": "rings total %.1f GB per rank >> L2; flushed before every rep" % (n_local * ring * 96 / 1e9)},
         "clocks": clocks, "gpu_launches": reps * (steps // kpl),
         "timing": {"reps": reps, "steps_per_rep": steps, "statistic": "median rep, max over ranks", "timed_region_s": timed_s},
         "replay_samples_per_sec": value * mean_b, "param_digest_sum": digest_sum,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * ctx.world, "unit": "GB/s", "frac": gbs / (peak * ctx.world),
-                     "traffic": traffic_from_profile("dqn_train_fused_kernel<4>/population", "agent_steps_per_launch", n_local * kpl),
-                     "kernel": "dqn_train_fused_kernel<4>", "peak_source": peak_src,
-                     "note": "compute-bound on the fp32 pipe, not HBM: see fp32",
+                     "traffic": traffic_from_profile(pop_kernel + "/population", "agent_steps_per_launch", n_local * kpl),
+                     "kernel": pop_kernel, "peak_source": peak_src,
+                     "note": "latency / issue-bound on the SM (fp32 pipe + tcgen05 round trips), not HBM: see fp32 (algorithmic flops, whichever pipe runs them)",
                      "fp32": {"achieved_gflops": flops, "ffma_peak_gflops": fp32_peak, "frac": flops / fp32_peak}}}
 
 
