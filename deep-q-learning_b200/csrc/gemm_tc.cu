@@ -676,10 +676,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                : "memory");
 }
 
-template <int EPI>
+// HEAD (with EPI = bias + relu): the epilogue also evaluates the dueling head's partial sums over the tile's 128 columns --
+// hp[(column tile * M + row) * 8 + c] = sum_j relu(...)[row][j] * Wh[j][c], c = 0 (V), 1..A (advantages) -- so that h2 is
+// never read back for the head (dddqn.py:29-31; mlp_large.cu sums the column tiles in order), and only rows < store_rows
+// of C are written at all (h2 of the s' rows feeds nothing but the head).
+template <int EPI, bool HEAD>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, float* __restrict__ C, int ldc,
-                const float* __restrict__ aux, int ldaux, int K) {
+                const float* __restrict__ aux, int ldaux, int K, const float* __restrict__ head_w, int head_a, float* __restrict__ hp,
+                int store_rows) {
   // PERSISTENT: cluster c of NC walks the 256 x 128 tiles t = c, c + NC, ... with t = (row pair) * (N / 128) + (column tile), so
   // the clusters running at the same time share rows of A (L2 hits) and the k-stage / accumulator-chunk counters simply
   // run on across tiles: while the epilogue warps drain the last chunk of a tile and store C, the TMA thread, the
@@ -694,6 +699,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   uint64_t* const full = bars, *const empty = bars + kStages, *const tfull = bars + 2 * kStages, *const tempty = bars + 2 * kStages + 2;
   uint64_t* const raw_full = bars + 2 * kStages + 4, *const raw_empty = raw_full + kRawStages;
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kRawStages);
+  float* const headw_s = reinterpret_cast<float*>(tiles + kStages * kStageBytes + 512);     // HEAD: [128 columns][8] head weights of the tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -824,6 +830,25 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[b]), 0u);
       }
       float* crow = C + (size_t)m * ldc + n0;
+      if constexpr (HEAD) {
+        // the tile's head weights [column][V, A_1..A_a, 0..] into shared memory (the four epilogue warps, named barrier 1)
+        asm volatile("bar.sync 1, 128;" ::: "memory");                     // everybody is done with the previous tile's copy
+        {
+          const int j = tid - 128;
+          const float* wv = head_w;                                         // flat layout: Wv [N] | bv | Wa [N][a] | ba [a]
+          const float* wa = head_w + N + 1;
+          float w8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) w8[c] = 0.f;
+          w8[0] = wv[n0 + j];
+          for (int c = 0; c < head_a; ++c) w8[1 + c] = wa[(size_t)(n0 + j) * head_a + c];
+          *reinterpret_cast<float4*>(headw_s + 8 * j) = make_float4(w8[0], w8[1], w8[2], w8[3]);
+          *reinterpret_cast<float4*>(headw_s + 8 * j + 4) = make_float4(w8[4], w8[5], w8[6], w8[7]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const bool store = !HEAD || m < store_rows;
 #pragma unroll
       for (int j = 0; j < TN; j += 4) {
         float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -834,7 +859,21 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           const float4 h = *reinterpret_cast<const float4*>(aux + (size_t)m * ldaux + n0 + j);
           v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
         }
-        *reinterpret_cast<float4*>(crow + j) = v;
+        if constexpr (HEAD) {
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 w0 = *reinterpret_cast<const float4*>(headw_s + 8 * (j + e)), w1 = *reinterpret_cast<const float4*>(headw_s + 8 * (j + e) + 4);
+            hacc[0] = fmaf(vv[e], w0.x, hacc[0]); hacc[1] = fmaf(vv[e], w0.y, hacc[1]); hacc[2] = fmaf(vv[e], w0.z, hacc[2]); hacc[3] = fmaf(vv[e], w0.w, hacc[3]);
+            hacc[4] = fmaf(vv[e], w1.x, hacc[4]); hacc[5] = fmaf(vv[e], w1.y, hacc[5]); hacc[6] = fmaf(vv[e], w1.z, hacc[6]); hacc[7] = fmaf(vv[e], w1.w, hacc[7]);
+          }
+        }
+        if (store) *reinterpret_cast<float4*>(crow + j) = v;
+      }
+      if constexpr (HEAD) {
+        float* dst = hp + ((size_t)(t % ntn) * M + m) * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(hacc[4], hacc[5], hacc[6], hacc[7]);
       }
     }
   }
@@ -873,13 +912,13 @@ bool make_map_2d(CUtensorMap* map, const float* base, int rows, int cols, int ld
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPI>
+template <int EPI, bool HEAD = false>
 cudaError_t launch_tc3(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       const float* aux, int ldaux) {
-  constexpr int smem = kRawStages * kRawBytes + 4 * (2 * kTileMN2) + 512;     // raw ring | UMMA B stages | barriers
+                       const float* aux, int ldaux, const float* head_w = nullptr, int head_a = 0, float* hp = nullptr, int store_rows = 0) {
+  constexpr int smem = kRawStages * kRawBytes + 4 * (2 * kTileMN2) + 512 + (HEAD ? 128 * 8 * 4 : 0);   // raw ring | UMMA B stages | barriers | head weights
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc3_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc3_kernel<EPI, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -905,7 +944,7 @@ cudaError_t launch_tc3(cudaStream_t st, int M, int N, int K, const float* A, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc3_kernel<EPI>, mapA, mapB, M, N, C, ldc, aux, ldaux, K);
+  return cudaLaunchKernelEx(&cfg, gemm_tc3_kernel<EPI, HEAD>, mapA, mapB, M, N, C, ldc, aux, ldaux, K, head_w, head_a, hp, store_rows);
 }
 
 // =====================================================================================================================
@@ -1142,6 +1181,13 @@ cudaError_t launch_tc(cudaStream_t st, int M, int N, int K, const float* A, int 
 }
 
 }  // namespace
+
+cudaError_t lb_gemm_tc_nn_head(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                               const float* bias, const float* head_w, int head_a, float* hp, int store_rows) {
+  if (M % (2 * TM) || N % TN || K % kChunkK || lda % 4 || ldb % 4 || (((uintptr_t)A | (uintptr_t)B) & 15) || encode_tiled_fn() == nullptr)
+    return cudaErrorNotSupported;
+  return launch_tc3<kEpiBiasRelu, true>(st, M, N, K, A, lda, B, ldb, C, ldc, bias, 0, head_w, head_a, hp, store_rows);
+}
 
 cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                        float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws) {

@@ -57,6 +57,11 @@ cudaError_t lb_gemm_ffma(cudaStream_t st, int kind, int M, int N, int K, const f
                          float* C, int ldc, const float* aux, int ldaux, int splitk);
 cudaError_t lb_gemm_tc(cudaStream_t st, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                        float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws);
+// h2 = relu(A . B + bias) with the dueling head's partial sums evaluated in the epilogue (gemm_tc.cu: gemm_tc3_kernel<.., HEAD>):
+// hp[(column tile * M + row) * 8 + c]; only rows < store_rows of C are written.  cudaErrorNotSupported when the shape / alignment
+// does not fit the SM-pair TMA kernel (the caller falls back to the separate head pass).
+cudaError_t lb_gemm_tc_nn_head(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                               const float* bias, const float* head_w, int head_a, float* hp, int store_rows);
 // dispatcher (gemm_mode: kGemmModeFFMA / kGemmModeTC3xTF32)
 cudaError_t lb_gemm(cudaStream_t st, int gemm_mode, int kind, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                     float* C, int ldc, const float* aux, int ldaux, int splitk, const LbWorkspace& ws);

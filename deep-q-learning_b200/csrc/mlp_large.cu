@@ -295,6 +295,32 @@ lb_head_kernel(const float* __restrict__ H2, const float* __restrict__ theta, co
   }
 }
 
+// The same head from the partial sums the tensor-core GEMM's epilogue left behind (lb_gemm_tc_nn_head): hp1 covers the 2B theta
+// rows, hp2 the B theta^- rows, each [column tile][row][8]; the tiles are summed in order, then bias and the dueling combine.
+__global__ void __launch_bounds__(256)
+lb_head_reduce_kernel(const float* __restrict__ hp1, const float* __restrict__ hp2, const float* __restrict__ theta,
+                      const float* __restrict__ theta_t, float* __restrict__ Q, int B, int H2n, int A, int offWv, int ntn) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= 3 * B) return;
+  const bool tm = row >= 2 * B;
+  const float* hp = tm ? hp2 : hp1;
+  const int M = tm ? B : 2 * B, r = tm ? row - 2 * B : row;
+  const float* bv = (tm ? theta_t : theta) + offWv + H2n;
+  const float* ba = bv + 1 + (size_t)H2n * A;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int tn = 0; tn < ntn; ++tn) {
+    const float4 p0 = *reinterpret_cast<const float4*>(hp + ((size_t)tn * M + r) * 8), p1 = *reinterpret_cast<const float4*>(hp + ((size_t)tn * M + r) * 8 + 4);
+    a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w; a[4] += p1.x; a[5] += p1.y; a[6] += p1.z; a[7] += p1.w;
+  }
+  const float val = a[0] + bv[0];
+  float msum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxA; ++j) if (j < A) { a[1 + j] += ba[j]; msum += a[1 + j]; }
+  const float mean = msum / (float)A;
+#pragma unroll
+  for (int j = 0; j < kMaxA; ++j) if (j < A) Q[(size_t)row * A + j] = val + a[1 + j] - mean;
+}
+
 // ------------------------------------------------------------------------------------------------
 // targets + Huber + d(head)   (q_learning_functions.py:55-59, :35-36).  One thread per sample.
 // dhd[i][0] = dV, dhd[i][1+j] = dAdv_j;  per-block partial sums of loss and of dhd columns (-> d head bias).
@@ -511,11 +537,35 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     lb_layer1_kernel<<<grid, 256, smem, st>>>(ws.s, ws.s2, ws.theta, ws.theta_t, ws.H1, B, D, H1n);
     LBCHK(cudaGetLastError());
   }
-  LBCHK(lb_gemm(st, gemm_mode, kGemmNN_BiasRelu, 2 * B, H2n, H1n, ws.H1, H1n, ws.theta + offW2, H2n, ws.H2, H2n, ws.theta + offb2, 0, 1, ws));
-  LBCHK(lb_gemm(st, gemm_mode, kGemmNN_BiasRelu, B, H2n, H1n, ws.H1 + (size_t)2 * B * H1n, H1n, ws.theta_t + offW2, H2n,
-                ws.H2 + (size_t)2 * B * H2n, H2n, ws.theta_t + offb2, 0, 1, ws));
-  lb_head_kernel<<<(3 * B / kHeadRows + 7) / 8, 256, 0, st>>>(ws.H2, ws.theta, ws.theta_t, ws.Q, B, H2n, A, offWv);
-  LBCHK(cudaGetLastError());
+  bool head_done = false;
+  static const bool fuse_head = [] { const char* e = getenv("DQN_B200_LB_FUSE_HEAD"); return !e || atoi(e) != 0; }();   // experiment knob
+  if (gemm_mode == kGemmModeTC3xTF32 && fuse_head) {
+    // The head rides in the epilogue of the two h2 products: h2 (805 MB at the BASELINE shape) is not read back, and the rows
+    // that feed nothing but the head (s' under theta and theta^-) are not even written.  Partial sums per 128-column tile go
+    // through the dH2 buffer (free until the backward pass): 3B x H2/128 x 8 floats.
+    const int ntn = H2n / 128;
+    float* hp1 = ws.dH2;
+    float* hp2 = hp1 + (size_t)ntn * 2 * B * 8;
+    cudaError_t e = lb_gemm_tc_nn_head(st, 2 * B, H2n, H1n, ws.H1, H1n, ws.theta + offW2, H2n, ws.H2, H2n, ws.theta + offb2,
+                                       ws.theta + offWv, A, hp1, B);
+    if (e == cudaSuccess)
+      e = lb_gemm_tc_nn_head(st, B, H2n, H1n, ws.H1 + (size_t)2 * B * H1n, H1n, ws.theta_t + offW2, H2n, ws.H2 + (size_t)2 * B * H2n, H2n,
+                             ws.theta_t + offb2, ws.theta_t + offWv, A, hp2, 0);
+    if (e == cudaSuccess) {
+      lb_head_reduce_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(hp1, hp2, ws.theta, ws.theta_t, ws.Q, B, H2n, A, offWv, ntn);
+      LBCHK(cudaGetLastError());
+      head_done = true;
+    } else if (e != cudaErrorNotSupported) {
+      return e;
+    }
+  }
+  if (!head_done) {
+    LBCHK(lb_gemm(st, gemm_mode, kGemmNN_BiasRelu, 2 * B, H2n, H1n, ws.H1, H1n, ws.theta + offW2, H2n, ws.H2, H2n, ws.theta + offb2, 0, 1, ws));
+    LBCHK(lb_gemm(st, gemm_mode, kGemmNN_BiasRelu, B, H2n, H1n, ws.H1 + (size_t)2 * B * H1n, H1n, ws.theta_t + offW2, H2n,
+                  ws.H2 + (size_t)2 * B * H2n, H2n, ws.theta_t + offb2, 0, 1, ws));
+    lb_head_kernel<<<(3 * B / kHeadRows + 7) / 8, 256, 0, st>>>(ws.H2, ws.theta, ws.theta_t, ws.Q, B, H2n, A, offWv);
+    LBCHK(cudaGetLastError());
+  }
   const int nblk = (B + 255) / 256;
   lb_targets_kernel<<<nblk, 256, 0, st>>>(ws.Q, ws.a, ws.r, ws.done, ws.dhd, ws.partial, B, A, gamma, inv_global_batch, loss_kind, taps);
   LBCHK(cudaGetLastError());
