@@ -534,6 +534,12 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
         if ((w >> 16) == next_seq && ((w >> 8) & 0xff) == kOpStep) {
           intake(w, pre_u, next_seq);
           early_w = w; early_done = true; have_pre = false;
+          // ... and the peers are told right away (they look at the word at the top of their loop, after their own wait below;
+          // everything of THIS step they could disturb -- the gradient slots -- was consumed by the Adam above)
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 1; c < CS; ++c) *CmdWordR[c] = w;
+          }
         }
       }
       mbar_wait(bar_w, par_w);
