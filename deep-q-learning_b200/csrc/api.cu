@@ -2,6 +2,8 @@
 // No compute happens on the host; every entry point either moves bytes or launches a kernel.
 // (Session mode lives in api_session.cu, the device-side episode loop in api_episode.cu.)
 #include "handle.h"
+#include <algorithm>
+#include <vector>
 
 using namespace dqn;
 
@@ -151,8 +153,11 @@ DQN_API int dqn_create(const dqn_config* cfg, dqn_handle** out) {
   if (e != cudaSuccess) { if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaMallocHost failed"); }
   h->bounce = h->pinned + kBounceOff;
   h->mailbox = nullptr; h->mailbox_dev = nullptr;
-  e = cudaHostAlloc((void**)&h->mailbox, sizeof(unsigned long long) * cfg->n_agents, cudaHostAllocMapped);
+  // + [n_agents] int: the launch order of the population kernel (costliest agents first), read once per CTA
+  e = cudaHostAlloc((void**)&h->mailbox, (sizeof(unsigned long long) + sizeof(int)) * cfg->n_agents, cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->mailbox_dev, (void*)h->mailbox, 0);
+  h->order = (int*)(h->mailbox + cfg->n_agents); h->order_dev = (const int*)(h->mailbox_dev + cfg->n_agents);
+  h->order_begin = h->order_end = -1;
   if (e != cudaSuccess) { cudaFreeHost(h->pinned); if (h->own_arena) cudaFree(h->arena); delete h; return fail(DQN_E_NOMEM, "cudaHostAlloc(mapped) failed"); }
   memset((void*)h->mailbox, 0, sizeof(unsigned long long) * cfg->n_agents);
   h->sess = nullptr; h->sess_dev = nullptr;
@@ -315,7 +320,7 @@ DQN_API int dqn_set_hparams(dqn_handle* h, int32_t agent, const dqn_hparams* hp)
   AgentCtl& c = h->hctl[agent];
   if (hp->batch_size > DQN_MAX_BATCH || hp->batch_size == 0) return fail(DQN_E_INVALID, "batch_size must be in [1,1024]");
   if (hp->gamma == hp->gamma && hp->gamma >= 0.f) c.gamma = hp->gamma;
-  if (hp->batch_size > 0) c.batch_size = hp->batch_size;
+  if (hp->batch_size > 0) { c.batch_size = hp->batch_size; h->order_begin = h->order_end = -1; }
   if (hp->lr == hp->lr && hp->lr >= 0.f) c.lr = hp->lr;
   if (hp->b1 == hp->b1 && hp->b1 >= 0.f) c.b1 = hp->b1;
   if (hp->b2 == hp->b2 && hp->b2 >= 0.f) c.b2 = hp->b2;
@@ -557,7 +562,23 @@ int train_common(dqn_handle* h, int b, int e, int K, const long long* idx_dev, d
   if (ist && !cluster) return fail(DQN_E_INVALID, "internal: inline store needs the cluster kernel");
   if (cluster) CU(launch_train_cluster(h->stream, ta, ist));
   else if (h->step_kernel == DQN_STEP_CTA) CU(launch_train_fused(h->stream, ta));
-  else CU(launch_train_tc(h->stream, ta));                                     // AUTO / CTA_TC: tensor-core form
+  else {                                                                       // AUTO / CTA_TC: tensor-core form
+    if (n_sel > h->sm_count && !idx_dev) {
+      // more agents than SMs = several waves of one-agent CTAs: start the costly agents (more 64-row tiles, a tail tile) first
+      // so that the last wave is made of short ones.  Agents are independent -- the order changes no result.
+      if (h->order_begin != b || h->order_end != e) {
+        CU(cudaStreamSynchronize(h->stream));                                  // an earlier launch may still be reading the old order
+        auto cost = [&](int s) { const int B = h->hctl[b + s].batch_size; return B <= 64 ? 10 : B <= 80 ? 14 : 10 * ((B + 63) / 64); };
+        std::vector<int> ord(n_sel);
+        for (int s = 0; s < n_sel; ++s) ord[s] = s;
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return cost(x) > cost(y); });
+        memcpy(h->order, ord.data(), sizeof(int) * n_sel);
+        h->order_begin = b; h->order_end = e;
+      }
+      ta.order = h->order_dev;
+    }
+    CU(launch_train_tc(h->stream, ta));
+  }
   if (ist) h->hctl[b].ring_counter += ist->n;
   for (int ag = b; ag < e; ++ag) {
     if (gate && !h->hep[ag].pending_train) continue;      // the device gate is closed for this agent: it does not step

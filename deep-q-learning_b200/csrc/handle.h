@@ -70,6 +70,9 @@ struct dqn_handle {
   uint8_t* bounce;              // pinned + kBounceOff
   volatile unsigned long long* mailbox;   // mapped pinned host memory, [n_agents]: (train_steps << 32) | loss bits of each
   unsigned long long* mailbox_dev;        //   agent's last launch (one 8-byte store by the kernel); device alias
+  int* order;                             // mapped pinned, behind the mailbox: launch order of the population kernel for the agent
+  const int* order_dev;                   //   range [order_begin, order_end) (-1: stale; rebuilt when batch sizes change)
+  int order_begin, order_end;
   cudaEvent_t slot_ev[dqn::kSlots];  // completion of the H2D copy that last used each pinned store slot
   int slot_next;
   std::vector<dqn::AgentCtl> hctl;   // host mirror of the per-agent control blocks

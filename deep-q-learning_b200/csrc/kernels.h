@@ -45,6 +45,7 @@ struct TrainArgs {
                                       //   of the launch's last step, one 8-byte store -- the host can poll it
   const long long* idx;       // device i64 [n_sel][K][B] or nullptr (Philox)
   const EpisodeCtl* gate;     // nullptr, or per-agent episode state: only agents with gate[agent].train_flag step
+  const int* order;           // nullptr, or (population kernel) [n_sel]: CTA b runs selected agent order[b] -- costliest first
   SessionCtl* sess;           // nullptr, or (cluster kernel, one agent) the session block: serve commands until EXIT / idle
   unsigned long long sess_first_seq;   // sequence number of the first command this launch serves
   Dims dims;
