@@ -98,7 +98,10 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
-__device__ __forceinline__ uint32_t pos_bit(float v) { return min(__float_as_uint(v), 1u); }   // v >= +0: 1 iff v > 0
+// relu' bits of a run of n values v >= +0, two instructions per value: m = (m << 1) | (v > 0) -- the top bit of 0 - bits(v) is
+// set iff bits(v) is in [1, 0x7f800000] -- then mask_finish puts value i of the run at bit i
+__device__ __forceinline__ void mask_push(uint32_t& m, float v) { m = __funnelshift_l(0u - __float_as_uint(v), m, 1); }
+__device__ __forceinline__ uint32_t mask_finish(uint32_t m, int n) { return __brev(m) >> (32 - n); }
 
 }  // namespace tcp
 }  // namespace dqn

@@ -181,7 +181,7 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
   auto prefetch = [&](int kstep, int tile) {
     const int nvalid = B - tile * BT < BT ? B - tile * BT : BT;
     if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nvalid * recw * 4));
-    if (u8 == 0) {
+    if (u8 == 0) {      // four lanes of every warp: all warps reach the MMA wait together (two whole warps doing this while 14 spin is slower)
       const int i = tile * BT + urow;
       float* dst = Stage + urow * recw;
       if (i < B) {
@@ -285,9 +285,10 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
           float a, b;
           unpack2(acc[i], a, b);
           a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
-          mask1 |= pos_bit(a) << (2 * i) | pos_bit(b) << (2 * i + 1);
+          mask_push(mask1, a); mask_push(mask1, b);
           split_tf32(a, hi[2 * i], lo[2 * i]); split_tf32(b, hi[2 * i + 1], lo[2 * i + 1]);
         }
+        mask1 = mask_finish(mask1, 8);
         tmem_st8(tmem + tlane + kA2Hi + 8u * wc, hi);
         tmem_st8(tmem + tlane + kA2Lo + 8u * wc, lo);
         if (wq < 2) {   // h1 of the s rows is also the B operand of P3 (mn = k, K = r): 4-byte stores, conflict-free (LBO = 144)
@@ -342,7 +343,7 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
           for (int e = 0; e < 4; ++e) {
             const int i = 4 * i4 + e;
             const float v = fmaxf(__uint_as_float(r0[i]) + bb[e], 0.f);
-            mask2 |= pos_bit(v) << i;
+            mask_push(mask2, v);
             if (wq < 2) H2[(16 * wc + i) * RS1 + row2] = v;
             const u64 vv = pack2(v, v);
             const u64x2 w0 = ld2x64(wh + i * HC);
@@ -351,6 +352,7 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
             if constexpr (NP > 2) { const u64x2 w1 = ld2x64(wh + i * HC + 4); ffma2(hp[2], vv, w1.lo); if constexpr (NP > 3) ffma2(hp[3], vv, w1.hi); }
           }
         }
+        mask2 = mask_finish(mask2, 16);
         {
           float* dst = HP + ((wq < 2 ? 0 : 1) * 4 + wc) * HC * BT + (row2 & 63);
 #pragma unroll

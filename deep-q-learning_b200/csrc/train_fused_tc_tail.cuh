@@ -212,22 +212,18 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
   auto prefetch = [&](int kstep, int tile) {
     const int nrows = tail ? B : (B - tile * BT < BT ? B - tile * BT : BT);
     if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * recw * 4));
-    if (u8 == 0) {
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1 && !(tail && urow < TL)) break;
-        const int row = urow + BT * pass;
-        const int i = tile * BT + row;
-        float* dst = Stage + row * recw;
-        if (i < B) {
-          long long slot;
-          if (args.idx) slot = args.idx[((size_t)sel * args.K + kstep) * B + i];
-          else slot = philox_index(args.seed, args.agent_id_base + agent, step0 + kstep, i, size);
-          bulk_load(smem_addr(dst), ring + slot * recw, (uint32_t)(recw * 4), bar);
-          if (args.taps.enabled && args.taps.indices) args.taps.indices[i] = slot;
-        } else {
-          for (int c = 0; c < cpr; ++c) st4(dst + 4 * c, 0.f, 0.f, 0.f, 0.f);
-        }
+    if (t < NR) {       // warps 0..2 (the third one half-way): one row each, rows 64..79 = tail
+      const int row = t;
+      const int i = tile * BT + row;
+      float* dst = Stage + row * recw;
+      if (i < B) {
+        long long slot;
+        if (args.idx) slot = args.idx[((size_t)sel * args.K + kstep) * B + i];
+        else slot = philox_index(args.seed, args.agent_id_base + agent, step0 + kstep, i, size);
+        bulk_load(smem_addr(dst), ring + slot * recw, (uint32_t)(recw * 4), bar);
+        if (args.taps.enabled && args.taps.indices) args.taps.indices[i] = slot;
+      } else {
+        for (int c = 0; c < cpr; ++c) st4(dst + 4 * c, 0.f, 0.f, 0.f, 0.f);
       }
     }
   };
@@ -338,9 +334,10 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
           float a, b;
           unpack2(acc[i], a, b);
           a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
-          mask1 |= pos_bit(a) << (2 * i) | pos_bit(b) << (2 * i + 1);
+          mask_push(mask1, a); mask_push(mask1, b);
           split_tf32(a, hi[2 * i], lo[2 * i]); split_tf32(b, hi[2 * i + 1], lo[2 * i + 1]);
         }
+        mask1 = mask_finish(mask1, 8);
         tmem_st8(tmem + tlane + kA2Hi + 8u * wc, hi);
         tmem_st8(tmem + tlane + kA2Lo + 8u * wc, lo);
         if (wq < 2) {   // h1 of the s rows is also the B operand of P3 (mn = k, K = r): 4-byte stores, conflict-free (LBO = 144)
@@ -380,9 +377,10 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
             float a, b;
             unpack2(acc[i], a, b);
             a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
-            mask1t |= pos_bit(a) << (2 * i) | pos_bit(b) << (2 * i + 1);
+            mask_push(mask1t, a); mask_push(mask1t, b);
             split_tf32(a, hi[2 * i], lo[2 * i]); split_tf32(b, hi[2 * i + 1], lo[2 * i + 1]);
           }
+          mask1t = mask_finish(mask1t, 8);
           tmem_st8(tmem + tlane + kA1Hi + 8u * wc, hi);
           tmem_st8(tmem + tlane + kA1Lo + 8u * wc, lo);
           if (wq == 0 && lane < TL) {      // h1 of the tail s rows: reduction index r = 64 + lane of the P3 operand, and its relu' bits
@@ -430,7 +428,7 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
             for (int e = 0; e < 4; ++e) {
               const int i = 4 * i4 + e;
               const float v = fmaxf(__uint_as_float(r0[i]) + bb[e], 0.f);
-              mask |= pos_bit(v) << i;
+              mask_push(mask, v);
               if (h2dst) h2dst[i * RS1] = v;
               const u64 vv = pack2(v, v);
               const u64x2 w0 = ld2x64(wh + i * HC);
@@ -448,7 +446,7 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
               if (2 * q + 1 <= A) hpdst[(2 * q + 1) * NR] = b;
             }
           }
-          return mask;
+          return mask_finish(mask, 16);
         };
         const float* bias = W + L.pW2 + kH1 * WS2 + 16 * wc;
         const float* wh = W + L.pWh + 16 * wc * HC;
