@@ -36,7 +36,8 @@ constexpr int RS2 = 2 * BT + 4;  // 132: row stride of X [d][s rows | s' rows]
 constexpr int RS1 = BT + 4;      // 68
 constexpr int HC = kHeadCols;
 constexpr int WS2 = kW2Stride;
-constexpr int NPT = 7;           // ceil(max packed params (3176 at D = 16) / NT)
+constexpr int NPP = 4;           // parameter PAIRS per thread: pair i of thread t = packed entries 2 (t + i NT), + 1 (3176 entries at D = 16;
+                                 // the fourth pair is only there when the agent has more than 6 NT entries)
 
 // Shared-memory B operands, K-major no-swizzle canonical layout (cute: ((8,n),(T,2)):((1T,SBO),(1,LBO)), T = 4 tf32):
 //   byte(mn, k) = (mn / 8) * SBO + (k / 4) * LBO + (mn % 8) * 16 + (k % 4) * 4        one k-step of 8 = two 16-byte chunks
@@ -125,12 +126,13 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
   const uint32_t* const ring = args.rings + (size_t)agent * args.dims.N * recw;
 
   // ---- one-time: parameters HBM -> smem / registers ---------------------------------------
-  float mreg[NPT], vreg[NPT];
+  float2 mreg[NPP], vreg[NPP];
+  const bool pair4 = L.PS > 6 * NT;    // uniform over the CTA
 #pragma unroll
-  for (int i = 0; i < NPT; ++i) {
-    const int p = t + i * NT;
-    mreg[i] = 0.f; vreg[i] = 0.f;
-    if (p < L.PS) { mreg[i] = gM[p]; vreg[i] = gV[p]; }      // padding entries are 0 and stay 0 (zero gradient)
+  for (int i = 0; i < NPP; ++i) {
+    const int p = 2 * (t + i * NT);
+    mreg[i] = make_float2(0.f, 0.f); vreg[i] = make_float2(0.f, 0.f);
+    if (p < L.PS) { mreg[i] = *reinterpret_cast<const float2*>(gM + p); vreg[i] = *reinterpret_cast<const float2*>(gV + p); }   // padding entries are 0 and stay 0 (zero gradient)
   }
   for (int p4 = t; p4 < (L.PS >> 2); p4 += NT) {
     const float4 w = reinterpret_cast<const float4*>(gW)[p4], wt = reinterpret_cast<const float4*>(gWt)[p4];
@@ -598,27 +600,42 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
       const float c1 = Red[8 + 2 * (kstep & 1)], c2 = Red[9 + 2 * (kstep & 1)];
       const float rc1 = 1.0f / c1, rc2 = 1.0f / c2;
       const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
-      // branch-free body (indices clamped, stores guarded) so that the seven sqrt / reciprocal chains of a thread overlap
-      float gv[NPT], th[NPT];
-      const int nW1 = (D + 1) * kH1;
+      // two adjacent packed entries per pass (8-byte loads / stores, one index and one guard for both), branch-free (indices
+      // clamped, stores guarded) so that the sqrt / reciprocal chains of a thread overlap
+      float2 gv[NPP], th[NPP];
+      const int nW1 = (D + 1) * kH1;                 // even, <= 544: only pair 0 can hold layer-1 parameters
 #pragma unroll
-      for (int i = 0; i < NPT; ++i) {
-        const int p = t + i * NT, pc = p < L.PS ? p : L.PS - 1;
-        gv[i] = G[pc]; th[i] = W[pc];
-        if (i == 0 && t < nW1) gv[0] += ((DW1P[t] + DW1P[17 * kH1 + t]) + DW1P[2 * 17 * kH1 + t]) + DW1P[3 * 17 * kH1 + t];   // nW1 <= 544: i = 0 and, below, i = 1
-        if (i == 1 && p < nW1) gv[1] += ((DW1P[p] + DW1P[17 * kH1 + p]) + DW1P[2 * 17 * kH1 + p]) + DW1P[3 * 17 * kH1 + p];
+      for (int i = 0; i < NPP; ++i) {
+        if (i == NPP - 1 && !pair4) break;
+        const int p = 2 * (t + i * NT), pc = p < L.PS ? p : L.PS - 2;
+        gv[i] = *reinterpret_cast<const float2*>(G + pc); th[i] = *reinterpret_cast<const float2*>(W + pc);
+        if (i == 0 && p < nW1) {
+          const float2 q0 = *reinterpret_cast<const float2*>(DW1P + p), q1 = *reinterpret_cast<const float2*>(DW1P + 17 * kH1 + p),
+                       q2 = *reinterpret_cast<const float2*>(DW1P + 2 * 17 * kH1 + p), q3 = *reinterpret_cast<const float2*>(DW1P + 3 * 17 * kH1 + p);
+          gv[0].x += ((q0.x + q1.x) + q2.x) + q3.x; gv[0].y += ((q0.y + q1.y) + q2.y) + q3.y;
+        }
       }
 #pragma unroll
-      for (int i = 0; i < NPT; ++i) {
-        const int p = t + i * NT;
-        const float g = p < L.PS ? gv[i] : 0.f;
-        const float m = b1 * mreg[i] + omb1 * g;
-        const float v = b2 * vreg[i] + omb2 * (g * g);
-        mreg[i] = m; vreg[i] = v;
-        const float u = (m * rc1) * fast_rcp(fast_sqrt(v * rc2 + eps_root) + eps);
-        if (p < L.PS) {
-          G[p] = 0.f;
-          W[p] = th[i] - lr * (u + wd * th[i]);  // add_decayed_weights (wd = 0 for adam); scale(-lr); apply_updates
+      for (int i = 0; i < NPP; ++i) {
+        if (i == NPP - 1 && !pair4) break;
+        const int p = 2 * (t + i * NT);
+        const bool live = p < L.PS;
+        float gg[2] = {live ? gv[i].x : 0.f, live ? gv[i].y : 0.f};
+        const float tt[2] = {th[i].x, th[i].y};
+        float mm[2] = {mreg[i].x, mreg[i].y}, vv[2] = {vreg[i].x, vreg[i].y}, ww[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float g = gg[e];
+          const float m = b1 * mm[e] + omb1 * g;
+          const float v = b2 * vv[e] + omb2 * (g * g);
+          mm[e] = m; vv[e] = v;
+          const float u = (m * rc1) * fast_rcp(fast_sqrt(v * rc2 + eps_root) + eps);
+          ww[e] = tt[e] - lr * (u + wd * tt[e]);  // add_decayed_weights (wd = 0 for adam); scale(-lr); apply_updates
+        }
+        mreg[i] = make_float2(mm[0], mm[1]); vreg[i] = make_float2(vv[0], vv[1]);
+        if (live) {
+          *reinterpret_cast<float2*>(G + p) = make_float2(0.f, 0.f);
+          *reinterpret_cast<float2*>(W + p) = make_float2(ww[0], ww[1]);
         }
       }
     }
@@ -635,9 +652,12 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
   __syncthreads();
   // ---- write back theta, mu, nu (theta^- is unchanged) --------------------------------------
 #pragma unroll
-  for (int i = 0; i < NPT; ++i) {
-    const int p = t + i * NT;
-    if (p < L.PS) { gW[p] = W[p]; gM[p] = mreg[i]; gV[p] = vreg[i]; }
+  for (int i = 0; i < NPP; ++i) {
+    const int p = 2 * (t + i * NT);
+    if (p < L.PS) {
+      *reinterpret_cast<float2*>(gW + p) = *reinterpret_cast<const float2*>(W + p);
+      *reinterpret_cast<float2*>(gM + p) = mreg[i]; *reinterpret_cast<float2*>(gV + p) = vreg[i];
+    }
   }
   if (t == 0) {
     ctl->train_steps = step0 + args.K;
