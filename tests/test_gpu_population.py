@@ -61,6 +61,24 @@ def test_sharded_population_is_bitwise_identical():
             assert np.array_equal(s.params_flat(i), full.params_flat(s.global_id(i)))
 
 
+def test_launch_order_changes_nothing():
+    """More agents than SMs: the tensor-core population kernel starts the costly agents (batch > 64) first (api.cu,
+    train_common).  Agents are independent, so one launch of all 200 must equal -- bit for bit -- the same agents trained in
+    four launches of 50 (<= SM count: launched in index order)."""
+    n, D, N = 200, 8, 300
+    one = dqn_b200.Population(n, D, 4, N, dqn_b200.adam(1e-3), seed=5)
+    four = dqn_b200.Population(n, D, 4, N, dqn_b200.adam(1e-3), seed=5)
+    fill(one, 200, D)
+    fill(four, 200, D)
+    sizes = {hp["batch_size"] for hp in one.hparams}
+    assert min(sizes) <= 64 < max(sizes)                      # both bodies of the kernel in the one launch
+    one.train_steps(3)
+    for b in range(0, n, 50):
+        four.engine.train_steps(3, agent_begin=b, agent_end=b + 50)
+    for i in range(n):
+        assert np.array_equal(one.params_flat(i), four.params_flat(i)), f"agent {i} (batch {one.hparams[i]['batch_size']})"
+
+
 @pytest.mark.timeout(600)
 def test_baseline_population_spot_check():
     """BASELINE configs[2] at full size: 1024 sweep agents x 40 000-slot rings (3.9 GB) in ONE launch; 16 agents spread over

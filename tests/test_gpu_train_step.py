@@ -86,6 +86,7 @@ def test_lunar_lander_config_from_reference_checkpoint(golden):
 @pytest.mark.parametrize("D,A,B,kind,gamma", [
     (8, 4, 64, "adam", 0.9028), (9, 4, 38, "adam", 0.0), (9, 4, 70, "adamw", 0.999), (8, 4, 1, "adam", 0.95),
     (8, 4, 128, "adamw", 0.99), (16, 2, 33, "adam", 0.9), (1, 7, 65, "adamw", 0.5), (4, 3, 200, "adam", 0.99),
+    (16, 5, 80, "adam", 0.97), (16, 2, 72, "adamw", 0.9), (8, 4, 81, "adam", 0.99),     # 65..80: one tile with tail rows; 81: two tiles
 ])
 def test_shapes_batches_optimisers(D, A, B, kind, gamma):
     eng, ora, rng = make_pair(D=D, A=A, B=B, kind=kind, lr=1e-3, gamma=gamma, seed=D * 7 + B)
