@@ -76,7 +76,7 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
   L.oMeta = o; o += BT * 4;
   L.oDummy = o; o += 4;
   L.oRed = o; o += 32 + 4 * kH2;      // [0..1] loss, [8..11] Adam bias corrections, [16..31] head-bias partials, [32..] db2 partials [quarter][j]
-  L.oBar = o; o += 8;                 // [0,1] mbarrier of the record gather, [2,3] mbarrier of the MMAs, [4] TMEM base address
+  L.oBar = o; o += 8;                 // [0,1] mbarrier of the record gather, [2,3] mbarrier of the MMAs, [4] TMEM base address, [6,7] mbarrier of P1
   L.oStage = o; o += BT * recw;
   L.oB2 = o; o += 2 * kB2Bytes / 4;   // hi | lo
   L.oBt2 = o; o += 2 * kB2Bytes / 4;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
   const int row2 = 32 * wq + lane;                  // forward row of batch A: < 64 = s row, else s' row (row2 - 64); backward: r | 64 + j
   const uint32_t tlane = (uint32_t)(32 * wq) << 16;
   const uint32_t sB2 = smem_addr(sm + L.oB2), sBt2 = smem_addr(sm + L.oBt2), sB4 = smem_addr(sm + L.oB4);
-  const uint32_t bar = smem_addr(sm + L.oBar), mbar = smem_addr(sm + L.oBar + 2);
+  const uint32_t bar = smem_addr(sm + L.oBar), mbar = smem_addr(sm + L.oBar + 2), mbar1 = smem_addr(sm + L.oBar + 6);
 
   float* const gW = args.params + (size_t)agent * 4 * PK;
   float* const gWt = gW + PK;
@@ -168,8 +168,8 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
     udst[q] = o;
   }
 
-  uint32_t bar_parity = 0, mma_parity = 0;
-  if (t == 0) { mbar_init(bar, 1); mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  uint32_t bar_parity = 0, mma_parity = 0, p1_parity = 0;
+  if (t == 0) { mbar_init(bar, 1); mbar_init(mbar, 1); mbar_init(mbar1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) {          // all 512 columns of the SM's tensor memory (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(sm + L.oBar + 4)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -318,8 +318,9 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
       if (t == 0) {   // ---- forward products: h2 pre-activations of all 192 forward rows ----
         tc_fence_after();
         umma_3x<kH1 / 8>(tmem + kD2, tmem + kA2Hi, tmem + kA2Lo, sB2, sB2 + kB2Bytes, kLbo2, kSbo2, make_idesc(kH2));
+        umma_commit(mbar);        // P2 alone: its epilogue pass runs while the tensor core is still on P1
         umma_3x<kH1 / 8>(tmem + kD1, tmem + kA1Hi, tmem + kA1Lo, sBt2, sBt2 + kB2Bytes, kLbo2, kSbo2, make_idesc(kH2));
-        umma_commit(mbar);
+        umma_commit(mbar1);
       }
       // the staging buffer is free (unpacked two barriers ago): gather the next tile / step while the tensor core works
       if (tile + 1 < ntiles) prefetch(kstep, tile + 1);
@@ -328,9 +329,8 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
       tc_fence_after();
       {  // ---- epilogue: + b2, relu; the head's partial sums over this thread's 16 units straight from the registers ----
         constexpr int NP = (A + 2) / 2;
-        uint32_t r0[16], r1[16];
+        uint32_t r0[16];
         tmem_ld16(tmem + tlane + kD2 + 16u * wc, r0);
-        if (wq >= 2) tmem_ld16(tmem + tlane + kD1 + 16u * wc, r1);
         tmem_wait_ld();
         const float* bias = W + L.pW2 + kH1 * WS2 + 16 * wc;
         const float* wh = W + L.pWh + 16 * wc * HC;
@@ -365,7 +365,12 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
             if (2 * q + 1 <= A) dst[(2 * q + 1) * BT] = b;
           }
         }
-        if (wq >= 2) {   // h2(theta^-, s') of the same batch row
+        if (wq >= 2) {   // h2(theta^-, s') of the same batch row (the barrier below keeps the other warps behind P1 as well)
+          mbar_wait(mbar1, p1_parity);
+          tc_fence_after();
+          uint32_t r1[16];
+          tmem_ld16(tmem + tlane + kD1 + 16u * wc, r1);
+          tmem_wait_ld();
           const float* biast = Wt + L.pW2 + kH1 * WS2 + 16 * wc;
           const float* wht = Wt + L.pWh + 16 * wc * HC;
 #pragma unroll
@@ -394,6 +399,7 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
             if (2 * q + 1 <= A) dst[(2 * q + 1) * BT] = b;
           }
         }
+        p1_parity ^= 1u;
         tc_fence_before();
       }
       __syncthreads();

@@ -86,7 +86,7 @@ __host__ __device__ inline Lay make_layout(int D, int recw) {
   L.oMeta = o; o += NR * 4;
   L.oDummy = o; o += 4;
   L.oRed = o; o += kRedDb2 + 4 * kH2; // [0..1] loss, [8..11] Adam bias corrections, [32..111] per-row loss, then db2 partials [quarter][j]
-  L.oBar = o; o += 8;                 // [0,1] mbarrier of the record gather, [2,3] mbarrier of the MMAs, [4] TMEM base address
+  L.oBar = o; o += 8;                 // [0,1] mbarrier of the record gather, [2,3] mbarrier of the MMAs, [4] TMEM base address, [6,7] mbarrier of P1
   L.oStage = o; o += NR * recw;
   L.oBt2 = o; o += kB2Bytes / 4;      // hi: W2^- | W2, lo: W2^- | W2
   L.oB2 = o; o += 3 * kB2Bytes / 4;
@@ -128,7 +128,7 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
   const int row2 = 32 * wq + lane;                  // forward row of batch A: < 64 = s row, else s' row (row2 - 64); backward: r | 64 + j
   const uint32_t tlane = (uint32_t)(32 * wq) << 16;
   const uint32_t sBt2 = smem_addr(sm + L.oBt2), sB2 = smem_addr(sm + L.oB2), sB4 = smem_addr(sm + L.oB4);
-  const uint32_t bar = smem_addr(sm + L.oBar), mbar = smem_addr(sm + L.oBar + 2);
+  const uint32_t bar = smem_addr(sm + L.oBar), mbar = smem_addr(sm + L.oBar + 2), mbar1 = smem_addr(sm + L.oBar + 6);
 
   float* const gW = args.params + (size_t)agent * 4 * PK;
   float* const gWt = gW + PK;
@@ -191,8 +191,8 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
     udst[q] = o;
   }
 
-  uint32_t bar_parity = 0, mma_parity = 0;
-  if (t == 0) { mbar_init(bar, 1); mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  uint32_t bar_parity = 0, mma_parity = 0, p1_parity = 0;
+  if (t == 0) { mbar_init(bar, 1); mbar_init(mbar, 1); mbar_init(mbar1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) {          // all 512 columns of the SM's tensor memory (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(sm + L.oBar + 4)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -214,8 +214,10 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
   auto prefetch = [&](int kstep, int tile) {
     const int nrows = tail ? B : (B - tile * BT < BT ? B - tile * BT : BT);
     if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * recw * 4));
-    if (t < NR) {       // warps 0..2 (the third one half-way): one row each, rows 64..79 = tail
-      const int row = t;
+    // four lanes of every warp (rows 0..63) + four more of warps 0..3 (tail rows 64..79): all warps reach the MMA wait together
+    const int prow = (t & 7) == 0 ? (t >> 3) : ((t & 7) == 4 && t < 8 * TL ? BT + (t >> 3) : -1);
+    if (prow >= 0) {
+      const int row = prow;
       const int i = tile * BT + row;
       float* dst = Stage + row * recw;
       if (i < B) {
@@ -403,10 +405,11 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
       if (t == 0) {   // ---- forward products: h2 pre-activations of all forward rows ----
         tc_fence_after();
         umma_3x<kH1 / 8>(tmem + kD2, tmem + kA2Hi, tmem + kA2Lo, sB2, sB2 + kBfHalf, kLbo2, kSbo2, make_idesc(kH2));
+        umma_commit(mbar);        // P2 alone: its epilogue pass runs while the tensor core is still on P1
         // P1: B = W2^- (64 columns), or with tail rows [W2^- | W2] (128 columns: the tail's theta rows take the right half)
         if (tail) umma_3x<kH1 / 8>(tmem + kD1, tmem + kA1Hi, tmem + kA1Lo, sBt2, sBt2 + kBfHalf, kLbo2, kSbo2, make_idesc(2 * kH2));
         else umma_3x<kH1 / 8>(tmem + kD1, tmem + kA1Hi, tmem + kA1Lo, sBt2, sBt2 + kBfHalf, kLbo2, kSbo2, make_idesc(kH2));
-        umma_commit(mbar);
+        umma_commit(mbar1);
       }
       // the staging buffer is free (unpacked two barriers ago): gather the next tile / step while the tensor core works
       if (tile + 1 < ntiles) prefetch(kstep, tile + 1);
@@ -460,9 +463,15 @@ __device__ __forceinline__ void step_body(const TrainArgs& args, const int sel) 
         const bool second = wq >= 2 || tail;
         uint32_t ra[16], rb[16];
         tmem_ld16(tmem + tlane + kD2 + 16u * wc, ra);
-        if (second) tmem_ld16(tmem + tlane + kD1 + (wq == 0 ? 64u : 0u) + 16u * wc, rb);
         tmem_wait_ld();
         mask2 = pass(ra, bias, wh, HP + ((wq < 2 ? 0 : 1) * 4 + wc) * HC * NR + (row2 & 63), wq < 2 ? H2 + (16 * wc) * RS1 + row2 : nullptr, true);
+        if (second) {
+          mbar_wait(mbar1, p1_parity);
+          tc_fence_after();
+          tmem_ld16(tmem + tlane + kD1 + (wq == 0 ? 64u : 0u) + 16u * wc, rb);
+          tmem_wait_ld();
+        }
+        p1_parity ^= 1u;
         if (wq >= 2) pass(rb, biast, wht, HP + (2 * 4 + wc) * HC * NR + (row2 & 63), nullptr, true);
         else if (tail && wq == 0)
           pass(rb, bias, wh, HP + ((lane < TL ? 0 : 1) * 4 + wc) * HC * NR + BT + (lane & 15),
