@@ -57,7 +57,7 @@ LbCarve lb_carve(const LbDims& d) {
   take(c.dH2, B * d.H2 * 4); take(c.dH1, B * d.H1 * 4);
   take(c.partial, (B / 256 + 1) * 16 * 4);
   const size_t colw = (size_t)(2 + kMaxA) * d.H2 > (size_t)(d.D + 1) * d.H1 ? (size_t)(2 + kMaxA) * d.H2 : (size_t)(d.D + 1) * d.H1;
-  take(c.colpart, (B / 128) * colw * 4);
+  take(c.colpart, (B / lb_row_chunk((long long)B)) * colw * 4);
   take(c.colred, colw * 4);
   take(c.gemmpart, (size_t)16 * d.H1 * d.H2 * 4);
   take(c.tc, (size_t)d.H1 * d.H2 * 4);          // tcgen05 path: W2^T for the dh1 GEMM

@@ -22,6 +22,10 @@ struct LbTaps {
   int enabled;
 };
 
+// rows per block of the two column-sum passes of the backward (dh2, dW1): 128, or 32 for small local batches -- at 8192 rows
+// (the 8-GPU shard of configs[3]) 128-row chunks are only 256 blocks, too few loads in flight to reach HBM speed
+inline int lb_row_chunk(long long B) { return B <= 16384 ? 32 : 128; }
+
 struct LbWorkspace {
   float *theta, *theta_t, *mu, *nu, *grads;       // flat layout, PF floats each (grads has the loss at [P])
   float *s, *r, *s2; long long* a; uint8_t* done; long long* idx;   // gathered local batch (SoA)
@@ -30,7 +34,7 @@ struct LbWorkspace {
   float *dhd;          // [B][8]
   float *dH2, *dH1;    // [B][H2], [B][H1]
   float *partial;      // [nblk][16]  targets-kernel block partials
-  float *colpart;      // column-sum partials  [B/128][max((2+kMaxA)*H2, (D+1)*H1)]
+  float *colpart;      // column-sum partials  [B / lb_row_chunk(B)][max((2+kMaxA)*H2, (D+1)*H1)]
   float *colred;       // [(2+kMaxA)*H2]
   float *gemmpart;     // split-K partials [16][H1*H2]
   float *tc_scratch;   // tcgen05 path: W2^T [H2][H1] for the dh1 GEMM (so that it runs in the faster NN form)

@@ -388,7 +388,7 @@ lb_targets_kernel(const float* __restrict__ Q, const long long* __restrict__ act
 // fused pass over H2(theta, s):  dH2 = relu'(h2) * (dhd . Wh^T);  partial column sums for dWh and db2.
 // thread = one hidden unit j, block = 256 units x RC rows.   part[chunk][c][j], c: 0..A = dWh cols, A+1 = db2
 // ------------------------------------------------------------------------------------------------
-constexpr int RC = 128;
+template <int RC>
 __global__ void __launch_bounds__(256)
 lb_dh2_kernel(const float* __restrict__ H2s, const float* __restrict__ dhd, const float* __restrict__ theta,
               float* __restrict__ dH2, float* __restrict__ part, int B, int H2n, int A, int offWv) {
@@ -423,7 +423,7 @@ lb_dh2_kernel(const float* __restrict__ H2s, const float* __restrict__ dhd, cons
 // DV = the obs dim padded to 8 or 16 (the padding of x is zero): the inner loop is DV / 4 broadcast 16-byte shared loads and DV
 // FMAs per element of dH1, eight rows of loads in flight -- the pass is a pure HBM read of dH1 (the round-1 form, with a
 // run-time D inside the row loop, spent ~40 instructions per element and ran at 1.8 TB/s).
-template <int DV>
+template <int DV, int RC>
 __global__ void __launch_bounds__(256)
 lb_dw1_kernel(const float* __restrict__ s, const float* __restrict__ dH1, float* __restrict__ part, int B, int D, int H1n) {
   __shared__ __align__(16) float sx[RC][DV];
@@ -589,10 +589,11 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
   lb_finish_kernel<<<1, 32 * (2 + kMaxA), 0, st>>>(ws.partial, nblk, ws.grads, d.P, A, offbv, offba);
   LBCHK(cudaGetLastError());
   // ---- backward ----
-  const int nchunk = B / RC;
+  const int rc = lb_row_chunk(B), nchunk = B / rc;
   {
     dim3 grid(H2n / 256, nchunk);
-    lb_dh2_kernel<<<grid, 256, 0, st>>>(ws.H2, ws.dhd, ws.theta, ws.dH2, ws.colpart, B, H2n, A, offWv);
+    if (rc == 32) lb_dh2_kernel<32><<<grid, 256, 0, st>>>(ws.H2, ws.dhd, ws.theta, ws.dH2, ws.colpart, B, H2n, A, offWv);
+    else lb_dh2_kernel<128><<<grid, 256, 0, st>>>(ws.H2, ws.dhd, ws.theta, ws.dH2, ws.colpart, B, H2n, A, offWv);
     LBCHK(cudaGetLastError());
     const long long n = (long long)(2 + kMaxA) * H2n;
     LBCHK(launch_reduce_partials(st, ws.colpart, ws.colred, n, nchunk, n));
@@ -624,8 +625,10 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
   }
   {
     dim3 grid(H1n / 256, nchunk);
-    if (D <= 8) lb_dw1_kernel<8><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
-    else lb_dw1_kernel<16><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
+    if (D <= 8 && rc == 32) lb_dw1_kernel<8, 32><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
+    else if (D <= 8) lb_dw1_kernel<8, 128><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
+    else if (rc == 32) lb_dw1_kernel<16, 32><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
+    else lb_dw1_kernel<16, 128><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
     LBCHK(cudaGetLastError());
     const long long n = (long long)(D + 1) * H1n;                 // [d][k] == flat [W1 | b1]
     LBCHK(launch_reduce_partials(st, ws.colpart, ws.grads, n, nchunk, n));
