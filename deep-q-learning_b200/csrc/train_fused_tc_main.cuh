@@ -1,17 +1,17 @@
-// train_fused_tc_main.cuh -- body of the tensor-core population kernel for batches of <= 64 rows and for tiles of 64 rows (> 80).
-// tensor cores (sm_100a, tcgen05 + tensor memory).  One CTA of 512 threads = one agent, K steps per launch; the same
-// arithmetic as train_fused.cu (General/QLearning/q_agent.py:146-169, q_learning_functions.py:14-64, dddqn.py:24-34),
-// but the four products that hold 80 % of the step's flops run as error-compensated 3xTF32 on tcgen05.mma
-// (kind::tf32, M = 128; a = a_hi + a_lo:  a_hi*b_lo + a_lo*b_hi + a_hi*b_hi, fp32 accumulation in tensor memory),
-// in two round trips per 64-row tile:
+// train_fused_tc_main.cuh -- body of the tensor-core population kernel (train_fused_tc.cu) for batches of <= 64 rows (one tile)
+// and of > 80 rows (tiles of 64 rows).  One CTA of 512 threads = one agent, K steps per launch; the same arithmetic as
+// train_fused.cu (General/QLearning/q_agent.py:146-169, q_learning_functions.py:14-64, dddqn.py:24-34), but the four
+// products that hold 80 % of the step's flops run as error-compensated 3xTF32 on tcgen05.mma (kind::tf32, M = 128;
+// a = a_hi + a_lo:  a_hi*b_lo + a_lo*b_hi + a_hi*b_hi, fp32 accumulation in tensor memory), in two round trips per tile:
 //   forward   P2  h2(theta; s | s') [128 x 64] = h1 [128 x 32] . W2       P1  h2(theta^-; s')   (rows in lanes 64..127)
-//   backward  P4  dh1 [64 r x 32 k] = dh2 [r x 64 j] . W2^T               P3  dW2^T [64 j x 32 k] = dh2^T [j x 64 r] . h1
+//             (P2 and P1 commit on mbarriers of their own: the P2 epilogue pass runs while the tensor core is on P1)
+//   backward  ONE product with B = [W2 | h1]:  dh1 [64 r x 32 k] = dh2 . W2^T  |  dW2^T [64 j x 32 k] = dh2^T . h1
 // "thread = TMEM lane = row": a warp reaches the 32 lanes of its quadrant (warp % 4), the four warps of a quadrant
 // split the columns.  A operands never touch shared memory: layer 1 is computed one batch row per thread and its
 // hi / lo halves go straight into tensor memory (tcgen05.st); dh2 is computed twice -- per row r (lanes 0..63) and
-// per unit j (lanes 64..127) -- so P4 and P3 read ONE A tile whose halves are dh2 and dh2^T.  B operands (W2 in both
-// orientations, h1 of the s rows) sit in shared memory in the K-major no-swizzle canonical layout (8 x 16 B core
-// matrices).  The head is evaluated from the epilogue's registers (h2 never makes a round trip for it); targets,
+// per unit j (lanes 64..127) -- so the backward product reads ONE A tile whose halves are dh2 and dh2^T.  B operands
+// (W2 in both orientations, h1 of the s rows) sit in shared memory in the K-major no-swizzle canonical layout (8 x 16 B
+// core matrices).  The head is evaluated from the epilogue's registers (h2 never makes a round trip for it); targets,
 // dh2, dWh, dW1 and Adam are fp32 on the CUDA cores.  16 warps (128 registers each) instead of the FFMA kernel's 8:
 // every phase is a short dependent chain, so the step is latency-bound and the extra warps are what hides it.
 #pragma once
