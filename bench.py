@@ -14,7 +14,7 @@ max-over-ranks device time.
            persistent launch); reps are repeated -- L2 flushed before each -- until the timed region is >= 50 ms and the
            MEDIAN rep is reported (a 20-step rep is 110 us: one sample of it says nothing).
   e2e      steps/s through the reference-facing API (ReplayBuffer.add x train_frequency from host memory,
-           Agent._step(), loss read back), >= 4000 steps -- host<->device traffic inside the timed region
+           Agent._step(), loss read back), 8000 steps (>= 50 ms) -- host<->device traffic inside the timed region
   roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md "Measurement"
   extras   (default workload) the sharded workloads AT THE SAME N, each a full line of its own (value, clocks, roofline):
            population = configs[2] (1024 sweep agents sharded over the ranks, no collective), dp = configs[3] (global batch
@@ -49,7 +49,7 @@ FLOP_PER_SAMPLE = 25728                  # D=8, H=(32,64): 3 forwards + backward
 STEPS_PER_LAUNCH = int(os.environ.get("DQN_BENCH_KPL", "500"))   # most train steps fused into one persistent launch
 MIN_TIMED_S = 0.05                       # every timed region lasts at least this long (reps of the requested step count)
 MAX_REPS = 2000
-E2E_STEPS = 4000
+E2E_STEPS = 8000
 
 
 def measured_peaks():
