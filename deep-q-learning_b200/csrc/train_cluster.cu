@@ -283,6 +283,20 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     cp_async_commit();
   };
 
+  // staged records -> k-major X / raw meta words; every thread reads back exactly the 16-byte chunks it copied itself
+  auto unpack = [&]() {
+    if (t < 4 * R) {
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int c = ul4 + 4 * cc;
+        if (c < cpr) {
+          const float4 v = ld4(Stage + urow * recw + 4 * c);
+          sm[udst[4 * cc + 0]] = v.x; sm[udst[4 * cc + 1]] = v.y; sm[udst[4 * cc + 2]] = v.z; sm[udst[4 * cc + 3]] = v.w;
+        }
+      }
+    }
+  };
+  bool unpacked = false;                    // K-step launches, one tile: the next step's rows were unpacked under the all-gather
   double pb1 = ctl->pb1, pb2 = ctl->pb2;    // b1**count, b2**count carried across launches (thread 0 uses them)
 
   PHASE_CLOCK(1);
@@ -441,20 +455,14 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
     float loss_acc = 0.f;    // warp 0 only
 
     for (int tile = 0; tile < ntiles; ++tile) {
-      // ---- unpack ----
-      cp_async_wait_all();
-      __syncthreads();
-      if (kstep == 0 && tile == 0) PHASE_CLOCK(3);
-      if (t < 4 * R) {
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-          const int c = ul4 + 4 * cc;
-          if (c < cpr) {
-            const float4 v = ld4(Stage + urow * recw + 4 * c);
-            sm[udst[4 * cc + 0]] = v.x; sm[udst[4 * cc + 1]] = v.y; sm[udst[4 * cc + 2]] = v.z; sm[udst[4 * cc + 3]] = v.w;
-          }
-        }
+      // ---- unpack (already done under the previous step's all-gather when `unpacked`) ----
+      if (!(unpacked && tile == 0)) {
+        cp_async_wait_all();
+        __syncthreads();
+        if (kstep == 0 && tile == 0) PHASE_CLOCK(3);
+        unpack();
       }
+      unpacked = false;
       __syncthreads();
       if (tile + 1 < ntiles) prefetch(kstep, tile + 1);
       else if (!serve && kstep + 1 < args.K) prefetch(kstep + 1, 0);
@@ -541,6 +549,13 @@ __global__ void __launch_bounds__(NT, 1) dqn_train_cluster_kernel(const TrainArg
             for (int c = 1; c < CS; ++c) *CmdWordR[c] = w;
           }
         }
+      }
+      if (!serve && ntiles == 1 && kstep + 1 < args.K) {
+        // the next step's rows (gathered since the top of this step) go to X / Meta while the weight slices travel: X is free
+        // since the barrier after the backward, and a thread unpacks only chunks of its own copies (no barrier needed before)
+        cp_async_wait_all();
+        unpack();
+        unpacked = true;
       }
       mbar_wait(bar_w, par_w);
       par_w ^= 1u;
