@@ -26,6 +26,7 @@ __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.
 // ------------------------------------------------------------------------------------------------
 // layer 1: H1[row][:] = relu(x[row] . W1 + b1).  rows [0,B): (theta, s); [B,2B): (theta, s'); [2B,3B): (theta^-, s')
 // ------------------------------------------------------------------------------------------------
+template <int DT>   // DT = 8: the observation width as a constant (two 16-byte loads per row); 0: run-time D
 __global__ void __launch_bounds__(256)
 lb_layer1_kernel(const float* __restrict__ s, const float* __restrict__ s2, const float* __restrict__ theta,
                  const float* __restrict__ theta_t, float* __restrict__ H1, int B, int D, int H1n) {
@@ -52,12 +53,32 @@ lb_layer1_kernel(const float* __restrict__ s, const float* __restrict__ s2, cons
     float4 acc[RP];
 #pragma unroll
     for (int i = 0; i < RP; ++i) acc[i] = bias;
-    for (int d = 0; d < D; ++d) {
-      const float4 w = reinterpret_cast<const float4*>(w1s)[d * 256 + j4];
+    if constexpr (DT == 8) {
+      float xr[RP][8];
 #pragma unroll
       for (int i = 0; i < RP; ++i) {
-        const float xv = r0 + i < B ? __ldg(x + (size_t)(r0 + i) * D + d) : 0.f;
-        acc[i].x = fmaf(xv, w.x, acc[i].x); acc[i].y = fmaf(xv, w.y, acc[i].y); acc[i].z = fmaf(xv, w.z, acc[i].z); acc[i].w = fmaf(xv, w.w, acc[i].w);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 x0 = r0 + i < B ? __ldg(reinterpret_cast<const float4*>(x + (size_t)(r0 + i) * 8)) : z;
+        const float4 x1 = r0 + i < B ? __ldg(reinterpret_cast<const float4*>(x + (size_t)(r0 + i) * 8 + 4)) : z;
+        xr[i][0] = x0.x; xr[i][1] = x0.y; xr[i][2] = x0.z; xr[i][3] = x0.w; xr[i][4] = x1.x; xr[i][5] = x1.y; xr[i][6] = x1.z; xr[i][7] = x1.w;
+      }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const float4 w = reinterpret_cast<const float4*>(w1s)[d * 256 + j4];
+#pragma unroll
+        for (int i = 0; i < RP; ++i) {
+          const float xv = xr[i][d];
+          acc[i].x = fmaf(xv, w.x, acc[i].x); acc[i].y = fmaf(xv, w.y, acc[i].y); acc[i].z = fmaf(xv, w.z, acc[i].z); acc[i].w = fmaf(xv, w.w, acc[i].w);
+        }
+      }
+    } else {
+      for (int d = 0; d < D; ++d) {
+        const float4 w = reinterpret_cast<const float4*>(w1s)[d * 256 + j4];
+#pragma unroll
+        for (int i = 0; i < RP; ++i) {
+          const float xv = r0 + i < B ? __ldg(x + (size_t)(r0 + i) * D + d) : 0.f;
+          acc[i].x = fmaf(xv, w.x, acc[i].x); acc[i].y = fmaf(xv, w.y, acc[i].y); acc[i].z = fmaf(xv, w.z, acc[i].z); acc[i].w = fmaf(xv, w.w, acc[i].w);
+        }
       }
     }
 #pragma unroll
@@ -548,10 +569,12 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     const int smem = (D + 1) * 1024 * 4;                       // <= 68 KB
     static bool configured = false;
     if (!configured) {
-      LBCHK(cudaFuncSetAttribute(lb_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kMaxD + 1) * 1024 * 4));
+      LBCHK(cudaFuncSetAttribute(lb_layer1_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kMaxD + 1) * 1024 * 4));
+      LBCHK(cudaFuncSetAttribute(lb_layer1_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kMaxD + 1) * 1024 * 4));
       configured = true;
     }
-    lb_layer1_kernel<<<grid, 256, smem, st>>>(ws.s, ws.s2, ws.theta, ws.theta_t, ws.H1, B, D, H1n);
+    if (D == 8) lb_layer1_kernel<8><<<grid, 256, smem, st>>>(ws.s, ws.s2, ws.theta, ws.theta_t, ws.H1, B, D, H1n);
+    else lb_layer1_kernel<0><<<grid, 256, smem, st>>>(ws.s, ws.s2, ws.theta, ws.theta_t, ws.H1, B, D, H1n);
     LBCHK(cudaGetLastError());
   }
   bool head_done = false;
