@@ -447,36 +447,42 @@ lb_dh2_kernel(const float* __restrict__ H2s, const float* __restrict__ dhd, cons
 template <int DV, int RC>
 __global__ void __launch_bounds__(256)
 lb_dw1_kernel(const float* __restrict__ s, const float* __restrict__ dH1, float* __restrict__ part, int B, int D, int H1n) {
+  // thread = FOUR adjacent hidden units (16-byte loads of dH1: a quarter of the load instructions of the one-column form)
   __shared__ __align__(16) float sx[RC][DV];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int r0 = blockIdx.y * RC;
   for (int q = threadIdx.x; q < RC * DV; q += blockDim.x) {
     const int r = q / DV, d = q - r * DV;
     sx[r][d] = d < D ? s[(size_t)(r0 + r) * D + d] : 0.f;
   }
   __syncthreads();
-  float acc[DV + 1];
+  if (k >= H1n) return;
+  float4 acc[DV + 1];
 #pragma unroll
-  for (int d = 0; d <= DV; ++d) acc[d] = 0.f;
+  for (int d = 0; d <= DV; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* g0 = dH1 + (size_t)r0 * H1n + k;
   for (int r = 0; r < RC; r += 8) {
-    float g[8];
+    float4 g[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = g0[(size_t)(r + i) * H1n];
+    for (int i = 0; i < 8; ++i) g[i] = *reinterpret_cast<const float4*>(g0 + (size_t)(r + i) * H1n);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
       for (int q = 0; q < DV / 4; ++q) {
         const float4 x = *reinterpret_cast<const float4*>(&sx[r + i][4 * q]);
-        acc[4 * q] = fmaf(x.x, g[i], acc[4 * q]); acc[4 * q + 1] = fmaf(x.y, g[i], acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(x.z, g[i], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x.w, g[i], acc[4 * q + 3]);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float4& a = acc[4 * q + e];
+          a.x = fmaf(xs[e], g[i].x, a.x); a.y = fmaf(xs[e], g[i].y, a.y); a.z = fmaf(xs[e], g[i].z, a.z); a.w = fmaf(xs[e], g[i].w, a.w);
+        }
       }
-      acc[DV] += g[i];
+      acc[DV].x += g[i].x; acc[DV].y += g[i].y; acc[DV].z += g[i].z; acc[DV].w += g[i].w;
     }
   }
 #pragma unroll
-  for (int d = 0; d < DV; ++d) if (d < D) part[((size_t)blockIdx.y * (D + 1) + d) * H1n + k] = acc[d];
-  part[((size_t)blockIdx.y * (D + 1) + D) * H1n + k] = acc[DV];
+  for (int d = 0; d < DV; ++d) if (d < D) *reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * (D + 1) + d) * H1n + k) = acc[d];
+  *reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * (D + 1) + D) * H1n + k) = acc[DV];
 }
 
 // scatter the reduced head partials [c][j] into the flat gradient: c = 0 -> dWv[j], 1..A -> dWa[j][c-1], A+1 (index 1+kMaxA) -> db2[j]
@@ -647,7 +653,7 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
     LBCHK(lb_gemm(st, gemm_mode, kGemmNT_ReluMask, B, H1n, H2n, ws.dH2, H2n, ws.theta + offW2, H2n, ws.dH1, H1n, ws.H1, H1n, 1, ws));
   }
   {
-    dim3 grid(H1n / 256, nchunk);
+    dim3 grid((H1n + 1023) / 1024, nchunk);
     if (D <= 8 && rc == 32) lb_dw1_kernel<8, 32><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
     else if (D <= 8) lb_dw1_kernel<8, 128><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
     else if (rc == 32) lb_dw1_kernel<16, 32><<<grid, 256, 0, st>>>(ws.s, ws.dH1, ws.colpart, B, D, H1n);
