@@ -413,31 +413,40 @@ template <int RC>
 __global__ void __launch_bounds__(256)
 lb_dh2_kernel(const float* __restrict__ H2s, const float* __restrict__ dhd, const float* __restrict__ theta,
               float* __restrict__ dH2, float* __restrict__ part, int B, int H2n, int A, int offWv) {
-  __shared__ float sd[RC][8];
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  // thread = FOUR adjacent hidden units (16-byte loads of h2, 16-byte stores of dh2)
+  __shared__ __align__(16) float sd[RC][8];
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int r0 = blockIdx.y * RC;
   for (int q = threadIdx.x; q < RC * 8; q += blockDim.x) sd[q >> 3][q & 7] = dhd[(size_t)r0 * 8 + q];
   __syncthreads();
+  if (j >= H2n) return;
   const float* Wv = theta + offWv;
   const float* Wa = Wv + H2n + 1;
-  float wh[1 + kMaxA], acc[2 + kMaxA];
-  wh[0] = Wv[j];
+  float4 wh[1 + kMaxA], acc[2 + kMaxA];
+  wh[0] = *reinterpret_cast<const float4*>(Wv + j);
 #pragma unroll
-  for (int c = 0; c < kMaxA; ++c) wh[1 + c] = c < A ? Wa[(size_t)j * A + c] : 0.f;
+  for (int c = 0; c < kMaxA; ++c)
+    wh[1 + c] = c < A ? make_float4(Wa[(size_t)j * A + c], Wa[(size_t)(j + 1) * A + c], Wa[(size_t)(j + 2) * A + c], Wa[(size_t)(j + 3) * A + c])
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < 2 + kMaxA; ++c) acc[c] = 0.f;
+  for (int c = 0; c < 2 + kMaxA; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int r = 0; r < RC; ++r) {
-    const float h = H2s[(size_t)(r0 + r) * H2n + j];
-    float v = 0.f;
+    const float4 h = *reinterpret_cast<const float4*>(H2s + (size_t)(r0 + r) * H2n + j);
+    const float4 d0 = *reinterpret_cast<const float4*>(&sd[r][0]), d1 = *reinterpret_cast<const float4*>(&sd[r][4]);
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c <= kMaxA; ++c) { const float dd = sd[r][c]; v = fmaf(dd, wh[c], v); acc[c] = fmaf(h, dd, acc[c]); }
-    v = h > 0.f ? v : 0.f;
-    dH2[(size_t)(r0 + r) * H2n + j] = v;
-    acc[1 + kMaxA] += v;
+    for (int c = 0; c <= kMaxA; ++c) {
+      v.x = fmaf(dd[c], wh[c].x, v.x); v.y = fmaf(dd[c], wh[c].y, v.y); v.z = fmaf(dd[c], wh[c].z, v.z); v.w = fmaf(dd[c], wh[c].w, v.w);
+      acc[c].x = fmaf(h.x, dd[c], acc[c].x); acc[c].y = fmaf(h.y, dd[c], acc[c].y); acc[c].z = fmaf(h.z, dd[c], acc[c].z); acc[c].w = fmaf(h.w, dd[c], acc[c].w);
+    }
+    v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+    *reinterpret_cast<float4*>(dH2 + (size_t)(r0 + r) * H2n + j) = v;
+    acc[1 + kMaxA].x += v.x; acc[1 + kMaxA].y += v.y; acc[1 + kMaxA].z += v.z; acc[1 + kMaxA].w += v.w;
   }
 #pragma unroll
-  for (int c = 0; c < 2 + kMaxA; ++c) part[((size_t)blockIdx.y * (2 + kMaxA) + c) * H2n + j] = acc[c];
+  for (int c = 0; c < 2 + kMaxA; ++c) *reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * (2 + kMaxA) + c) * H2n + j) = acc[c];
 }
 
 // fused pass over dH1: partial sums for dW1[d][k] = sum_r x[r][d] dH1[r][k] and db1[k].  part[chunk][d][k], d = D -> db1.
@@ -620,7 +629,7 @@ cudaError_t lb_forward_backward(cudaStream_t st, const LbDims& d, const LbWorksp
   // ---- backward ----
   const int rc = lb_row_chunk(B), nchunk = B / rc;
   {
-    dim3 grid(H2n / 256, nchunk);
+    dim3 grid((H2n + 1023) / 1024, nchunk);
     if (rc == 32) lb_dh2_kernel<32><<<grid, 256, 0, st>>>(ws.H2, ws.dhd, ws.theta, ws.dH2, ws.colpart, B, H2n, A, offWv);
     else lb_dh2_kernel<128><<<grid, 256, 0, st>>>(ws.H2, ws.dhd, ws.theta, ws.dH2, ws.colpart, B, H2n, A, offWv);
     LBCHK(cudaGetLastError());
